@@ -1,0 +1,155 @@
+/* agbnp_b200.h -- C-ABI of libagbnp_b200.so: the B200-native (sm_100a) AGBNP1 / GaussVol energy+force path.
+ *
+ * This is the drop-in boundary for ONE path of Gallicchio-Lab/openmm_agbnp_plugin: what the reference does inside
+ *     CalcAGBNPForceKernel::initialize / execute / copyParametersToContext
+ *         (openmmapi/include/AGBNPKernels.h:19-47; Reference platform: platforms/reference/src/ReferenceAGBNPKernels.cpp:58-149,
+ *          1796-1815; OpenCL platform being replaced: platforms/opencl/src/OpenCLAGBNPKernels.cpp:393-556,5439-5468).
+ * A platforms/cuda kernel object (see INTEGRATION.md and openmm_agbnp_plugin_b200/platforms/cuda/) holds one handle per
+ * OpenMM Context and forwards those three calls here.  Plain C types only: no torch, no OpenMM, no C++ in the signatures.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative agbnp_b200_status on failure; nothing throws across the ABI;
+ *     the message is available from agbnp_b200_last_error(handle) (or (NULL) for create failures).
+ *   - units are OpenMM's: nm, kJ/mol, elementary charge (reference README.md:97-103).
+ *   - a handle is bound to one CUDA device and one stream at a time and is not re-entrant; distinct handles are
+ *     independent (replica mode: one handle per GPU).
+ *   - there is no CPU fallback: if no CUDA device is usable, create fails with AGBNP_B200_ERR_CUDA.
+ */
+#ifndef AGBNP_B200_H_
+#define AGBNP_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agbnp_b200 agbnp_b200;
+
+typedef enum {
+    AGBNP_B200_OK = 0,
+    AGBNP_B200_ERR_ARG = -1,          /* bad argument (incl. illegal version, CutoffPeriodic, multiple gamma values) */
+    AGBNP_B200_ERR_CUDA = -2,         /* CUDA runtime failure / no device */
+    AGBNP_B200_ERR_CAPACITY = -3,     /* internal capacity could not be grown */
+    AGBNP_B200_ERR_PARAM_CHANGE = -4  /* copyParametersToContext rules violated (N, radius, heavy<->hydrogen) */
+} agbnp_b200_status;
+
+/* AGBNPForce::NonbondedMethod (openmmapi/include/AGBNPForce.h:44-59) */
+#define AGBNP_B200_NOCUTOFF 0
+#define AGBNP_B200_CUTOFF_NONPERIODIC 1
+#define AGBNP_B200_CUTOFF_PERIODIC 2 /* accepted by the reference API, implemented nowhere: rejected here */
+
+typedef struct {
+    int version;           /* AGBNPForce::setVersion: 0 = GVolSA, 1 = AGBNP1 (default); 2 (AGBNP2) is out of scope -> ERR_ARG */
+    int nonbonded_method;  /* AGBNP_B200_NOCUTOFF | AGBNP_B200_CUTOFF_NONPERIODIC */
+    double cutoff;         /* nm; ignored for NoCutoff (AGBNPForce default 1.0, AGBNPForce.cpp:15) */
+    int device;            /* CUDA device ordinal */
+    /* atom-block tile sharding of the three pair passes across GPUs: this handle evaluates the tile rows
+     * of shard `shard_rank` of `shard_count`; the GaussVol tree is replicated.  1 GPU: rank 0 of 1. */
+    int shard_rank;
+    int shard_count;
+    int reorder_interval;  /* evaluations between spatial re-sorts of the internal atom order; <= 0: library default */
+} agbnp_b200_config;
+
+/* fill with the reference defaults: version 1, NoCutoff, cutoff 1.0 nm, device 0, shard 0 of 1 */
+void agbnp_b200_default_config(agbnp_b200_config* cfg);
+
+/* == CalcAGBNPForceKernel::initialize.  Per-particle arrays are what AGBNPForce::addParticle(radius, gamma, vdw_alpha,
+ * charge, ishydrogen) collected (AGBNPForce.h:75).  Hydrogens get gamma 0 and volume 0; all heavy-atom gammas must be
+ * equal, otherwise ERR_ARG with the reference's message "initialize(): AGBNP does not support multiple gamma values."
+ * (ReferenceAGBNPKernels.cpp:110-116). */
+int agbnp_b200_create(const agbnp_b200_config* cfg, int num_particles, const double* radius, const double* gamma,
+                      const double* vdw_alpha, const double* charge, const unsigned char* ishydrogen,
+                      agbnp_b200** out);
+
+void agbnp_b200_destroy(agbnp_b200* h);
+
+const char* agbnp_b200_last_error(const agbnp_b200* h);
+
+/* == CalcAGBNPForceKernel::copyParametersToContext (ReferenceAGBNPKernels.cpp:1796-1815): gamma, alpha and charge may
+ * change; a different particle count, a radius changed by more than 1e-3 nm or a heavy atom turned hydrogen return
+ * ERR_PARAM_CHANGE with the reference's messages. */
+int agbnp_b200_set_params(agbnp_b200* h, int num_particles, const double* radius, const double* gamma,
+                          const double* vdw_alpha, const double* charge, const unsigned char* ishydrogen);
+
+/* == CalcAGBNPForceKernel::execute, host buffers (the Reference platform's calling convention: positions in, energy
+ * returned, forces ADDED into the caller's array -- ReferenceAGBNPKernels.cpp:27-35,139-149).
+ *   pos      [3*N] doubles, nm (rounded to float on upload: the device path computes in float / selective double)
+ *   forces   [3*N] doubles, kJ/mol/nm, accumulated (+=); may be NULL when include_forces == 0
+ *   energy   receives the potential energy (kJ/mol); may be NULL
+ * The host<->device copies are part of the call (this is what bench.py's `e2e` times). */
+int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces, int include_energy,
+                            double* energy, double* forces);
+
+/* == CalcAGBNPForceKernel::execute, device buffers (the CUDA-platform calling convention).
+ *   d_posq        device float4[padded or N]: x,y,z (nm) and charge slot (ignored; charges come from create/set_params)
+ *   stream        cudaStream_t cast to void* (NULL = default stream); all work is enqueued on it
+ *   d_force       device force sink, or NULL:
+ *                   layout 0: float[3*N] xyz-interleaved, forces are added (+=)
+ *                   layout 1: OpenMM CUDA fixed point: unsigned long long[3*padded_n], component-major
+ *                             (x[0..padded_n), y[..], z[..]), value*2^32, added with 64-bit atomics
+ *   d_energy      device double accumulator to which the energy is added, or NULL
+ *   h_energy      host double receiving the energy (forces a stream synchronize), or NULL
+ * Returns after enqueueing unless h_energy is given. */
+int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, void* d_force, int force_layout,
+                              int padded_n, double* d_energy, double* h_energy);
+
+/* Evaluate the same device-resident positions `repeats` times back to back on the handle's stream and return the mean
+ * device time per evaluation in milliseconds (CUDA events on that stream).  Used by bench.py for `value` (inputs already
+ * resident in HBM) and for the per-kernel breakdown. */
+int agbnp_b200_time_device(agbnp_b200* h, const void* d_posq, int repeats, float* ms_per_eval);
+
+/* per-kernel device times of the last agbnp_b200_time_device / profile run, in ms per evaluation.
+ * names: newline-separated kernel names in launch order (static storage). */
+int agbnp_b200_kernel_times(agbnp_b200* h, int repeats, const void* d_posq, float* ms_out, int max_kernels,
+                            const char** names);
+
+/* diagnostics / by-products of the last evaluation, copied to host (atom order = caller's order).  `what`: */
+typedef enum {
+    AGBNP_B200_GET_SELF_VOLUME_VDW = 0,   /* double[N]  self-volumes, vdW radii (after S3) */
+    AGBNP_B200_GET_SELF_VOLUME_LARGE = 1, /* double[N]  self-volumes, enlarged radii (after S2) */
+    AGBNP_B200_GET_SURFACE_AREA = 2,      /* double[N]  (selfvol_large - selfvol_vdw)/roffset, nm^2 */
+    AGBNP_B200_GET_BORN_RADIUS = 3,       /* double[N]  nm */
+    AGBNP_B200_GET_VOLUME_SCALING = 4,    /* double[N]  s_i */
+    AGBNP_B200_GET_SCALARS = 5,           /* double[8]  vol_energy1, vol_energy2, gb_energy(self+pair), vdw_energy,
+                                                         volume1, volume2, total, n_tree_nodes */
+    AGBNP_B200_GET_TREE_SIZE = 6,         /* long long[1] number of overlap-tree nodes below the atom level */
+    AGBNP_B200_GET_TREE_TOPOLOGY = 7,     /* int[4*M]   per node: root atom, parent (index into this dump, -1 = root
+                                                         atom), last atom, sibling rank; grouped by root atom */
+    AGBNP_B200_GET_DERIV_Y = 8,           /* double[N]  Y_i (GB derivative accumulator) */
+    AGBNP_B200_GET_DERIV_WU = 9,          /* double[N]  (W_i + U_i) before division by the atomic volume */
+    AGBNP_B200_GET_NEIGHBOR_PAIRS = 10,   /* int[2*P]   (i<j) with r2 < cutoff2 as used by the GB pass (cutoff mode) */
+    AGBNP_B200_GET_NEIGHBOR_COUNT = 11,   /* long long[1] P */
+    AGBNP_B200_GET_WORK_COUNTERS = 12     /* double[8]  P_gb, P_q(directed, evaluated), C2, C3+, M, tiles_gb, tiles_q, - */
+} agbnp_b200_get_what;
+
+int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);
+
+/* ---- multi-GPU plumbing: the caller (one process per GPU) runs the phases and does the collectives
+ * between them on the exported device buffers (NCCL via torch.distributed in this repo's host layer).
+ *   phase 0: upload/sort, tree build + sweeps 1-2 (replicated), Born-radius pass for the owned rows
+ *            -> exchange: all-gather  born  (N floats, owned slices)
+ *   phase 1: GB pair pass + vdW for the owned rows, bru/brw
+ *            -> exchange: all-gather  bw    (N floats)
+ *   phase 2: Born-derivative pass for the owned rows (as screened and as screener), tree gamma sweep with nu restricted
+ *            to owned atoms, partial forces
+ *            -> exchange: all-reduce  forces (3N) + energy scalars
+ * With shard_count == 1 execute_* run all phases back to back. */
+int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* stream);
+typedef enum {
+    AGBNP_B200_BUF_BORN = 0,     /* float[n_sorted_padded]  Born radii, internal (sorted) order */
+    AGBNP_B200_BUF_BW = 1,       /* float[n_sorted_padded]  bru+brw */
+    AGBNP_B200_BUF_FORCE = 2,    /* long long[3*n_sorted_padded] fixed-point partial forces */
+    AGBNP_B200_BUF_ENERGY = 3    /* double[8] partial energy scalars */
+} agbnp_b200_buffer;
+int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes, int* own_begin, int* own_end);
+int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int force_layout, int padded_n,
+                            double* d_energy, double* h_energy);
+
+/* library / build identification, e.g. "agbnp_b200 0.1 sm_100a" */
+const char* agbnp_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGBNP_B200_H_ */

@@ -1,0 +1,730 @@
+// libagbnp_b200.so -- C-ABI (include/agbnp_b200.h) and host driver of the sm_100a AGBNP1/GaussVol kernels.
+// One handle = one CalcAGBNPForceKernel instance of the reference (openmmapi/include/AGBNPKernels.h:19-47).
+// There is no CPU fallback anywhere in this file: every evaluation is the kernel sequence below.
+#include "../../include/agbnp_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "agbnp_setup.h"
+#include "agbnp_device.cuh"
+#include "agbnp_tree.cuh"
+#include "agbnp_pair.cuh"
+
+using namespace agbnp_b200_impl;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaFail { std::string msg; };
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    throw CudaFail{std::string(#call) + ": " + cudaGetErrorString(e_)}; } } while (0)
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc((void**) &p, count*sizeof(T)));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void upload(const std::vector<T>& h, cudaStream_t s) {
+        if (h.size() > n) alloc(h.size());
+        if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size()*sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    ~DevBuf() { release(); }
+};
+
+enum KernelId { K_ZERO = 0, K_PREP, K_TREE, K_BORN, K_GB, K_BW, K_DERIV, K_GAMMA, K_FINISH, K_COUNT };
+const char* const kKernelNames = "memset_accum\nk_prep\nk_tree\nk_born\nk_gb\nk_bw\nk_deriv\nk_tree_gamma\nk_finish";
+
+// control words inside the zeroed slab
+enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_COUNT = 8 };
+
+} // namespace
+
+struct agbnp_b200 {
+    agbnp_b200_config cfg;
+    Constants k;
+    SystemParams sp;
+    std::string err;
+    int n = 0, nh = 0, nhy = 0, nhp = 0, np = 0, nhb = 0, nb = 0;
+    int num_sm = 148;
+    cudaStream_t own_stream = nullptr;
+    bool params_dirty = true, order_valid = false;
+    long long evals_since_sort = 0, total_evals = 0;
+    std::vector<int> orig;                  // sorted -> caller (size np, -1 padding)
+
+    // static sorted arrays
+    DevBuf<int> d_orig;
+    DevBuf<float> d_charge, d_radius, d_alpha, d_gamma;
+    DevBuf<double> d_aL, d_vL, d_aS, d_vS;
+    DevBuf<unsigned char> d_rcbin, d_ts;
+    DevBuf<signed char> d_tj;
+    DevBuf<float> d_rc2, d_rc2max;
+    DevBuf<float4> d_i4;
+    DevBuf<int2> d_units;
+    int nunits = 0;
+    // per-evaluation arrays
+    DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in;
+    DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bw, d_wu;
+    DevBuf<unsigned char> d_slab;           // zeroed every evaluation
+    double *d_svS = nullptr, *d_svL = nullptr, *d_scalars = nullptr;
+    unsigned long long *d_force = nullptr, *d_counters = nullptr;
+    float* d_yq = nullptr;
+    int* d_ctrl = nullptr;
+    size_t slab_bytes = 0;
+    DevBuf<double> d_force_out;             // double[3n] for the host path
+    // tree
+    int tree_cap = 768, nbrmax = 128, lwmax = 512;
+    int tree_grid = 0, gamma_grid = 0, gb_grid = 0;
+    DevBuf<unsigned char> d_tree_scratch, d_gamma_scratch;
+    TreeStore st{};
+    DevBuf<int> d_root_off, d_root_cnt, d_st_atom;
+    DevBuf<short> d_root_lvs, d_st_parent, d_st_cstart, d_st_ccount, d_st_rank;
+    DevBuf<float> d_st_f;                   // 7 float arrays
+    // pinned host staging
+    float4* h_posq = nullptr;
+    double* h_force = nullptr;
+    double* h_scal = nullptr;               // SC_COUNT doubles + status
+    int* h_ctrl = nullptr;
+    // diagnostics
+    DevBuf<int2> d_pairs;
+    cudaEvent_t ev[K_COUNT+1] = {};
+    bool have_events = false;
+
+    ~agbnp_b200() {
+        if (h_posq) cudaFreeHost(h_posq);
+        if (h_force) cudaFreeHost(h_force);
+        if (h_scal) cudaFreeHost(h_scal);
+        if (h_ctrl) cudaFreeHost(h_ctrl);
+        if (have_events) for (auto& e : ev) cudaEventDestroy(e);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+};
+
+namespace {
+
+void alloc_store(agbnp_b200* h, int cap) {
+    h->d_st_f.alloc((size_t) 7*cap);
+    h->d_st_atom.alloc(cap);
+    h->d_st_parent.alloc(cap); h->d_st_cstart.alloc(cap); h->d_st_ccount.alloc(cap); h->d_st_rank.alloc(cap);
+    TreeStore& s = h->st;
+    s.cap = cap;
+    s.cs = h->d_st_f.p; s.dvv = s.cs+cap; s.dx = s.dvv+cap; s.dy = s.dx+cap; s.dz = s.dy+cap; s.c2a = s.dz+cap; s.c2b = s.c2a+cap;
+    s.atom = h->d_st_atom.p; s.parent = h->d_st_parent.p; s.cstart = h->d_st_cstart.p; s.ccount = h->d_st_ccount.p;
+    s.rank = h->d_st_rank.p;
+    s.root_off = h->d_root_off.p; s.root_cnt = h->d_root_cnt.p; s.root_lvs = h->d_root_lvs.p;
+}
+
+void alloc_tree_scratch(agbnp_b200* h) {
+    h->d_tree_scratch.alloc((size_t) h->tree_grid*TREE_WARPS*tree_scratch_bytes(h->tree_cap));
+    h->d_gamma_scratch.alloc((size_t) h->gamma_grid*TREE_WARPS*5*h->tree_cap*sizeof(float));
+}
+
+// (re)compute the internal atom order from caller-order positions and upload every order-dependent static array
+void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
+    const SystemParams& sp = h->sp;
+    std::vector<int> hv, hy;
+    morton_order(xyz, stride, sp.ishydrogen, hv, hy);
+    h->nh = (int) hv.size(); h->nhy = (int) hy.size();
+    h->nhp = (h->nh+TILE-1)/TILE*TILE;
+    const int nhyp = (h->nhy+TILE-1)/TILE*TILE;
+    h->np = h->nhp+nhyp;
+    h->nhb = h->nhp/TILE; h->nb = h->np/TILE;
+    h->orig.assign(h->np, -1);
+    for (int i = 0; i < h->nh; i++) h->orig[i] = hv[i];
+    for (int i = 0; i < h->nhy; i++) h->orig[h->nhp+i] = hy[i];
+    h->order_valid = true;
+    h->params_dirty = true;
+    h->evals_since_sort = 0;
+    (void) s;
+}
+
+void upload_static(agbnp_b200* h, cudaStream_t s) {
+    const SystemParams& sp = h->sp;
+    const int np = h->np;
+    std::vector<float> charge(np, 0.f), radius(np, 0.15f), alpha(np, 0.f), gamma(np, 0.f);
+    std::vector<double> aL(np, 1.0), vL(np, 0.0), aS(np, 1.0), vS(np, 0.0);
+    std::vector<unsigned char> rcbin(np, 0), ts(np, 0);
+    std::vector<signed char> tj(np, -1);
+    for (int k = 0; k < np; k++) {
+        const int o = h->orig[k];
+        if (o < 0) continue;
+        charge[k] = (float) sp.charge[o]; radius[k] = (float) sp.radius[o]; alpha[k] = (float) sp.alpha[o];
+        gamma[k] = (float) sp.gamma[o];
+        aL[k] = sp.aL[o]; vL[k] = sp.vL[o]; aS[k] = sp.aS[o]; vS[k] = sp.vS[o];
+        rcbin[k] = (unsigned char) sp.rc_bin[o];
+        ts[k] = (unsigned char) sp.i4.type_screened[o];
+        tj[k] = (signed char) sp.i4.type_screener[o];
+    }
+    h->d_orig.upload(h->orig, s);
+    h->d_charge.upload(charge, s); h->d_radius.upload(radius, s); h->d_alpha.upload(alpha, s); h->d_gamma.upload(gamma, s);
+    h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s);
+    h->d_rcbin.upload(rcbin, s); h->d_ts.upload(ts, s); h->d_tj.upload(tj, s);
+    h->d_rc2.upload(sp.rc2, s); h->d_rc2max.upload(sp.rc2max, s);
+    std::vector<float4> i4(sp.i4.packed.size()/4);
+    for (size_t i = 0; i < i4.size(); i++)
+        i4[i] = make_float4(sp.i4.packed[4*i], sp.i4.packed[4*i+1], sp.i4.packed[4*i+2], sp.i4.packed[4*i+3]);
+    h->d_i4.upload(i4, s);
+    // GB work units: triangular cover of the block-pair matrix in chunks of GB_CHUNK column tiles
+    std::vector<int2> units;
+    for (int ra = 0; ra < h->nb; ra++)
+        for (int c = ra; c < h->nb; c += GB_CHUNK) units.push_back(make_int2(ra, c));
+    h->nunits = (int) units.size();
+    h->d_units.upload(units, s);
+    CK(cudaStreamSynchronize(s));      // the host vectors above go out of scope
+    // per-evaluation arrays
+    if (h->d_posq.n < (size_t) np) {
+        h->d_posq.alloc(np); h->d_bbc.alloc(h->nb); h->d_bbh.alloc(h->nb);
+        h->d_vsf.alloc(np); h->d_born.alloc(np); h->d_bfp.alloc(np); h->d_brw.alloc(np); h->d_bw.alloc(np); h->d_wu.alloc(np);
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o += (bytes+255)/256*256; return r; };
+        const size_t o_svS = take(sizeof(double)*np), o_svL = take(sizeof(double)*np), o_force = take(sizeof(unsigned long long)*3*np);
+        const size_t o_yq = take(sizeof(float)*np), o_scal = take(sizeof(double)*SC_COUNT), o_cnt = take(sizeof(unsigned long long)*CT_COUNT);
+        const size_t o_ctrl = take(sizeof(int)*CW_COUNT);
+        h->slab_bytes = o;
+        h->d_slab.alloc(o);
+        unsigned char* b = h->d_slab.p;
+        h->d_svS = (double*) (b+o_svS); h->d_svL = (double*) (b+o_svL); h->d_force = (unsigned long long*) (b+o_force);
+        h->d_yq = (float*) (b+o_yq); h->d_scalars = (double*) (b+o_scal); h->d_counters = (unsigned long long*) (b+o_cnt);
+        h->d_ctrl = (int*) (b+o_ctrl);
+        h->d_root_off.alloc(h->nhp); h->d_root_cnt.alloc(h->nhp); h->d_root_lvs.alloc((size_t) h->nhp*MAX_LEVELS);
+        CK(cudaMemset(h->d_root_cnt.p, 0, sizeof(int)*h->nhp));
+        if (h->st.cap == 0) alloc_store(h, std::max(4096, 160*h->nh + 4096));
+        else alloc_store(h, h->st.cap);
+    }
+    h->params_dirty = false;
+}
+
+PairCommon pair_common(agbnp_b200* h) {
+    PairCommon c;
+    c.np = h->np; c.nhb = h->nhb; c.nb = h->nb;
+    c.posq = h->d_posq.p; c.orig = h->d_orig.p; c.bbc = h->d_bbc.p; c.bbh = h->d_bbh.p;
+    c.ts = h->d_ts.p; c.tj = h->d_tj.p; c.i4 = h->d_i4.p;
+    c.ntj = h->sp.i4.ntypes_screener;
+    c.ntables = h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener;
+    c.inv_h = (float) (1.0/h->sp.i4.h);
+    c.range2 = (float) (h->k.i4_maxa*h->k.i4_maxa);
+    const float cut = (float) h->cfg.cutoff;
+    c.cut2 = cut*cut;
+    // shard: contiguous ranges of row blocks
+    const int per = (h->nb + h->cfg.shard_count-1)/h->cfg.shard_count;
+    c.row_begin = std::min(h->nb, per*h->cfg.shard_rank);
+    c.row_end = std::min(h->nb, c.row_begin+per);
+    return c;
+}
+
+struct ForceSink { void* ptr; int layout; int padded_n; double* d_energy; };
+
+// enqueue one evaluation.  phase_mask: bit0 = prep+tree+born, bit1 = gb+bw, bit2 = deriv+gamma, bit3 = finish
+void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_mask, const ForceSink* sink, bool timed) {
+    const bool cutoff = h->cfg.nonbonded_method == AGBNP_B200_CUTOFF_NONPERIODIC;
+    const bool v1 = h->cfg.version == 1;
+    auto mark = [&](int id) { if (timed) CK(cudaEventRecord(h->ev[id], s)); };
+    PairCommon pc = pair_common(h);
+    mark(K_ZERO);
+    if (phase_mask & 1) {
+        CK(cudaMemsetAsync(h->d_slab.p, 0, h->slab_bytes, s));
+        mark(K_PREP);
+        PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p};
+        k_prep<<<(h->nb+7)/8, 256, 0, s>>>(pa);
+        mark(K_TREE);
+        TreeArgs ta{};
+        ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
+        ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.rcbin = h->d_rcbin.p;
+        ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;
+        ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
+        ta.volmina = h->k.volmina; ta.volminb = h->k.volminb; ta.min_gvol = h->k.min_gvol;
+        ta.swd = 1.0/(h->k.volminb-h->k.volmina);
+        ta.inv_roffset = (float) (1.0/h->k.roffset);
+        ta.max_order = h->k.max_order;
+        ta.scratch = h->d_tree_scratch.p; ta.scratch_stride = tree_scratch_bytes(h->tree_cap);
+        ta.cap = h->tree_cap; ta.nbrmax = h->nbrmax; ta.lwmax = h->lwmax;
+        ta.svS = h->d_svS; ta.svL = h->d_svL; ta.force = h->d_force; ta.scalars = h->d_scalars; ta.counters = h->d_counters;
+        ta.st = h->st; ta.st.cursor = h->d_ctrl+CW_TREE_CURSOR;
+        ta.work_counter = h->d_ctrl+CW_WORK_TREE; ta.status = h->d_ctrl+CW_STATUS;
+        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax, h->lwmax);
+        k_tree<<<h->tree_grid, TREE_THREADS, smem, s>>>(ta);
+        mark(K_BORN);
+        if (v1) {
+            BornArgs ba{};
+            ba.c = pc; ba.svS = h->d_svS; ba.vS = h->d_vS.p; ba.radius = h->d_radius.p; ba.alpha = h->d_alpha.p;
+            ba.vsf = h->d_vsf.p; ba.born = h->d_born.p; ba.bfp = h->d_bfp.p; ba.brw = h->d_brw.p;
+            ba.scalars = h->d_scalars; ba.counters = h->d_counters;
+            ba.kdiel = (float) h->k.dielectric_factor; ba.hb_radius = (float) h->k.hb_radius;
+            const size_t sm = (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(int)+sizeof(float));
+            const int rows = pc.row_end-pc.row_begin;
+            if (rows > 0) {
+                if (cutoff) k_born<true><<<rows, PAIR_THREADS, sm, s>>>(ba);
+                else k_born<false><<<rows, PAIR_THREADS, sm, s>>>(ba);
+            }
+        }
+    } else { mark(K_PREP); mark(K_TREE); mark(K_BORN); }
+    mark(K_GB);
+    if (v1 && (phase_mask & 2)) {
+        GBArgs ga{};
+        ga.c = pc; ga.born = h->d_born.p; ga.units = h->d_units.p; ga.nunits = h->nunits;
+        ga.shard_rank = h->cfg.shard_rank; ga.shard_count = h->cfg.shard_count;
+        ga.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
+        ga.yq = h->d_yq; ga.force = h->d_force; ga.scalars = h->d_scalars; ga.counters = h->d_counters;
+        ga.work_counter = h->d_ctrl+CW_WORK_GB;
+        if (cutoff) k_gb<true><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
+        else k_gb<false><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
+        mark(K_BW);
+        BwArgs wa{h->np, h->d_posq.p, h->d_yq, h->d_born.p, h->d_bfp.p, h->d_brw.p, (float) h->k.dielectric_factor, h->d_bw.p};
+        k_bw<<<(h->np+255)/256, 256, 0, s>>>(wa);
+    } else mark(K_BW);
+    mark(K_DERIV);
+    if (v1 && (phase_mask & 4)) {
+        DerivArgs da{};
+        da.c = pc; da.vsf = h->d_vsf.p; da.bw = h->d_bw.p; da.wu = h->d_wu.p; da.force = h->d_force; da.counters = h->d_counters;
+        const size_t sm = (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4));
+        const int rows = pc.row_end-pc.row_begin;
+        if (rows > 0) {
+            if (cutoff) k_deriv<true><<<rows, PAIR_THREADS, sm, s>>>(da);
+            else k_deriv<false><<<rows, PAIR_THREADS, sm, s>>>(da);
+        }
+        mark(K_GAMMA);
+        GammaArgs gm{};
+        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.wu = h->d_wu.p; gm.vS = h->d_vS.p;
+        gm.own_begin = pc.row_begin*TILE; gm.own_end = pc.row_end*TILE;
+        gm.force = h->d_force; gm.scratch = h->d_gamma_scratch.p; gm.scratch_stride = (size_t) 5*h->tree_cap*sizeof(float);
+        gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
+        k_tree_gamma<<<h->gamma_grid, TREE_THREADS, 0, s>>>(gm);
+    } else mark(K_GAMMA);
+    mark(K_FINISH);
+    if (phase_mask & 8) {
+        FinishArgs fa{};
+        fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.force = h->d_force; fa.scalars = h->d_scalars;
+        fa.padded_n = sink ? sink->padded_n : 0;
+        if (sink && sink->ptr) {
+            if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;
+            else if (sink->layout == 1) fa.out_fixed = (unsigned long long*) sink->ptr;
+            else fa.out_f64 = (double*) sink->ptr;
+        }
+        fa.energy_accum = sink ? sink->d_energy : nullptr;
+        k_finish<<<(h->np+255)/256, 256, 0, s>>>(fa);
+    }
+    if (timed) CK(cudaEventRecord(h->ev[K_COUNT], s));
+    CK(cudaGetLastError());
+}
+
+// read back status + scalars (synchronises the stream); returns the status bits
+int fetch_status(agbnp_b200* h, cudaStream_t s) {
+    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return h->h_ctrl[CW_STATUS];
+}
+
+// grow whatever overflowed; returns false if a limit was hit
+bool grow(agbnp_b200* h, int status) {
+    if (status & ST_NBR_OVERFLOW) { if (h->nbrmax >= 1024) return false; h->nbrmax *= 2; }
+    if (status & ST_LEVEL_OVERFLOW) { if (h->lwmax >= 8192) return false; h->lwmax *= 2; }
+    if (status & ST_NODE_OVERFLOW) { if (h->tree_cap >= 16384) return false; h->tree_cap *= 2; }
+    if (status & (ST_NBR_OVERFLOW | ST_LEVEL_OVERFLOW)) {
+        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax, h->lwmax);
+        if (smem > 200*1024) return false;
+        CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    }
+    if (status & ST_NODE_OVERFLOW) alloc_tree_scratch(h);
+    if (status & ST_TREE_OVERFLOW) {
+        const int need = h->h_ctrl[CW_TREE_CURSOR];
+        alloc_store(h, std::max(need + need/4 + 4096, h->st.cap*2));
+    }
+    return true;
+}
+
+void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_posq_in, cudaStream_t s) {
+    const int interval = h->cfg.reorder_interval > 0 ? h->cfg.reorder_interval : 500;
+    if (!h->order_valid || h->evals_since_sort >= interval) {
+        std::vector<float> tmp;
+        if (!host_xyz) {
+            tmp.resize((size_t) 4*h->n);
+            CK(cudaMemcpyAsync(tmp.data(), d_posq_in, sizeof(float4)*h->n, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            host_xyz = tmp.data(); stride = 4;
+        }
+        build_order(h, host_xyz, stride, s);
+    }
+    if (h->params_dirty) upload_static(h, s);
+}
+
+int run_checked(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        // forces are only delivered to the caller's sink by a run that did not overflow: run phases first, finish after
+        enqueue(h, d_posq_in, s, 7, nullptr, false);
+        const int status = fetch_status(h, s);
+        if (status == 0) {
+            enqueue(h, d_posq_in, s, 8, sink, false);
+            h->evals_since_sort++; h->total_evals++;
+            return AGBNP_B200_OK;
+        }
+        if (!grow(h, status)) { h->err = "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")"; return AGBNP_B200_ERR_CAPACITY; }
+    }
+    h->err = "agbnp_b200: capacity growth did not converge";
+    return AGBNP_B200_ERR_CAPACITY;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* agbnp_b200_version(void) { return "agbnp_b200 0.1 sm_100a"; }
+
+void agbnp_b200_default_config(agbnp_b200_config* cfg) {
+    cfg->version = 1; cfg->nonbonded_method = AGBNP_B200_NOCUTOFF; cfg->cutoff = 1.0; cfg->device = 0;
+    cfg->shard_rank = 0; cfg->shard_count = 1; cfg->reorder_interval = 0;
+}
+
+const char* agbnp_b200_last_error(const agbnp_b200* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius, const double* gamma, const double* alpha,
+                      const double* charge, const unsigned char* ishydrogen, agbnp_b200** out) {
+    if (out) *out = nullptr;
+    if (!cfg || !out || n <= 0 || !radius || !gamma || !alpha || !charge || !ishydrogen) {
+        g_create_error = "agbnp_b200_create: null or empty argument"; return AGBNP_B200_ERR_ARG;
+    }
+    if (cfg->version < 0 || cfg->version > 2) { g_create_error = "AGBNPForce::setVersion(): illegal version number"; return AGBNP_B200_ERR_ARG; }
+    if (cfg->version == 2) { g_create_error = "agbnp_b200: AGBNP2 (version 2) is outside this library's path"; return AGBNP_B200_ERR_ARG; }
+    if (cfg->nonbonded_method == AGBNP_B200_CUTOFF_PERIODIC) {
+        g_create_error = "agbnp_b200: CutoffPeriodic is not supported (the reference implements it on no platform)"; return AGBNP_B200_ERR_ARG;
+    }
+    if (cfg->nonbonded_method != AGBNP_B200_NOCUTOFF && cfg->nonbonded_method != AGBNP_B200_CUTOFF_NONPERIODIC) {
+        g_create_error = "agbnp_b200: unknown nonbonded method"; return AGBNP_B200_ERR_ARG;
+    }
+    if (cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count) {
+        g_create_error = "agbnp_b200: bad shard rank/count"; return AGBNP_B200_ERR_ARG;
+    }
+    if (cfg->nonbonded_method == AGBNP_B200_CUTOFF_NONPERIODIC && !(cfg->cutoff > 0)) {
+        g_create_error = "agbnp_b200: cutoff must be positive"; return AGBNP_B200_ERR_ARG;
+    }
+    agbnp_b200* h = new agbnp_b200();
+    h->cfg = *cfg;
+    h->k = Constants::make();
+    h->n = n;
+    std::string e = h->sp.init(cfg->version, n, radius, gamma, alpha, charge, ishydrogen, h->k);
+    if (!e.empty()) { g_create_error = e; delete h; return AGBNP_B200_ERR_ARG; }
+    if (h->sp.i4.ntypes_screened > 255 || h->sp.i4.ntypes_screener > 127) {
+        g_create_error = "agbnp_b200: too many distinct atomic radii (max 255 screened / 127 screener classes)"; delete h; return AGBNP_B200_ERR_ARG;
+    }
+    try {
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0) throw CudaFail{"no CUDA device available (this library has no CPU fallback)"};
+        CK(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, cfg->device));
+        h->num_sm = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        for (auto& e2 : h->ev) CK(cudaEventCreate(&e2));
+        h->have_events = true;
+        h->tree_grid = h->num_sm*2;
+        h->gamma_grid = h->num_sm*4;
+        h->gb_grid = h->num_sm*3;
+        CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) (TREE_WARPS*tree_smem_per_warp(h->nbrmax, h->lwmax))));
+        const size_t tab_bytes = (size_t) h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener*I4_INTERVALS*sizeof(float4);
+        const int pair_smem = (int) (tab_bytes + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4)));
+        if (pair_smem > 200*1024) throw CudaFail{"I4 tables do not fit in shared memory (too many radius classes)"};
+        CK(cudaFuncSetAttribute(k_born<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_born<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_deriv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_deriv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        alloc_tree_scratch(h);
+        CK(cudaMallocHost((void**) &h->h_posq, sizeof(float4)*n));
+        CK(cudaMallocHost((void**) &h->h_force, sizeof(double)*3*n));
+        CK(cudaMallocHost((void**) &h->h_scal, sizeof(double)*SC_COUNT));
+        CK(cudaMallocHost((void**) &h->h_ctrl, sizeof(int)*CW_COUNT));
+        h->d_posq_in.alloc(n);
+        h->d_force_out.alloc((size_t) 3*n);
+    } catch (const CudaFail& f) {
+        g_create_error = "agbnp_b200_create: " + f.msg;
+        delete h;
+        return AGBNP_B200_ERR_CUDA;
+    }
+    *out = h;
+    return AGBNP_B200_OK;
+}
+
+void agbnp_b200_destroy(agbnp_b200* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    delete h;
+}
+
+int agbnp_b200_set_params(agbnp_b200* h, int n, const double* radius, const double* gamma, const double* alpha,
+                          const double* charge, const unsigned char* ishydrogen) {
+    if (!h) return AGBNP_B200_ERR_ARG;
+    std::string e = h->sp.update(n, radius, gamma, alpha, charge, ishydrogen);
+    if (!e.empty()) { h->err = e; return AGBNP_B200_ERR_PARAM_CHANGE; }
+    h->params_dirty = true;
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces, int include_energy,
+                            double* energy, double* forces) {
+    if (!h || !pos) return AGBNP_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        cudaStream_t s = h->own_stream;
+        for (int i = 0; i < h->n; i++)
+            h->h_posq[i] = make_float4((float) pos[3*i], (float) pos[3*i+1], (float) pos[3*i+2], 0.f);
+        CK(cudaMemcpyAsync(h->d_posq_in.p, h->h_posq, sizeof(float4)*h->n, cudaMemcpyHostToDevice, s));
+        prepare(h, (const float*) h->h_posq, 4, nullptr, s);
+        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
+        const int rc = run_checked(h, h->d_posq_in.p, s, &sink);
+        if (rc != AGBNP_B200_OK) return rc;
+        if (include_forces && forces)
+            CK(cudaMemcpyAsync(h->h_force, h->d_force_out.p, sizeof(double)*3*h->n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (include_forces && forces) for (int i = 0; i < 3*h->n; i++) forces[i] += h->h_force[i];
+        if (energy) *energy = include_energy ? h->h_scal[SC_SPARE0] : 0.0;
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, void* d_force, int force_layout,
+                              int padded_n, double* d_energy, double* h_energy) {
+    if (!h || !d_posq) return AGBNP_B200_ERR_ARG;
+    if (d_force && force_layout != 0 && force_layout != 1) { h->err = "agbnp_b200_execute_device: bad force layout"; return AGBNP_B200_ERR_ARG; }
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        cudaStream_t s = (cudaStream_t) stream;
+        prepare(h, nullptr, 0, d_posq, s);
+        ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
+        const int rc = run_checked(h, (const float4*) d_posq, s, &sink);
+        if (rc != AGBNP_B200_OK) return rc;
+        if (h_energy) {
+            CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            *h_energy = h->h_scal[SC_SPARE0];
+        }
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_time_device(agbnp_b200* h, const void* d_posq, int repeats, float* ms_per_eval) {
+    if (!h || !d_posq || repeats < 1 || !ms_per_eval) return AGBNP_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        cudaStream_t s = h->own_stream;
+        prepare(h, nullptr, 0, d_posq, s);
+        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
+        int rc = run_checked(h, (const float4*) d_posq, s, &sink);       // settles capacities
+        if (rc != AGBNP_B200_OK) return rc;
+        CK(cudaEventRecord(h->ev[0], s));
+        for (int i = 0; i < repeats; i++) enqueue(h, (const float4*) d_posq, s, 15, &sink, false);
+        CK(cudaEventRecord(h->ev[1], s));
+        const int status = fetch_status(h, s);
+        if (status != 0) { h->err = "agbnp_b200_time_device: capacity overflow during timing"; return AGBNP_B200_ERR_CAPACITY; }
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        *ms_per_eval = ms/repeats;
+        h->total_evals += repeats;
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_kernel_times(agbnp_b200* h, int repeats, const void* d_posq, float* ms_out, int max_kernels, const char** names) {
+    if (!h || !d_posq || repeats < 1 || !ms_out) return AGBNP_B200_ERR_ARG;
+    if (names) *names = kKernelNames;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        cudaStream_t s = h->own_stream;
+        prepare(h, nullptr, 0, d_posq, s);
+        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
+        int rc = run_checked(h, (const float4*) d_posq, s, &sink);
+        if (rc != AGBNP_B200_OK) return rc;
+        std::vector<double> acc(K_COUNT, 0.0);
+        for (int i = 0; i < repeats; i++) {
+            enqueue(h, (const float4*) d_posq, s, 15, &sink, true);
+            CK(cudaStreamSynchronize(s));
+            for (int k = 0; k < K_COUNT; k++) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k+1]));
+                acc[k] += ms;
+            }
+        }
+        for (int k = 0; k < K_COUNT && k < max_kernels; k++) ms_out[k] = (float) (acc[k]/repeats);
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return K_COUNT;
+}
+
+int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
+    if (!h || !host_out) return AGBNP_B200_ERR_ARG;
+    if (!h->order_valid) { h->err = "agbnp_b200_get: no evaluation has run yet"; return AGBNP_B200_ERR_ARG; }
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        CK(cudaDeviceSynchronize());
+        const int n = h->n, np = h->np;
+        auto need = [&](size_t b) { if (bytes < b) throw CudaFail{"agbnp_b200_get: output buffer too small"}; };
+        auto per_atom_d = [&](const double* dptr, double* out) {
+            std::vector<double> t(np);
+            CK(cudaMemcpy(t.data(), dptr, sizeof(double)*np, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) out[h->orig[k]] = t[k];
+        };
+        auto per_atom_f = [&](const float* dptr, double* out) {
+            std::vector<float> t(np);
+            CK(cudaMemcpy(t.data(), dptr, sizeof(float)*np, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) out[h->orig[k]] = t[k];
+        };
+        double* od = (double*) host_out;
+        switch (what) {
+        case AGBNP_B200_GET_SELF_VOLUME_VDW: need(sizeof(double)*n); per_atom_d(h->d_svS, od); break;
+        case AGBNP_B200_GET_SELF_VOLUME_LARGE: need(sizeof(double)*n); per_atom_d(h->d_svL, od); break;
+        case AGBNP_B200_GET_SURFACE_AREA: {
+            need(sizeof(double)*n);
+            std::vector<double> a(n), b(n);
+            per_atom_d(h->d_svL, a.data()); per_atom_d(h->d_svS, b.data());
+            for (int i = 0; i < n; i++) od[i] = (a[i]-b[i])/h->k.roffset;
+            break;
+        }
+        case AGBNP_B200_GET_BORN_RADIUS: need(sizeof(double)*n); per_atom_f(h->d_born.p, od); break;
+        case AGBNP_B200_GET_VOLUME_SCALING: need(sizeof(double)*n); per_atom_f(h->d_vsf.p, od); break;
+        case AGBNP_B200_GET_DERIV_Y: {
+            need(sizeof(double)*n); per_atom_f(h->d_yq, od);
+            for (int i = 0; i < n; i++) od[i] /= (-2.0*h->k.dielectric_factor);
+            break;
+        }
+        case AGBNP_B200_GET_DERIV_WU: need(sizeof(double)*n); per_atom_f(h->d_wu.p, od); break;
+        case AGBNP_B200_GET_SCALARS: {
+            need(sizeof(double)*8);
+            double sc[SC_COUNT];
+            CK(cudaMemcpy(sc, h->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+            int cur = 0;
+            CK(cudaMemcpy(&cur, h->d_ctrl+CW_TREE_CURSOR, sizeof(int), cudaMemcpyDeviceToHost));
+            od[0] = sc[SC_EVOL_L]; od[1] = sc[SC_EVOL_S]; od[2] = sc[SC_EGB]; od[3] = sc[SC_EVDW];
+            od[4] = sc[SC_VOL_L]; od[5] = sc[SC_VOL_S]; od[6] = sc[SC_SPARE0]; od[7] = (double) (cur - h->nh);
+            break;
+        }
+        case AGBNP_B200_GET_WORK_COUNTERS: {
+            need(sizeof(double)*8);
+            unsigned long long c[CT_COUNT];
+            CK(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 8; i++) od[i] = (double) c[i];
+            break;
+        }
+        case AGBNP_B200_GET_TREE_SIZE: {
+            need(sizeof(long long));
+            int cur = 0;
+            CK(cudaMemcpy(&cur, h->d_ctrl+CW_TREE_CURSOR, sizeof(int), cudaMemcpyDeviceToHost));
+            *(long long*) host_out = (long long) cur - h->nh;
+            break;
+        }
+        case AGBNP_B200_GET_TREE_TOPOLOGY: {
+            int cur = 0;
+            CK(cudaMemcpy(&cur, h->d_ctrl+CW_TREE_CURSOR, sizeof(int), cudaMemcpyDeviceToHost));
+            const long long m = (long long) cur - h->nh;
+            need(sizeof(int)*4*(size_t) m);
+            std::vector<int> off(h->nh), cnt(h->nh), atom(cur);
+            std::vector<short> par(cur), rank(cur);
+            CK(cudaMemcpy(off.data(), h->st.root_off, sizeof(int)*h->nh, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(cnt.data(), h->st.root_cnt, sizeof(int)*h->nh, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(atom.data(), h->st.atom, sizeof(int)*cur, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(par.data(), h->st.parent, sizeof(short)*cur, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(rank.data(), h->st.rank, sizeof(short)*cur, cudaMemcpyDeviceToHost));
+            // roots in increasing caller index
+            std::vector<int> roots(h->nh);
+            for (int r = 0; r < h->nh; r++) roots[r] = r;
+            std::sort(roots.begin(), roots.end(), [&](int a, int b) { return h->orig[a] < h->orig[b]; });
+            int* o = (int*) host_out;
+            long long w = 0;
+            for (int r : roots) {
+                const long long base = w;
+                for (int sl = 1; sl < cnt[r]; sl++) {
+                    const int g = off[r]+sl;
+                    o[4*w+0] = h->orig[r];
+                    o[4*w+1] = par[g] == 0 ? -1 : (int) (base + par[g]-1);
+                    o[4*w+2] = h->orig[atom[g]];
+                    o[4*w+3] = rank[g];
+                    w++;
+                }
+            }
+            break;
+        }
+        case AGBNP_B200_GET_NEIGHBOR_COUNT:
+        case AGBNP_B200_GET_NEIGHBOR_PAIRS: {
+            PairCommon pc = pair_common(h);
+            DevBuf<unsigned long long> cnt;
+            cnt.alloc(1);
+            CK(cudaMemset(cnt.p, 0, sizeof(unsigned long long)));
+            const long long cap = what == AGBNP_B200_GET_NEIGHBOR_PAIRS ? (long long) (bytes/(2*sizeof(int))) : 0;
+            if (cap > 0) h->d_pairs.alloc((size_t) cap);
+            ListArgs la{pc, h->d_pairs.p, cap, cnt.p};
+            k_list_pairs<<<h->num_sm*4, 256>>>(la);
+            CK(cudaDeviceSynchronize());
+            unsigned long long c = 0;
+            CK(cudaMemcpy(&c, cnt.p, sizeof(c), cudaMemcpyDeviceToHost));
+            if (what == AGBNP_B200_GET_NEIGHBOR_COUNT) { need(sizeof(long long)); *(long long*) host_out = (long long) c; }
+            else {
+                if ((long long) c > cap) throw CudaFail{"agbnp_b200_get: output buffer too small for the pair list"};
+                CK(cudaMemcpy(host_out, h->d_pairs.p, sizeof(int2)*c, cudaMemcpyDeviceToHost));
+            }
+            break;
+        }
+        default: h->err = "agbnp_b200_get: unknown selector"; return AGBNP_B200_ERR_ARG;
+        }
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* stream) {
+    if (!h || phase < 0 || phase > 2) return AGBNP_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        cudaStream_t s = (cudaStream_t) stream;
+        if (phase == 0) {
+            if (!d_posq) return AGBNP_B200_ERR_ARG;
+            prepare(h, nullptr, 0, d_posq, s);
+        }
+        enqueue(h, (const float4*) d_posq, s, 1 << phase, nullptr, false);
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes, int* own_begin, int* own_end) {
+    if (!h || !d_ptr || !bytes) return AGBNP_B200_ERR_ARG;
+    if (!h->order_valid || h->params_dirty) { h->err = "agbnp_b200_shard_buffer: call shard_phase(0) first"; return AGBNP_B200_ERR_ARG; }
+    PairCommon pc = pair_common(h);
+    if (own_begin) *own_begin = pc.row_begin*TILE;
+    if (own_end) *own_end = pc.row_end*TILE;
+    switch (which) {
+    case AGBNP_B200_BUF_BORN: *d_ptr = h->d_born.p; *bytes = sizeof(float)*h->np; break;
+    case AGBNP_B200_BUF_BW: *d_ptr = h->d_bw.p; *bytes = sizeof(float)*h->np; break;
+    case AGBNP_B200_BUF_FORCE: *d_ptr = h->d_force; *bytes = sizeof(unsigned long long)*3*h->np; break;
+    case AGBNP_B200_BUF_ENERGY: *d_ptr = h->d_scalars; *bytes = sizeof(double)*SC_COUNT; break;
+    default: return AGBNP_B200_ERR_ARG;
+    }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int force_layout, int padded_n,
+                            double* d_energy, double* h_energy) {
+    if (!h) return AGBNP_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        cudaStream_t s = (cudaStream_t) stream;
+        ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
+        enqueue(h, nullptr, s, 8, &sink, false);
+        const int status = fetch_status(h, s);
+        if (status != 0) { h->err = "agbnp_b200_shard_finish: capacity overflow (status " + std::to_string(status) + ")"; return AGBNP_B200_ERR_CAPACITY; }
+        CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_energy) *h_energy = h->h_scal[SC_SPARE0];
+        h->evals_since_sort++; h->total_evals++;
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+} // extern "C"

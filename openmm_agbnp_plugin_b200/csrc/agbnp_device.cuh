@@ -1,0 +1,89 @@
+// Shared device-side definitions for the sm_100a AGBNP1/GaussVol kernels.
+//
+// HBM layout (all arrays in the library's internal "sorted" atom order: heavy atoms first in Morton order, padded to a
+// multiple of 32, then hydrogens in Morton order, padded to a multiple of 32):
+//   posq      float4[np]   x,y,z (nm), charge                     (SoA float4, one 16-byte load per atom)
+//   orig      int[np]      caller's atom index, -1 for padding
+//   aL,vL,aS,vS double[np] Gaussian exponent / volume for enlarged and vdW radii (v = 0 for hydrogens / padding)
+//   accumulators (zeroed per evaluation by one memset): see Accum
+#ifndef AGBNP_DEVICE_CUH_
+#define AGBNP_DEVICE_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace agbnp_b200_impl {
+
+constexpr int TILE = 32;                      // atoms per block (one warp lane each)
+constexpr double FORCE_SCALE = 4294967296.0;  // 2^32, OpenMM's fixed-point force scale
+constexpr unsigned FULL = 0xffffffffu;
+
+// status bits written by kernels when a capacity is exceeded (host grows the buffer and re-runs the evaluation)
+enum StatusBits { ST_NBR_OVERFLOW = 1, ST_NODE_OVERFLOW = 2, ST_LEVEL_OVERFLOW = 4, ST_TREE_OVERFLOW = 8, ST_PAIRLIST_OVERFLOW = 16 };
+
+// energy / diagnostic scalar slots (double)
+enum ScalarSlot { SC_EVOL_L = 0, SC_EVOL_S = 1, SC_EGB = 2, SC_EVDW = 3, SC_VOL_L = 4, SC_VOL_S = 5, SC_SPARE0 = 6, SC_SPARE1 = 7, SC_COUNT = 8 };
+// work counters (unsigned long long)
+enum CounterSlot { CT_PGB = 0, CT_PQ = 1, CT_C2 = 2, CT_C3 = 3, CT_M = 4, CT_TILES_GB = 5, CT_TILES_Q = 6, CT_SPARE = 7, CT_COUNT = 8 };
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL, v, o);
+        if (lane_id() >= o) v += t;
+    }
+    return v;
+}
+
+// fixed-point force accumulation (bitwise reproducible; same representation as OpenMM's CUDA force buffer)
+__device__ __forceinline__ void add_force_fixed(unsigned long long* f, float v) {
+    atomicAdd(f, (unsigned long long) (long long) (v*(float) 4294967296.0f));
+}
+__device__ __forceinline__ void add_force_fixed(unsigned long long* f, double v) {
+    atomicAdd(f, (unsigned long long) (long long) (v*FORCE_SCALE));
+}
+
+// squared distance between two axis-aligned boxes given as centre/half-extent
+__device__ __forceinline__ float box_box_dist2(float4 ca, float4 ha, float4 cb, float4 hb) {
+    float dx = fmaxf(0.f, fabsf(ca.x-cb.x) - ha.x - hb.x);
+    float dy = fmaxf(0.f, fabsf(ca.y-cb.y) - ha.y - hb.y);
+    float dz = fmaxf(0.f, fabsf(ca.z-cb.z) - ha.z - hb.z);
+    return dx*dx + dy*dy + dz*dz;
+}
+__device__ __forceinline__ float point_box_dist2(float x, float y, float z, float4 cb, float4 hb) {
+    float dx = fmaxf(0.f, fabsf(x-cb.x) - hb.x);
+    float dy = fmaxf(0.f, fabsf(y-cb.y) - hb.y);
+    float dz = fmaxf(0.f, fabsf(z-cb.z) - hb.z);
+    return dx*dx + dy*dy + dz*dz;
+}
+
+// r2 exactly as the oracle's membership rule evaluates it: float, left to right, no FMA contraction
+__device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+} // namespace agbnp_b200_impl
+#endif
