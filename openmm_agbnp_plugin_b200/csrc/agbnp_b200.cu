@@ -84,7 +84,7 @@ struct agbnp_b200 {
     size_t slab_bytes = 0;
     DevBuf<double> d_force_out;             // double[3n] for the host path
     // tree
-    int tree_cap = 768, nbrmax = 128, lwmax = 512;
+    int tree_cap = 768, nbrmax = 128;
     int tree_grid = 0, gamma_grid = 0, gb_grid = 0;
     DevBuf<unsigned char> d_tree_scratch, d_gamma_scratch;
     TreeStore st{};
@@ -248,11 +248,11 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ta.inv_roffset = (float) (1.0/h->k.roffset);
         ta.max_order = h->k.max_order;
         ta.scratch = h->d_tree_scratch.p; ta.scratch_stride = tree_scratch_bytes(h->tree_cap);
-        ta.cap = h->tree_cap; ta.nbrmax = h->nbrmax; ta.lwmax = h->lwmax;
+        ta.cap = h->tree_cap; ta.nbrmax = h->nbrmax;
         ta.svS = h->d_svS; ta.svL = h->d_svL; ta.force = h->d_force; ta.scalars = h->d_scalars; ta.counters = h->d_counters;
         ta.st = h->st; ta.st.cursor = h->d_ctrl+CW_TREE_CURSOR;
         ta.work_counter = h->d_ctrl+CW_WORK_TREE; ta.status = h->d_ctrl+CW_STATUS;
-        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax, h->lwmax);
+        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax);
         k_tree<<<h->tree_grid, TREE_THREADS, smem, s>>>(ta);
         mark(K_BORN);
         if (v1) {
@@ -329,10 +329,9 @@ int fetch_status(agbnp_b200* h, cudaStream_t s) {
 // grow whatever overflowed; returns false if a limit was hit
 bool grow(agbnp_b200* h, int status) {
     if (status & ST_NBR_OVERFLOW) { if (h->nbrmax >= 1024) return false; h->nbrmax *= 2; }
-    if (status & ST_LEVEL_OVERFLOW) { if (h->lwmax >= 8192) return false; h->lwmax *= 2; }
     if (status & ST_NODE_OVERFLOW) { if (h->tree_cap >= 16384) return false; h->tree_cap *= 2; }
-    if (status & (ST_NBR_OVERFLOW | ST_LEVEL_OVERFLOW)) {
-        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax, h->lwmax);
+    if (status & ST_NBR_OVERFLOW) {
+        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax);
         if (smem > 200*1024) return false;
         CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     }
@@ -432,7 +431,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         h->gamma_grid = h->num_sm*4;
         h->gb_grid = h->num_sm*3;
         CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) (TREE_WARPS*tree_smem_per_warp(h->nbrmax, h->lwmax))));
+                                (int) (TREE_WARPS*tree_smem_per_warp(h->nbrmax))));
         const size_t tab_bytes = (size_t) h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener*I4_INTERVALS*sizeof(float4);
         const int pair_smem = (int) (tab_bytes + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4)));
         if (pair_smem > 200*1024) throw CudaFail{"I4 tables do not fit in shared memory (too many radius classes)"};

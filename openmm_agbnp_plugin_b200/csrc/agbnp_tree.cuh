@@ -49,7 +49,7 @@ struct TreeArgs {
     int max_order;
     unsigned char* scratch;
     size_t scratch_stride;
-    int cap, nbrmax, lwmax;
+    int cap, nbrmax;
     double *svS, *svL;
     unsigned long long* force;        // [3][np] fixed point
     double* scalars;
@@ -60,12 +60,12 @@ struct TreeArgs {
 };
 
 __host__ __device__ inline size_t tree_scratch_bytes(int cap) {
-    size_t b = (size_t) cap*(11*sizeof(double) + 24*sizeof(float) + 6*sizeof(short) + 1);
+    size_t b = (size_t) cap*(11*sizeof(double) + 24*sizeof(float) + sizeof(int) + 6*sizeof(short) + 1) + 2*sizeof(int);
     return (b + 255) & ~(size_t) 255;
 }
-__host__ __device__ inline size_t tree_smem_per_warp(int nbrmax, int lwmax) {
+__host__ __device__ inline size_t tree_smem_per_warp(int nbrmax) {
     size_t b = (size_t) nbrmax*3*sizeof(double) + (size_t) 5*(nbrmax+1)*sizeof(float) + (size_t) nbrmax*sizeof(int)
-             + (size_t) (lwmax+1)*sizeof(int) + (size_t) (MAX_LEVELS+2)*sizeof(int);
+             + (size_t) (MAX_LEVELS+2)*sizeof(int);
     return (b + 15) & ~(size_t) 15;
 }
 
@@ -96,6 +96,7 @@ struct TreeScratch {
     double *gLa, *gLv, *gLx, *gLy, *gLz, *gSa, *gSv, *gSx, *gSy, *gSz, *key;
     float *sfpL, *dvvL, *dLx, *dLy, *dLz, *volS, *sfpS, *dvvS, *dSx, *dSy, *dSz, *gam;
     float *aEL, *afL, *apLx, *apLy, *apLz, *apsL, *aES, *afS, *apSx, *apSy, *apSz, *apsS;
+    int* pref;               // [cap+2] exclusive prefix of candidate counts of the level being expanded
     short *parent, *nbr, *cstart, *ccount, *perm, *gend;
     unsigned char* lvl;
     __device__ void bind(unsigned char* base, int cap) {
@@ -108,7 +109,8 @@ struct TreeScratch {
         float* a = f+12*(size_t) cap;
         aEL = a; afL = a+cap; apLx = a+2*cap; apLy = a+3*cap; apLz = a+4*cap; apsL = a+5*cap;
         aES = a+6*cap; afS = a+7*cap; apSx = a+8*cap; apSy = a+9*cap; apSz = a+10*cap; apsS = a+11*cap;
-        short* s = (short*) (a+12*(size_t) cap);
+        pref = (int*) (a+12*(size_t) cap);
+        short* s = (short*) (pref + (cap+2 - (cap & 1)));      // keeps 4-byte alignment irrelevant for shorts; even count
         parent = s; nbr = s+cap; cstart = s+2*cap; ccount = s+3*cap; perm = s+4*cap; gend = s+5*cap;
         lvl = (unsigned char*) (s+6*(size_t) cap);
     }
@@ -123,14 +125,13 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nbrmax = A.nbrmax, cap = A.cap;
 
-    unsigned char* sm = smem_raw + (size_t) warp*tree_smem_per_warp(nbrmax, A.lwmax);
+    unsigned char* sm = smem_raw + (size_t) warp*tree_smem_per_warp(nbrmax);
     double* nb_x = (double*) sm;
     double* nb_y = nb_x+nbrmax;
     double* nb_z = nb_y+nbrmax;
     float* acc = (float*) (nb_z+nbrmax);            // [5][nbrmax+1]: svS, svL, gx, gy, gz; index 0 = root, 1+k = neighbor k
     int* nb_idx = (int*) (acc+5*(nbrmax+1));
-    int* pref = nb_idx+nbrmax;                      // [lwmax+1]
-    int* lvs = pref+A.lwmax+1;                      // [MAX_LEVELS+2]
+    int* lvs = nb_idx+nbrmax;                       // [MAX_LEVELS+2]
     const int accs = nbrmax+1;
 
     TreeScratch S;
@@ -207,7 +208,6 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
             if (level == 1) {
                 T = nn;
             } else {
-                if (width > A.lwmax) { if (lane == 0) atomicOr(A.status, ST_LEVEL_OVERFLOW); failed = true; break; }
                 // candidates of node at sorted position t: its younger siblings t+1 .. gend[t]-1 (gaussvol.cpp:221)
                 int carry = 0;
                 for (int t0 = 0; t0 < width; t0 += 32) {
@@ -215,10 +215,10 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
                     int c = 0;
                     if (t < width) c = (int) S.gend[ls+t] - (ls+t) - 1;
                     const int inc = warp_incl_scan(c);
-                    if (t < width) pref[t] = carry + inc - c;
+                    if (t < width) S.pref[t] = carry + inc - c;
                     carry += __shfl_sync(FULL, inc, 31);
                 }
-                if (lane == 0) pref[width] = carry;
+                if (lane == 0) S.pref[width] = carry;
                 T = carry;
                 __syncwarp();
             }
@@ -234,10 +234,10 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
                     int lo = 0, hi = width-1;
                     while (lo < hi) {
                         const int mid = (lo+hi+1) >> 1;
-                        if (pref[mid] <= k) lo = mid; else hi = mid-1;
+                        if (S.pref[mid] <= k) lo = mid; else hi = mid-1;
                     }
                     const int tpos = ls+lo;
-                    const int u = tpos + 1 + (k - pref[lo]);
+                    const int u = tpos + 1 + (k - S.pref[lo]);
                     p = S.perm[tpos];
                     kn = (int) S.nbr[S.perm[u]] - 1;
                 }

@@ -1,0 +1,288 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI behind the plugin interface, against the
+oracle on the same seeded / float-rounded inputs.
+
+Bars (BASELINE.json north_star): overlap-tree topology and neighbor membership bit-exact; energy within 1e-5 relative;
+per-atom forces within 1e-4 relative RMS (float path against the Reference platform's double arithmetic)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_system, sys_args, relrms, gpu_topology
+import openmm_agbnp_plugin_b200 as plug
+from openmm_agbnp_plugin_b200 import systems, _lib
+from oracle import portlib
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-5        # relative energy tolerance (north_star)
+F_TOL = 1e-4        # relative RMS force tolerance (north_star)
+
+
+def _sig(x, digits=6):
+    return float("%.*g" % (digits, x))
+
+
+def _gpu(s, pos, version=1, method=0, cutoff=1.0):
+    ctx = plug.Context(systems.make_force(s, version, method, cutoff))
+    ctx.setPositions(pos)
+    e = ctx.calcForcesAndEnergy()
+    return ctx, e, ctx.getForces().copy()
+
+
+@pytest.mark.parametrize("version", [0, 1])
+def test_golden_reference_files(golden, version):
+    """The reference's own golden outputs (platforms/reference/tests/v{0,1}.reference) through the CUDA path."""
+    s = load_system("gaussvol")
+    g = golden["v%d" % version]
+    ctx, e, f = _gpu(s, s["pos"], version)
+    assert abs(e - g["energy"]) <= E_TOL * abs(g["energy"]) + 0.5e-3 * 10 ** np.floor(np.log10(abs(g["energy"])) - 5)
+    a, ax, dx = golden["displaced_atom"], golden["displaced_axis"], golden["displacement_nm"]
+    p2 = s["pos"].copy(); p2[a, ax] += dx
+    ctx.setPositions(p2)
+    e2 = ctx.calcForcesAndEnergy()
+    # energy change (a difference of two ~1e3 numbers in float arithmetic) and its gradient estimate
+    assert abs((e2 - e) - g["energy_change"]) < 2e-3
+    assert abs(-f[a, ax] * dx - g["energy_change_from_gradient"]) <= 1e-4 * abs(g["energy_change_from_gradient"]) + 1e-7
+    if version == 0:
+        sc = ctx.kernel.get("SCALARS")
+        assert _sig(sc[0]) == g["vol_energy1"] and _sig(sc[1]) == g["vol_energy2"]
+
+
+@pytest.mark.parametrize("name", ["gaussvol", "trpcage", "1li2", "rnaseh"])
+@pytest.mark.parametrize("version", [0, 1])
+def test_nocutoff_parity(name, version):
+    s = load_system(name)
+    pos = systems.float_rounded(s["pos"])
+    o = portlib.OracleKernel(version, *sys_args(s))
+    e_ref, f_ref = o.execute(pos)
+    ctx, e, f = _gpu(s, pos, version)
+    k = ctx.kernel
+    # bit-exact topology: same nodes, same parent/child relations, same sibling order
+    assert int(k.get("TREE_SIZE")[0]) == len(o.tree()["level"]) - 1 - len(pos)
+    assert gpu_topology(k.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+    # by-products: self-volumes (both radius sets), surface areas
+    assert relrms(k.get("SELF_VOLUME_VDW"), o.get("self_volume")) <= 1e-5
+    assert relrms(k.get("SELF_VOLUME_LARGE"), o.get("self_volume_large")) <= 1e-5
+    area_ref = (o.get("self_volume_large") - o.get("self_volume")) / 0.05000000074505806
+    assert relrms(k.get("SURFACE_AREA"), area_ref) <= 1e-4
+    sc = k.get("SCALARS")
+    assert abs(sc[0] - o.scalar("vol_energy1")) <= 1e-6 * abs(o.scalar("vol_energy1"))
+    assert abs(sc[1] - o.scalar("vol_energy2")) <= 1e-6 * abs(o.scalar("vol_energy2"))
+    assert abs(sc[4] - o.scalar("volume1")) <= 1e-5 * abs(o.scalar("volume1"))
+    assert abs(sc[5] - o.scalar("volume2")) <= 1e-5 * abs(o.scalar("volume2"))
+    if version == 1:
+        assert np.abs(k.get("BORN_RADIUS") / o.get("born_radius") - 1).max() <= 1e-5
+        assert relrms(k.get("VOLUME_SCALING"), o.get("volume_scaling_factor")) <= 1e-5
+        assert relrms(k.get("DERIV_Y"), o.get("Y")) <= 1e-5
+        assert relrms(k.get("DERIV_WU"), o.get("W") + o.get("U")) <= 1e-5
+
+
+@pytest.mark.parametrize("name,cutoff", [("trpcage", 1.2), ("rnaseh", 1.2), ("1li2", 1.0), ("trpcage", 0.8)])
+def test_cutoff_parity_and_membership(name, cutoff):
+    """CutoffNonPeriodic against the cutoff-aware restatement ("parity unpinned" by any reference test, see
+    oracle/agbnp_oracle.h); the neighbor set must be identical pair for pair."""
+    s = load_system(name)
+    pos = systems.float_rounded(s["pos"])
+    o = portlib.OracleKernel(1, *sys_args(s), nonbonded_method=portlib.CutoffNonPeriodic, cutoff=cutoff)
+    e_ref, f_ref = o.execute(pos)
+    ctx, e, f = _gpu(s, pos, 1, plug.AGBNPForce.CutoffNonPeriodic, cutoff)
+    pg = ctx.kernel.get("NEIGHBOR_PAIRS")
+    pr = portlib.neighbor_pairs(pos.astype(np.float32), cutoff)
+    assert len(pg) == len(pr)
+    assert set(map(tuple, pg.tolist())) == set(map(tuple, pr.tolist()))
+    assert int(ctx.kernel.get("WORK_COUNTERS")[0]) == len(pr)          # pairs the GB pass actually evaluated
+    assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+
+
+def test_2clr_full_size():
+    """BASELINE config 3 system at full size (5983 atoms, 3.3e5 overlaps)."""
+    s = load_system("2clr")
+    pos = systems.float_rounded(s["pos"])
+    o = portlib.OracleKernel(1, *sys_args(s))
+    e_ref, f_ref = o.execute(pos)
+    ctx, e, f = _gpu(s, pos, 1)
+    assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+
+
+def test_hivrt_size_properties():
+    """The headline workload (HIV-RT or its 2clr x 3 stand-in, ~18k atoms) through size-independent properties:
+    three far-apart... no: the stand-in's copies are in contact, so instead (a) the tree of the stand-in is three copies of
+    2clr's tree plus cross-copy overlaps only at the contact faces: node count >= 3x 2clr; (b) Newton's third law: the
+    total force vanishes; (c) translation invariance of the energy; (d) the evaluation is reproducible."""
+    s = systems.hivrt()
+    pos = systems.float_rounded(s["pos"])
+    ctx, e, f = _gpu(s, pos, 1)
+    m = int(ctx.kernel.get("TREE_SIZE")[0])
+    assert m > 9e5 or not s["name"].startswith("hivrt-standin")
+    fsum = np.abs(f.sum(axis=0)).max()
+    assert fsum < 1e-3 * np.abs(f).max() * np.sqrt(len(pos))
+    ctx.setPositions(pos)
+    e_again = ctx.calcForcesAndEnergy()
+    assert abs(e_again - e) <= 1e-7 * abs(e)
+    shifted = systems.float_rounded(pos + np.array([0.25, -0.5, 0.125]))      # exactly representable shifts
+    ctx.setPositions(shifted)
+    e_shift = ctx.calcForcesAndEnergy()
+    assert abs(e_shift - e) <= 2e-6 * abs(e)
+    assert int(ctx.kernel.get("TREE_SIZE")[0]) in range(m - 50, m + 51)
+
+
+def test_hivrt_standin_one_copy_against_oracle():
+    """Linearity-style check at full size: a single isolated copy inside the stand-in geometry equals 2clr."""
+    b = load_system("2clr")
+    pos = systems.float_rounded(b["pos"])
+    far = np.concatenate([pos, pos + np.array([64.0, 0.0, 0.0])])          # two copies 64 nm apart (exact shift)
+    two = {k: np.concatenate([b[k]] * 2) for k in ("radius", "gamma", "alpha", "charge", "ishydrogen")}
+    ctx1, e1, f1 = _gpu(b, pos, 0)
+    ctx2, e2, f2 = _gpu(two, systems.float_rounded(far), 0)
+    # GaussVol is short-ranged: two copies far apart give exactly twice the tree and (to float precision) twice the energy
+    assert int(ctx2.kernel.get("TREE_SIZE")[0]) == 2 * int(ctx1.kernel.get("TREE_SIZE")[0])
+    assert abs(e2 - 2 * e1) <= 2e-6 * abs(e1)
+    assert relrms(f2[:len(pos)], f1) <= 1e-5
+
+
+def test_execute_accumulates_forces_like_the_reference():
+    """Reference convention (ReferenceAGBNPKernels.cpp:337,378): execute does force[i] += ...; energy is returned."""
+    s = load_system("trpcage")
+    pos = systems.float_rounded(s["pos"])
+    ctx, e, f = _gpu(s, pos, 1)
+    ctx.forces[:] = 1.0
+    e2 = ctx.kernel.execute(ctx, True, True)
+    assert np.allclose(ctx.forces - 1.0, f, rtol=0, atol=1e-6 * np.abs(f).max())
+    assert abs(e2 - e) <= 1e-7 * abs(e)
+
+
+def test_update_parameters_in_context():
+    """copyParametersToContext (ReferenceAGBNPKernels.cpp:1796-1815): gamma/alpha/charge may change, the rest may not."""
+    s = load_system("trpcage")
+    pos = systems.float_rounded(s["pos"])
+    force = systems.make_force(s, 1)
+    ctx = plug.Context(force)
+    ctx.setPositions(pos)
+    ctx.calcForcesAndEnergy()
+    for i in range(force.getNumParticles()):
+        r, g, a, q, h = force.getParticleParameters(i)
+        force.setParticleParameters(i, r, g, 0.5 * a, -q, h)
+    force.updateParametersInContext(ctx)
+    e = ctx.calcForcesAndEnergy()
+    o = portlib.OracleKernel(1, s["radius"], s["gamma"], 0.5 * s["alpha"], -s["charge"], s["ishydrogen"])
+    e_ref, f_ref = o.execute(pos)
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(ctx.getForces(), f_ref) <= F_TOL
+    r, g, a, q, h = force.getParticleParameters(0)
+    force.setParticleParameters(0, r + 0.01, g, a, q, h)
+    with pytest.raises(plug.OpenMMException, match="changing atomic radii"):
+        force.updateParametersInContext(ctx)
+    force.setParticleParameters(0, r, g, a, q, True)
+    with pytest.raises(plug.OpenMMException, match="heavy/hydrogen"):
+        force.updateParametersInContext(ctx)
+
+
+def test_device_buffer_entry_point():
+    """agbnp_b200_execute_device: float4 posq on the device, both force-sink layouts, energy accumulator."""
+    import torch
+    s = load_system("trpcage")
+    pos = systems.float_rounded(s["pos"])
+    n = len(pos)
+    ctx, e, f = _gpu(s, pos, 1)
+    L = _lib.lib()
+    posq = torch.zeros((n, 4), dtype=torch.float32)
+    posq[:, :3] = torch.from_numpy(pos.astype(np.float32))
+    d_posq = posq.cuda()
+    d_f32 = torch.ones((n, 3), dtype=torch.float32, device="cuda")
+    d_e = torch.full((1,), 10.0, dtype=torch.float64, device="cuda")
+    he = C.c_double(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = L.agbnp_b200_execute_device(ctx.kernel.handle, C.c_void_p(d_posq.data_ptr()), C.c_void_p(stream),
+                                     C.c_void_p(d_f32.data_ptr()), 0, n, C.c_void_p(d_e.data_ptr()), C.byref(he))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert abs(he.value - e) <= 1e-7 * abs(e)
+    assert abs(d_e.item() - 10.0 - e) <= 1e-7 * abs(e)
+    assert relrms(d_f32.cpu().numpy().astype(np.float64) - 1.0, f) <= 1e-5
+    padded = (n + 31) // 32 * 32
+    d_fix = torch.zeros((3, padded), dtype=torch.int64, device="cuda")
+    rc = L.agbnp_b200_execute_device(ctx.kernel.handle, C.c_void_p(d_posq.data_ptr()), C.c_void_p(stream),
+                                     C.c_void_p(d_fix.data_ptr()), 1, padded, None, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ffix = d_fix.cpu().numpy().astype(np.float64)[:, :n].T / 2.0 ** 32
+    assert relrms(ffix, f) <= 1e-7
+
+
+def test_edge_cases():
+    """Edge inputs: a single heavy atom; only hydrogens besides one heavy atom; two atoms at overlap distance;
+    a system smaller than one 32-atom block; coincident-free random cloud with all-distinct radii."""
+    kw = dict(gamma=np.array([48.9528]), alpha=np.array([-0.3]), charge=np.array([0.4]))
+    one = dict(radius=np.array([0.17]), ishydrogen=np.array([0]), pos=np.array([[0.1, 0.2, 0.3]]), **kw)
+    o = portlib.OracleKernel(1, *sys_args(one))
+    e_ref, f_ref = o.execute(one["pos"])
+    ctx, e, f = _gpu(one, one["pos"], 1)
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref) and np.abs(f).max() < 1e-6
+    assert int(ctx.kernel.get("TREE_SIZE")[0]) == 0
+
+    rng = np.random.default_rng(5)
+    n = 40
+    pos = systems.float_rounded(rng.uniform(0, 1.2, (n, 3)))
+    ish = (rng.uniform(size=n) < 0.5).astype(np.int32)
+    cloud = dict(radius=rng.uniform(0.12, 0.2, n), gamma=np.where(ish > 0, 0.0, 48.9528), alpha=rng.uniform(-0.5, -0.1, n),
+                 charge=rng.normal(0, 0.3, n), ishydrogen=ish, pos=pos)
+    for version in (0, 1):
+        o = portlib.OracleKernel(version, *sys_args(cloud))
+        e_ref, f_ref = o.execute(pos)
+        ctx, e, f = _gpu(cloud, pos, version)
+        assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
+        assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+        assert relrms(f, f_ref) <= F_TOL
+
+
+def _spaced_cloud(n, box, dmin, seed):
+    rng = np.random.default_rng(seed)
+    pts = []
+    while len(pts) < n:
+        p = rng.uniform(0, box, 3)
+        if all(np.linalg.norm(p - q) >= dmin for q in pts):
+            pts.append(p)
+    return np.array(pts)
+
+
+def test_dense_cluster_grows_capacity_and_hits_max_order():
+    """A cluster twice as dense as a protein (102 heavy atoms / nm^3): subtrees reach 14 250 nodes and MAX_ORDER = 8
+    binds (gaussvol.cpp:211), overflowing the default per-warp node capacity many times over; the library must grow
+    and re-run inside evaluate and never return invalid forces."""
+    n = 200
+    pos = systems.float_rounded(_spaced_cloud(n, 1.25, 0.12, 11))
+    rng = np.random.default_rng(1)
+    s = dict(radius=np.full(n, 0.17), gamma=np.full(n, 48.9528), alpha=np.full(n, -0.2), charge=rng.normal(0, 0.2, n),
+             ishydrogen=np.zeros(n, dtype=np.int32), pos=pos)
+    o = portlib.OracleKernel(1, *sys_args(s))
+    e_ref, f_ref = o.execute(pos)
+    t = o.tree()
+    assert t["level"].max() == 8
+    ctx, e, f = _gpu(s, pos, 1)
+    assert int(ctx.kernel.get("TREE_SIZE")[0]) == len(t["level"]) - 1 - n
+    assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(t)
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+
+
+def test_jittered_trajectory_frames():
+    """MD-like sequence: seeded +-0.001 nm jitter per frame through ONE context (exercises tree rebuild + reuse of buffers)."""
+    s = load_system("trpcage")
+    base = s["pos"]
+    ctx = plug.Context(systems.make_force(s, 1))
+    o = portlib.OracleKernel(1, *sys_args(s))
+    for frame in range(4):
+        pos = systems.float_rounded(systems.jitter(base, 100 + frame))
+        ctx.setPositions(pos)
+        e = ctx.calcForcesAndEnergy()
+        e_ref, f_ref = o.execute(pos)
+        assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
+        assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+        assert relrms(ctx.getForces(), f_ref) <= F_TOL
