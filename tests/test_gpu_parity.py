@@ -36,6 +36,7 @@ def test_golden_reference_files(golden, version):
     s = load_system("gaussvol")
     g = golden["v%d" % version]
     ctx, e, f = _gpu(s, s["pos"], version)
+    sc = ctx.kernel.get("SCALARS")
     assert abs(e - g["energy"]) <= E_TOL * abs(g["energy"]) + 0.5e-3 * 10 ** np.floor(np.log10(abs(g["energy"])) - 5)
     a, ax, dx = golden["displaced_atom"], golden["displaced_axis"], golden["displacement_nm"]
     p2 = s["pos"].copy(); p2[a, ax] += dx
@@ -45,7 +46,6 @@ def test_golden_reference_files(golden, version):
     assert abs((e2 - e) - g["energy_change"]) < 2e-3
     assert abs(-f[a, ax] * dx - g["energy_change_from_gradient"]) <= 1e-4 * abs(g["energy_change_from_gradient"]) + 1e-7
     if version == 0:
-        sc = ctx.kernel.get("SCALARS")
         assert _sig(sc[0]) == g["vol_energy1"] and _sig(sc[1]) == g["vol_energy2"]
 
 
@@ -136,8 +136,9 @@ def test_hivrt_size_properties():
 def test_hivrt_standin_one_copy_against_oracle():
     """Linearity-style check at full size: a single isolated copy inside the stand-in geometry equals 2clr."""
     b = load_system("2clr")
-    pos = systems.float_rounded(b["pos"])
-    far = np.concatenate([pos, pos + np.array([64.0, 0.0, 0.0])])          # two copies 64 nm apart (exact shift)
+    # coordinates on a 2^-16 nm grid so that the 64 nm shift is exact in float (|x| < 128 needs 7 + 16 = 23 bits)
+    pos = systems.float_rounded(np.round(b["pos"] * 65536.0) / 65536.0)
+    far = np.concatenate([pos, pos + np.array([64.0, 0.0, 0.0])])          # two copies 64 nm apart
     two = {k: np.concatenate([b[k]] * 2) for k in ("radius", "gamma", "alpha", "charge", "ishydrogen")}
     ctx1, e1, f1 = _gpu(b, pos, 0)
     ctx2, e2, f2 = _gpu(two, systems.float_rounded(far), 0)
