@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- AGBNP1 energy+force evaluations per second on HIV-RT (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            this repo's sm_100a path (N=1: one GPU; N>1 under torchrun:
+                                                              one evaluation sharded over N GPUs, NCCL exchanges)
+    python bench.py --impl reference --gpus N ...            the reference's own Reference-platform CPU code (oracle/_ref,
+                                                              compiled unmodified from /root/reference) on the host cores
+
+A step is ONE energy+force evaluation of the workload (HIV-RT, AGBNP1 version 1, NoCutoff -- the only method the
+Reference platform implements) on freshly jittered coordinates (+-0.001 nm, seeded), so every step rebuilds the overlap
+tree as an MD step would.  `value` times the evaluation with positions already resident in HBM (CUDA events on the
+launching stream, one bracket per step, L2 flushed between steps outside the brackets); `e2e` times the plugin-level
+call with HOST buffers (positions up, forces + energy down, every step).  DESIGN.md section "Measurement" has the details.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "AGBNP1 energy+force evals/s on HIV RT"
+UNIT = "evals/s"
+NS_PER_DAY_PER_EVAL_PER_S = 0.0864          # dt = 1 fs, one evaluation per step (example/hivrt_benchmark.py:20)
+JITTER_SETS = 8
+FLUSH_BYTES = 256 << 20                     # > 126 MB L2
+
+# algorithmic work per unit (counted from the reference source)
+FLOP_GB, MUFU_GB = 42.0, 2.0                # per GB pair
+FLOP_Q, MUFU_Q = 86.0, 3.0                  # per directed screening pair (Born pass 28+1, derivative pass 58+2)
+FLOP_CAND, MUFU_CAND = 20.0, 3.0            # per overlap candidate examined
+FLOP_NODE, MUFU_NODE = 190.0, 5.0           # per tree node: build 25 + rescan 45 + three sweeps 120; 1 + 4 MUFU
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload():
+    from openmm_agbnp_plugin_b200 import systems
+    s = systems.hivrt()
+    s["pos"] = systems.float_rounded(s["pos"])
+    return s
+
+
+def jittered(pos, k):
+    from openmm_agbnp_plugin_b200 import systems
+    return systems.float_rounded(systems.jitter(pos, 20261018 + k))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML; nvidia-smi is the fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        nv = self.nv
+        if nv is None:
+            return
+        names = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")]
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, attr in names:
+                    if r & getattr(nv, attr, 0):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        if not self.sm:
+            try:
+                import subprocess
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     stdout=subprocess.PIPE, text=True, timeout=10).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 0, "note": "idle nvidia-smi sample"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(self.max_mhz), "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own Reference-platform code on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _ref_backend():
+    from oracle import reflib, portlib
+    if reflib.available():
+        return "reference", reflib.ReferenceKernel
+    return "port", (lambda v, *a: portlib.OracleKernel(v, *a))
+
+
+def _worker_init(m):
+    s = workload()
+    kind, make = _ref_backend()
+    _W["pos"] = s["pos"][:m]
+    _W["k"] = make(1, s["radius"][:m], s["gamma"][:m], s["alpha"][:m], s["charge"][:m], s["ishydrogen"][:m].astype(np.int32))
+
+
+def _worker_eval(seed):
+    t0 = time.perf_counter()
+    e, f = _W["k"].execute(jittered(_W["pos"], seed))
+    return time.perf_counter() - t0, float(e)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    """bench.py --impl reference: every step evaluates, on each host core in parallel, the Reference platform on a bounded
+    sample of the workload; throughput is scaled to the full workload by (N/m)^2 (every dominant loop of the Reference
+    platform -- level-2 sibling scan, GB pairs, Born and derivative passes -- is O(N^2); validated in DESIGN.md)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+    s = workload()
+    n = len(s["pos"])
+    kind, _ = _ref_backend()
+    cores = max(1, host_cores())
+    steps, warmup = args.steps, args.warmup
+    budget_s = 120.0
+    t_full = 3.1 * (n / 5983.0) ** 2                       # seconds per full evaluation on one core (measured: 2clr 3.1 s)
+    per_step = budget_s / max(1, steps + warmup)
+    m = n if t_full <= per_step else max(1000, min(n, int(n * (per_step / t_full) ** 0.5)))
+    scale = (n / m) ** 2
+    with ProcessPoolExecutor(cores, initializer=_worker_init, initargs=(m,)) as pool:
+        seeds = iter(range(10 ** 6))
+        for _ in range(warmup):
+            list(pool.map(_worker_eval, [next(seeds) for _ in range(cores)]))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            list(pool.map(_worker_eval, [next(seeds) for _ in range(cores)]))
+        wall = time.perf_counter() - t0
+    ms_per_step = wall / steps * 1e3
+    value = cores * steps / (wall * scale)
+    sample = ("full workload, one evaluation per core per step" if m == n else
+              "first %d of %d atoms per evaluation (one evaluation per core per step); time scaled by (N/m)^2 = %.2f" % (m, n, scale))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": s.get("name", "hivrt"), "config": config_dict(s, args, "host CPU, Reference platform"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ns_per_day": value * NS_PER_DAY_PER_EVAL_PER_S, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(s, args, parallelism):
+    return {"workload": "%s AGBNP1 (setVersion 1) energy+force, NoCutoff, N=%d atoms" % (s.get("name", "hivrt"), len(s["pos"])),
+            "n_atoms": int(len(s["pos"])), "nonbonded_method": "NoCutoff", "version": 1,
+            "inputs": "positions jittered +-0.001 nm per step (seeded, %d sets)" % JITTER_SETS,
+            "l2": "256 MiB memset between timed evaluations (outside the per-step CUDA-event brackets)",
+            "parallelism": parallelism}
+
+
+def cpu_baseline(s, e_gpu, f_gpu):
+    """One full-size Reference-platform evaluation on one host core (bounded: ~30 s); doubles as the full-size parity check."""
+    kind, make = _ref_backend()
+    k = make(1, s["radius"], s["gamma"], s["alpha"], s["charge"], s["ishydrogen"].astype(np.int32))
+    t0 = time.perf_counter()
+    e, f = k.execute(s["pos"])
+    dt = time.perf_counter() - t0
+    f = np.asarray(f).reshape(-1, 3)
+    parity = {"energy_rel_err": abs(e_gpu - e) / abs(e), "force_rel_rms": float(np.sqrt(((f_gpu - f) ** 2).sum() / (f ** 2).sum())),
+              "energy_gpu": e_gpu, "energy_cpu": float(e), "against": kind, "tolerance": {"energy_rel": 1e-5, "force_rel_rms": 1e-4}}
+    base = {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "1 full-size evaluation (N=%d, unjittered positions), %.1f s on one core; the Reference platform is serial" % (len(s["pos"]), dt)}
+    return base, parity
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import openmm_agbnp_plugin_b200 as plug
+    from openmm_agbnp_plugin_b200 import systems, _lib, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log("bench: WORLD_SIZE=%d but --gpus %d; using WORLD_SIZE" % (world, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    s = workload()
+    n = len(s["pos"])
+    sharded = world > 1 and args.mode == "shard"
+    force = systems.make_force(s, 1, plug.AGBNPForce.NoCutoff, 1.0)
+
+    # device-resident inputs: JITTER_SETS jittered coordinate sets as float4
+    posq_sets = []
+    for k in range(JITTER_SETS):
+        p = torch.zeros((n, 4), dtype=torch.float32)
+        p[:, :3] = torch.from_numpy(jittered(s["pos"], k).astype(np.float32))
+        posq_sets.append(p.to(dev))
+    d_force = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+    d_energy = torch.zeros(1, dtype=torch.float64, device=dev)
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    if sharded:
+        sk = sharding.CudaShardKernel(force, local, rank, world)
+        ev = sharding.ShardedEvaluator(sk, position_owner=0)
+        handle = sk.handle
+
+        def one_eval(k, want_energy=False):
+            return ev.evaluate(posq_sets[k % JITTER_SETS], sp, d_force, 0, n, d_energy, want_energy)
+    else:
+        ctx = plug.Context(force, device=local)
+        handle = ctx.kernel.handle
+
+        def one_eval(k, want_energy=False):
+            e = C.c_double(0.0)
+            rc = L.agbnp_b200_execute_device(handle, posq_sets[k % JITTER_SETS].data_ptr(), sp, d_force.data_ptr(), 0, n,
+                                             d_energy.data_ptr(), C.byref(e) if want_energy else None)
+            if rc != 0:
+                raise RuntimeError(L.agbnp_b200_last_error(handle).decode())
+            return e.value
+
+    def sync():
+        rc = L.agbnp_b200_synchronize(handle, sp)
+        if rc != 0:
+            raise RuntimeError(L.agbnp_b200_last_error(handle).decode())
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # issue-rate peaks of this GPU (roofline denominators)
+    pk = (C.c_double * 8)()
+    L.agbnp_b200_measure_peaks(local, pk, 8)
+    peak_fp32 = 2.0 * max(pk[0], pk[1])             # flop/s
+    peak_mufu = min(pk[2], pk[3])                   # op/s
+    one_eval(0, want_energy=True)                   # settles capacities (synchronous, re-runs on overflow)
+    for k in range(max(args.warmup, 3)):
+        flush.zero_()
+        one_eval(k)
+    sync()
+
+    # ---- timed region: K steps, one CUDA-event bracket per step on the launching stream ----
+    K = args.steps
+    GB_BIT = 4                                       # index of k_gb in the library's kernel list
+    L.agbnp_b200_profile(handle, 1 << GB_BIT)
+    launches0 = L.agbnp_b200_launch_count(handle)
+    d_force.zero_(); d_energy.zero_()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    coll0 = ev.collectives if sharded else 0
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()
+        ev0[k].record(stream)
+        one_eval(k)
+        ev1[k].record(stream)
+    sync()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.result()
+    coll_per_step = ((ev.collectives - coll0) / K) if sharded else 0
+    launches = L.agbnp_b200_launch_count(handle) - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    sums = (C.c_double * 16)(); cnts = (C.c_int * 16)(); names_p = C.c_char_p()
+    L.agbnp_b200_profile_read(handle, sums, cnts, 16, C.byref(names_p))
+    L.agbnp_b200_profile(handle, 0)
+    gb_ms = sums[GB_BIT] / max(1, cnts[GB_BIT])
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / K
+    value = (1e3 / ms_per_step) * (world if (world > 1 and not sharded) else 1)
+    e_mean = float(d_energy.item()) / K
+
+    # ---- per-kernel breakdown (untimed pass) and work counters ----
+    L.agbnp_b200_profile(handle, 0xffffffff)
+    for k in range(20):
+        one_eval(k)
+    nk = L.agbnp_b200_profile_read(handle, sums, cnts, 16, C.byref(names_p))
+    L.agbnp_b200_profile(handle, 0)
+    kn = names_p.value.decode().split("\n")
+    kernels_us = {kn[i]: round(sums[i] / max(1, cnts[i]) * 1e3, 2) for i in range(nk)}
+    wc = np.zeros(8)
+    L.agbnp_b200_get(handle, _lib.GET["WORK_COUNTERS"], wc.ctypes.data_as(C.c_void_p), wc.nbytes)
+    if world > 1:
+        tw = torch.from_numpy(wc).to(dev)
+        dist.all_reduce(tw)
+        wc = tw.cpu().numpy()
+    p_gb, p_q, c2, c3, m_nodes = wc[0], wc[1], wc[2], wc[3], wc[4]
+    flop = FLOP_GB * p_gb + FLOP_Q * p_q + FLOP_CAND * (c2 + c3) + FLOP_NODE * m_nodes
+    mufu = MUFU_GB * p_gb + MUFU_Q * p_q + MUFU_CAND * (c2 + c3) + MUFU_NODE * m_nodes
+    t_roof_ms = max(flop / (peak_fp32 * world), mufu / (peak_mufu * world)) * 1e3
+    gb_pairs_this_rank = p_gb / world
+    roofline = {"bound": "fp32", "kernel": "k_gb", "achieved": FLOP_GB * gb_pairs_this_rank / (gb_ms * 1e-3) / 1e12,
+                "peak": peak_fp32 / 1e12, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                "peak_source": "measured here by agbnp_b200_measure_peaks (FFMA issue rate; MEASURED_PEAKS.json has no FP32 figure)",
+                "launch_ms": gb_ms, "algorithmic_flop_per_launch": FLOP_GB * gb_pairs_this_rank,
+                "mufu_achieved_gops": MUFU_GB * gb_pairs_this_rank / (gb_ms * 1e-3) / 1e9, "mufu_peak_gops": peak_mufu / 1e9}
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    path_roofline = {"flop": flop, "mufu": mufu, "t_roof_ms": t_roof_ms, "t_eval_ms": ms_per_step, "frac": t_roof_ms / ms_per_step,
+                     "peak_fp32_tflops": peak_fp32 / 1e12, "peak_ffma2_tflops": 2 * pk[1] / 1e12, "peak_mufu_gops": peak_mufu / 1e9,
+                     "counters": {"P_gb": p_gb, "P_q": p_q, "C2": c2, "C3plus": c3, "M": m_nodes}}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    tree_ms = kernels_us.get("k_tree", 0.0) * 1e-3
+    tree_bytes = 200.0 * m_nodes / world         # >= 100 B written + read per node over the build + store
+    roofline_tree = {"bound": "hbm", "kernel": "k_tree", "achieved": tree_bytes / max(tree_ms, 1e-9) / 1e6, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": tree_bytes / max(tree_ms, 1e-9) / 1e6 / hbm_peak, "traffic": None, "peak_source": hbm_src}
+
+    # ---- end to end through the plugin interface with HOST buffers (single-GPU handle; sharded: the evaluator) ----
+    e2e = None
+    if not sharded:
+        host_sets = [jittered(s["pos"], k) for k in range(JITTER_SETS)]
+        for k in range(3):
+            ctx.setPositions(host_sets[k]); ctx.calcForcesAndEnergy()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            ctx.setPositions(host_sets[k % JITTER_SETS])
+            ctx.calcForcesAndEnergy()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": K * (world if world > 1 else 1) / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 24 * n + 8 * 8 + 4 * 8,
+               "how": "AGBNPplugin Context.setPositions + calcForcesAndEnergy (agbnp_b200_execute_host): pinned staging, H2D positions, D2H forces+energy, host wall clock"}
+    else:
+        pinned = [p.cpu().pin_memory() for p in posq_sets]
+        h_force = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+        d_in = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+        sync()
+        t0 = time.perf_counter()
+        for k in range(K):
+            if rank == 0:
+                d_in.copy_(pinned[k % JITTER_SETS], non_blocking=True)
+            d_force.zero_()
+            ev.evaluate(d_in, sp, d_force, 0, n, None, True)
+            if rank == 0:
+                h_force.copy_(d_force, non_blocking=True)
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": K / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 12 * n + 8,
+               "how": "rank 0: pinned H2D positions -> broadcast -> sharded evaluation -> D2H forces + energy, host wall clock"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic" if s.get("name", "").startswith("hivrt-standin") else "example/hivrt_agbnp1.dms",
+            "config": config_dict(s, args, "1 GPU" if world == 1 else ("one evaluation sharded over %d GPUs, NCCL" % world if sharded else "%d independent replicas" % world)),
+            "ns_per_day": value * NS_PER_DAY_PER_EVAL_PER_S, "roofline": roofline, "path_roofline": path_roofline, "roofline_tree": roofline_tree,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "kernels_us": kernels_us, "mean_energy_kj_mol": e_mean,
+            "host_wall_ms_per_step": t_wall / K * 1e3}
+    if s.get("name", "").startswith("hivrt-standin"):
+        line["config"]["stand_in"] = "example/hivrt_agbnp1.dms is absent from the reference checkout (.MISSING_LARGE_BLOBS); 2clr x 3 stand-in, N=17949 (SURVEY 8d)"
+    if sharded:
+        line["collectives_per_step"] = coll_per_step
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # unjittered evaluation through the synchronous device path for the full-size parity check
+        p = torch.zeros((n, 4), dtype=torch.float32)
+        p[:, :3] = torch.from_numpy(s["pos"].astype(np.float32))
+        p = p.to(dev)
+        d_force.zero_()
+        e = C.c_double(0.0)
+        rc = L.agbnp_b200_execute_device(handle, p.data_ptr(), sp, d_force.data_ptr(), 0, n, None, C.byref(e))
+        assert rc == 0
+        torch.cuda.synchronize()
+        base, parity = cpu_baseline(s, e.value, d_force.cpu().numpy().astype(np.float64))
+        line["cpu_baseline"] = base
+        line["parity"] = parity
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="shard", choices=["shard", "replica"], help="N>1: shard one evaluation (default) or run replicas")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

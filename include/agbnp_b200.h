@@ -44,8 +44,8 @@ typedef struct {
     int nonbonded_method;  /* AGBNP_B200_NOCUTOFF | AGBNP_B200_CUTOFF_NONPERIODIC */
     double cutoff;         /* nm; ignored for NoCutoff (AGBNPForce default 1.0, AGBNPForce.cpp:15) */
     int device;            /* CUDA device ordinal */
-    /* atom-block tile sharding of the three pair passes across GPUs: this handle evaluates the tile rows
-     * of shard `shard_rank` of `shard_count`; the GaussVol tree is replicated.  1 GPU: rank 0 of 1. */
+    /* sharding of one evaluation across GPUs (see "multi-GPU plumbing" below): this handle evaluates the
+     * share of shard `shard_rank` of `shard_count`.  1 GPU: rank 0 of 1. */
     int shard_rank;
     int shard_count;
     int reorder_interval;  /* evaluations between spatial re-sorts of the internal atom order; <= 0: library default */
@@ -77,7 +77,7 @@ int agbnp_b200_set_params(agbnp_b200* h, int num_particles, const double* radius
  *   pos      [3*N] doubles, nm (rounded to float on upload: the device path computes in float / selective double)
  *   forces   [3*N] doubles, kJ/mol/nm, accumulated (+=); may be NULL when include_forces == 0
  *   energy   receives the potential energy (kJ/mol); may be NULL
- * The host<->device copies are part of the call (this is what bench.py's `e2e` times). */
+ * The host<->device copies are part of the call (this is what bench.py's `e2e` times).  Synchronous. */
 int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces, int include_energy,
                             double* energy, double* forces);
 
@@ -90,19 +90,34 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
  *                             (x[0..padded_n), y[..], z[..]), value*2^32, added with 64-bit atomics
  *   d_energy      device double accumulator to which the energy is added, or NULL
  *   h_energy      host double receiving the energy (forces a stream synchronize), or NULL
- * Returns after enqueueing unless h_energy is given. */
+ * Returns after enqueueing unless h_energy is given (see "Asynchronous use" below). */
 int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, void* d_force, int force_layout,
                               int padded_n, double* d_energy, double* h_energy);
 
-/* Evaluate the same device-resident positions `repeats` times back to back on the handle's stream and return the mean
- * device time per evaluation in milliseconds (CUDA events on that stream).  Used by bench.py for `value` (inputs already
- * resident in HBM) and for the per-kernel breakdown. */
-int agbnp_b200_time_device(agbnp_b200* h, const void* d_posq, int repeats, float* ms_per_eval);
+/* Asynchronous use of agbnp_b200_execute_device (h_energy == NULL): the call returns after enqueueing; forces and energy
+ * are delivered on the stream by the last kernel of the evaluation, and only if no internal capacity overflowed (the
+ * check is on the device).  The status words follow the evaluation to pinned memory and are examined a few calls later
+ * and by agbnp_b200_synchronize: capacities are grown ahead of need from the high-water marks every evaluation reports
+ * (so an overflow needs a >33% jump in local packing between two evaluations); if one happens anyway the call that
+ * notices it returns ERR_CAPACITY naming the evaluation, which must be re-issued.  With h_energy != NULL (and in
+ * agbnp_b200_execute_host) the call is synchronous and re-runs an overflowed evaluation itself.
+ * agbnp_b200_synchronize waits for the stream and retires every pending status. */
+int agbnp_b200_synchronize(agbnp_b200* h, void* stream);
 
-/* per-kernel device times of the last agbnp_b200_time_device / profile run, in ms per evaluation.
- * names: newline-separated kernel names in launch order (static storage). */
-int agbnp_b200_kernel_times(agbnp_b200* h, int repeats, const void* d_posq, float* ms_out, int max_kernels,
-                            const char** names);
+/* Per-kernel CUDA-event brackets for bench.py's roofline: kernels whose bit is set in kernel_mask (bit i = i-th name of
+ * agbnp_b200_profile_read's list) get an event before and after every launch, on the launching stream, until the mask
+ * is cleared.  profile_read synchronises the device, sums the bracketed durations (ms) and launch counts per kernel,
+ * and resets the record.  Returns the number of kernels in the list. */
+int agbnp_b200_profile(agbnp_b200* h, unsigned kernel_mask);
+int agbnp_b200_profile_read(agbnp_b200* h, double* ms_sum, int* launches, int max_kernels, const char** names);
+
+/* kernels this handle has launched since creation (bench.py's gpu_launches) */
+long long agbnp_b200_launch_count(const agbnp_b200* h);
+
+/* Issue-rate microbenchmarks on `device` for the FP32/SFU roofline denominators (north_star: "fraction of the FP32/SFU
+ * roofline"): out[0] scalar FFMA lanes/s, out[1] packed fma.rn.f32x2 lanes/s, out[2] MUFU.EX2 ops/s, out[3] MUFU.RSQ
+ * ops/s, out[4] instruction lanes/s of a 14:1 FFMA:MUFU mix.  n_out >= 5. */
+int agbnp_b200_measure_peaks(int device, double* out, int n_out);
 
 /* diagnostics / by-products of the last evaluation, copied to host (atom order = caller's order).  `what`: */
 typedef enum {
@@ -125,24 +140,29 @@ typedef enum {
 
 int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);
 
-/* ---- multi-GPU plumbing: the caller (one process per GPU) runs the phases and does the collectives
- * between them on the exported device buffers (NCCL via torch.distributed in this repo's host layer).
- *   phase 0: upload/sort, tree build + sweeps 1-2 (replicated), Born-radius pass for the owned rows
- *            -> exchange: all-gather  born  (N floats, owned slices)
- *   phase 1: GB pair pass + vdW for the owned rows, bru/brw
- *            -> exchange: all-gather  bw    (N floats)
- *   phase 2: Born-derivative pass for the owned rows (as screened and as screener), tree gamma sweep with nu restricted
- *            to owned atoms, partial forces
- *            -> exchange: all-reduce  forces (3N) + energy scalars
+/* ---- multi-GPU plumbing: one process per GPU; the caller runs the phases and does the collectives between
+ * them on the exported device buffers (NCCL through torch.distributed in this repo's host layer, sharding.py).
+ * Work split: overlap-tree roots are dealt block-cyclically (each shard builds, sweeps and stores only its subtrees);
+ * the Born-radius pass is replicated (cheaper than an exchange); GB tile units are dealt round-robin; the derivative
+ * pass is split by contiguous row blocks.
+ *   phase 0: gather/sort, tree build + rescan + sweeps for the owned roots   -> all-reduce SELFVOL (2*np doubles)
+ *   phase 1: Born radii (all rows), GB pair pass for the owned tile units     -> all-reduce YQ      (np floats)
+ *   phase 2: bru/brw (all atoms), derivative pass for the owned rows          -> all-reduce WU      (np floats)
+ *   phase 3: tree gamma sweep over the owned subtrees                         -> all-reduce FORCE (3*np int64, exact)
+ *                                                                                 and ENERGY (8 doubles)
+ *   finish : scatter forces to the caller's sink, total energy
  * With shard_count == 1 execute_* run all phases back to back. */
 int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* stream);
 typedef enum {
-    AGBNP_B200_BUF_BORN = 0,     /* float[n_sorted_padded]  Born radii, internal (sorted) order */
-    AGBNP_B200_BUF_BW = 1,       /* float[n_sorted_padded]  bru+brw */
-    AGBNP_B200_BUF_FORCE = 2,    /* long long[3*n_sorted_padded] fixed-point partial forces */
-    AGBNP_B200_BUF_ENERGY = 3    /* double[8] partial energy scalars */
+    AGBNP_B200_BUF_SELFVOL = 0,  /* double[2*np]  partial self-volumes (vdW radii, then enlarged radii), internal order */
+    AGBNP_B200_BUF_YQ = 1,       /* float[np]     partial GB derivative accumulator */
+    AGBNP_B200_BUF_FORCE = 2,    /* long long[3*np] fixed-point partial forces */
+    AGBNP_B200_BUF_ENERGY = 3,   /* double[8]     partial energy scalars */
+    AGBNP_B200_BUF_WU = 4        /* float[np]     W+U of the owned rows, zero elsewhere */
 } agbnp_b200_buffer;
-int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes, int* own_begin, int* own_end);
+int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes);
+/* h_energy == NULL: asynchronous.  Otherwise synchronises and returns ERR_CAPACITY if THIS shard overflowed (the caller
+ * must agree on the outcome across ranks before re-running; sharding.py all-reduces the return code). */
 int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int force_layout, int padded_n,
                             double* d_energy, double* h_energy);
 

@@ -11,7 +11,7 @@ NOCUTOFF, CUTOFF_NONPERIODIC, CUTOFF_PERIODIC = 0, 1, 2
 
 GET = dict(SELF_VOLUME_VDW=0, SELF_VOLUME_LARGE=1, SURFACE_AREA=2, BORN_RADIUS=3, VOLUME_SCALING=4, SCALARS=5,
            TREE_SIZE=6, TREE_TOPOLOGY=7, DERIV_Y=8, DERIV_WU=9, NEIGHBOR_PAIRS=10, NEIGHBOR_COUNT=11, WORK_COUNTERS=12)
-BUF = dict(BORN=0, BW=1, FORCE=2, ENERGY=3)
+BUF = dict(SELFVOL=0, YQ=1, FORCE=2, ENERGY=3, WU=4)
 
 
 class Config(C.Structure):
@@ -42,11 +42,15 @@ def lib():
         L.agbnp_b200_set_params.argtypes = [vp, C.c_int, dp, dp, dp, dp, ucp]
         L.agbnp_b200_execute_host.argtypes = [vp, dp, C.c_int, C.c_int, dp, dp]
         L.agbnp_b200_execute_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, dp]
-        L.agbnp_b200_time_device.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_float)]
-        L.agbnp_b200_kernel_times.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_char_p)]
+        L.agbnp_b200_synchronize.argtypes = [vp, vp]
+        L.agbnp_b200_profile.argtypes = [vp, C.c_uint]
+        L.agbnp_b200_profile_read.argtypes = [vp, dp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_char_p)]
+        L.agbnp_b200_launch_count.argtypes = [vp]
+        L.agbnp_b200_launch_count.restype = C.c_longlong
+        L.agbnp_b200_measure_peaks.argtypes = [C.c_int, dp, C.c_int]
         L.agbnp_b200_get.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.agbnp_b200_shard_phase.argtypes = [vp, C.c_int, vp, vp]
-        L.agbnp_b200_shard_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.agbnp_b200_shard_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.agbnp_b200_shard_finish.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, dp]
         _lib = L
     return _lib

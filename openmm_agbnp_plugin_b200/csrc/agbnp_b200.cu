@@ -16,6 +16,7 @@
 #include "agbnp_device.cuh"
 #include "agbnp_tree.cuh"
 #include "agbnp_pair.cuh"
+#include "agbnp_peaks.cuh"
 
 using namespace agbnp_b200_impl;
 
@@ -47,7 +48,7 @@ enum KernelId { K_ZERO = 0, K_PREP, K_TREE, K_BORN, K_GB, K_BW, K_DERIV, K_GAMMA
 const char* const kKernelNames = "memset_accum\nk_prep\nk_tree\nk_born\nk_gb\nk_bw\nk_deriv\nk_tree_gamma\nk_finish";
 
 // control words inside the zeroed slab
-enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_COUNT = 8 };
+enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_MAX_NBR, CW_MAX_NODES, CW_COUNT = 8 };
 
 } // namespace
 
@@ -75,11 +76,12 @@ struct agbnp_b200 {
     int nunits = 0;
     // per-evaluation arrays
     DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in;
-    DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bw, d_wu;
+    DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bw;
     DevBuf<unsigned char> d_slab;           // zeroed every evaluation
     double *d_svS = nullptr, *d_svL = nullptr, *d_scalars = nullptr;
     unsigned long long *d_force = nullptr, *d_counters = nullptr;
-    float* d_yq = nullptr;
+    float *d_yq = nullptr, *d_wu = nullptr;
+    int* d_root_cnt = nullptr;
     int* d_ctrl = nullptr;
     size_t slab_bytes = 0;
     DevBuf<double> d_force_out;             // double[3n] for the host path
@@ -88,7 +90,7 @@ struct agbnp_b200 {
     int tree_grid = 0, gamma_grid = 0, gb_grid = 0;
     DevBuf<unsigned char> d_tree_scratch, d_gamma_scratch;
     TreeStore st{};
-    DevBuf<int> d_root_off, d_root_cnt, d_st_atom;
+    DevBuf<int> d_root_off, d_st_atom;
     DevBuf<short> d_root_lvs, d_st_parent, d_st_cstart, d_st_ccount, d_st_rank;
     DevBuf<float> d_st_f;                   // 7 float arrays
     // pinned host staging
@@ -98,15 +100,32 @@ struct agbnp_b200 {
     int* h_ctrl = nullptr;
     // diagnostics
     DevBuf<int2> d_pairs;
-    cudaEvent_t ev[K_COUNT+1] = {};
+    cudaEvent_t ev[2] = {};
     bool have_events = false;
+    long long launches = 0;                 // kernels launched by this handle (bench.py's gpu_launches)
+    // per-kernel CUDA-event brackets (agbnp_b200_profile): events come from a pool so that a whole timed region can be
+    // bracketed launch by launch and summed afterwards
+    unsigned prof_mask = 0;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
+    struct ProfRec { int id; size_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    // deferred validation of asynchronous evaluations: status words of evaluation k land in slot k % ASYNC_DEPTH
+    static constexpr int ASYNC_DEPTH = 4;
+    int* h_async = nullptr;                 // pinned [ASYNC_DEPTH][CW_COUNT]
+    cudaEvent_t async_ev[ASYNC_DEPTH] = {};
+    bool async_pending[ASYNC_DEPTH] = {};
+    long long async_issued = 0;
+    bool async_fault = false;
 
     ~agbnp_b200() {
         if (h_posq) cudaFreeHost(h_posq);
         if (h_force) cudaFreeHost(h_force);
         if (h_scal) cudaFreeHost(h_scal);
         if (h_ctrl) cudaFreeHost(h_ctrl);
-        if (have_events) for (auto& e : ev) cudaEventDestroy(e);
+        if (have_events) { for (auto& e : ev) cudaEventDestroy(e); for (auto& e : async_ev) cudaEventDestroy(e); }
+        for (auto& e : prof_pool) cudaEventDestroy(e);
+        if (h_async) cudaFreeHost(h_async);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
@@ -122,7 +141,7 @@ void alloc_store(agbnp_b200* h, int cap) {
     s.cs = h->d_st_f.p; s.dvv = s.cs+cap; s.dx = s.dvv+cap; s.dy = s.dx+cap; s.dz = s.dy+cap; s.c2a = s.dz+cap; s.c2b = s.c2a+cap;
     s.atom = h->d_st_atom.p; s.parent = h->d_st_parent.p; s.cstart = h->d_st_cstart.p; s.ccount = h->d_st_ccount.p;
     s.rank = h->d_st_rank.p;
-    s.root_off = h->d_root_off.p; s.root_cnt = h->d_root_cnt.p; s.root_lvs = h->d_root_lvs.p;
+    s.root_off = h->d_root_off.p; s.root_cnt = h->d_root_cnt; s.root_lvs = h->d_root_lvs.p;
 }
 
 void alloc_tree_scratch(agbnp_b200* h) {
@@ -185,20 +204,21 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     // per-evaluation arrays
     if (h->d_posq.n < (size_t) np) {
         h->d_posq.alloc(np); h->d_bbc.alloc(h->nb); h->d_bbh.alloc(h->nb);
-        h->d_vsf.alloc(np); h->d_born.alloc(np); h->d_bfp.alloc(np); h->d_brw.alloc(np); h->d_bw.alloc(np); h->d_wu.alloc(np);
+        h->d_vsf.alloc(np); h->d_born.alloc(np); h->d_bfp.alloc(np); h->d_brw.alloc(np); h->d_bw.alloc(np);
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o += (bytes+255)/256*256; return r; };
         const size_t o_svS = take(sizeof(double)*np), o_svL = take(sizeof(double)*np), o_force = take(sizeof(unsigned long long)*3*np);
         const size_t o_yq = take(sizeof(float)*np), o_scal = take(sizeof(double)*SC_COUNT), o_cnt = take(sizeof(unsigned long long)*CT_COUNT);
         const size_t o_ctrl = take(sizeof(int)*CW_COUNT);
+        const size_t o_wu = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->nhp);
         h->slab_bytes = o;
         h->d_slab.alloc(o);
         unsigned char* b = h->d_slab.p;
         h->d_svS = (double*) (b+o_svS); h->d_svL = (double*) (b+o_svL); h->d_force = (unsigned long long*) (b+o_force);
         h->d_yq = (float*) (b+o_yq); h->d_scalars = (double*) (b+o_scal); h->d_counters = (unsigned long long*) (b+o_cnt);
         h->d_ctrl = (int*) (b+o_ctrl);
-        h->d_root_off.alloc(h->nhp); h->d_root_cnt.alloc(h->nhp); h->d_root_lvs.alloc((size_t) h->nhp*MAX_LEVELS);
-        CK(cudaMemset(h->d_root_cnt.p, 0, sizeof(int)*h->nhp));
+        h->d_wu = (float*) (b+o_wu); h->d_root_cnt = (int*) (b+o_rcnt);
+        h->d_root_off.alloc(h->nhp); h->d_root_lvs.alloc((size_t) h->nhp*MAX_LEVELS);
         if (h->st.cap == 0) alloc_store(h, std::max(4096, 160*h->nh + 4096));
         else alloc_store(h, h->st.cap);
     }
@@ -223,21 +243,45 @@ PairCommon pair_common(agbnp_b200* h) {
     return c;
 }
 
+enum Phase { PH_TREE = 1, PH_GB = 2, PH_DERIV = 4, PH_FINISH = 8, PH_GAMMA = 16, PH_BORN = 32 };
+
 struct ForceSink { void* ptr; int layout; int padded_n; double* d_energy; };
 
-// enqueue one evaluation.  phase_mask: bit0 = prep+tree+born, bit1 = gb+bw, bit2 = deriv+gamma, bit3 = finish
-void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_mask, const ForceSink* sink, bool timed) {
+cudaEvent_t prof_take(agbnp_b200* h) {
+    if (h->prof_used == h->prof_pool.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->prof_pool.push_back(e);
+    }
+    return h->prof_pool[h->prof_used++];
+}
+
+// enqueue one evaluation (phase_mask: Phase bits).
+// Nothing here synchronises; k_finish delivers to the caller's sink only if no capacity overflowed (device-side check).
+void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_mask, const ForceSink* sink) {
     const bool cutoff = h->cfg.nonbonded_method == AGBNP_B200_CUTOFF_NONPERIODIC;
     const bool v1 = h->cfg.version == 1;
-    auto mark = [&](int id) { if (timed) CK(cudaEventRecord(h->ev[id], s)); };
+    size_t open_a = 0;
+    auto begin = [&](int id) {
+        if (h->prof_mask & (1u << id)) { cudaEvent_t e = prof_take(h); open_a = h->prof_used-1; CK(cudaEventRecord(e, s)); }
+    };
+    auto end = [&](int id, bool kernel = true) {
+        if (kernel) h->launches++;
+        if (h->prof_mask & (1u << id)) {
+            cudaEvent_t e = prof_take(h);
+            CK(cudaEventRecord(e, s));
+            h->prof_recs.push_back({id, open_a, h->prof_used-1});
+        }
+    };
     PairCommon pc = pair_common(h);
-    mark(K_ZERO);
-    if (phase_mask & 1) {
+    if (phase_mask & PH_TREE) {
+        begin(K_ZERO);
         CK(cudaMemsetAsync(h->d_slab.p, 0, h->slab_bytes, s));
-        mark(K_PREP);
+        end(K_ZERO, false);
         PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p};
+        begin(K_PREP);
         k_prep<<<(h->nb+7)/8, 256, 0, s>>>(pa);
-        mark(K_TREE);
+        end(K_PREP);
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
         ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.rcbin = h->d_rcbin.p;
@@ -252,59 +296,74 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ta.svS = h->d_svS; ta.svL = h->d_svL; ta.force = h->d_force; ta.scalars = h->d_scalars; ta.counters = h->d_counters;
         ta.st = h->st; ta.st.cursor = h->d_ctrl+CW_TREE_CURSOR;
         ta.work_counter = h->d_ctrl+CW_WORK_TREE; ta.status = h->d_ctrl+CW_STATUS;
+        ta.shard_rank = h->cfg.shard_rank; ta.shard_count = h->cfg.shard_count;
+        ta.hw_nbr = h->d_ctrl+CW_MAX_NBR; ta.hw_nodes = h->d_ctrl+CW_MAX_NODES;
         const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax);
+        begin(K_TREE);
         k_tree<<<h->tree_grid, TREE_THREADS, smem, s>>>(ta);
-        mark(K_BORN);
+        end(K_TREE);
+    }
+    if (phase_mask & PH_BORN) {
         if (v1) {
             BornArgs ba{};
-            ba.c = pc; ba.svS = h->d_svS; ba.vS = h->d_vS.p; ba.radius = h->d_radius.p; ba.alpha = h->d_alpha.p;
+            // the Born pass is replicated on every shard (cheap; saves an exchange)
+            ba.c = pc; ba.c.row_begin = 0; ba.c.row_end = h->nb;
+            ba.svS = h->d_svS; ba.vS = h->d_vS.p; ba.radius = h->d_radius.p; ba.alpha = h->d_alpha.p;
             ba.vsf = h->d_vsf.p; ba.born = h->d_born.p; ba.bfp = h->d_bfp.p; ba.brw = h->d_brw.p;
             ba.scalars = h->d_scalars; ba.counters = h->d_counters;
             ba.kdiel = (float) h->k.dielectric_factor; ba.hb_radius = (float) h->k.hb_radius;
+            ba.own_row_begin = pc.row_begin; ba.own_row_end = pc.row_end;
             const size_t sm = (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(int)+sizeof(float));
-            const int rows = pc.row_end-pc.row_begin;
+            const int rows = h->nb;
             if (rows > 0) {
+                begin(K_BORN);
                 if (cutoff) k_born<true><<<rows, PAIR_THREADS, sm, s>>>(ba);
                 else k_born<false><<<rows, PAIR_THREADS, sm, s>>>(ba);
+                end(K_BORN);
             }
         }
-    } else { mark(K_PREP); mark(K_TREE); mark(K_BORN); }
-    mark(K_GB);
-    if (v1 && (phase_mask & 2)) {
+    }
+    if (v1 && (phase_mask & PH_GB)) {
         GBArgs ga{};
         ga.c = pc; ga.born = h->d_born.p; ga.units = h->d_units.p; ga.nunits = h->nunits;
         ga.shard_rank = h->cfg.shard_rank; ga.shard_count = h->cfg.shard_count;
         ga.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
         ga.yq = h->d_yq; ga.force = h->d_force; ga.scalars = h->d_scalars; ga.counters = h->d_counters;
         ga.work_counter = h->d_ctrl+CW_WORK_GB;
+        begin(K_GB);
         if (cutoff) k_gb<true><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
         else k_gb<false><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
-        mark(K_BW);
+        end(K_GB);
+    }
+    if (v1 && (phase_mask & PH_DERIV)) {
         BwArgs wa{h->np, h->d_posq.p, h->d_yq, h->d_born.p, h->d_bfp.p, h->d_brw.p, (float) h->k.dielectric_factor, h->d_bw.p};
+        begin(K_BW);
         k_bw<<<(h->np+255)/256, 256, 0, s>>>(wa);
-    } else mark(K_BW);
-    mark(K_DERIV);
-    if (v1 && (phase_mask & 4)) {
+        end(K_BW);
         DerivArgs da{};
-        da.c = pc; da.vsf = h->d_vsf.p; da.bw = h->d_bw.p; da.wu = h->d_wu.p; da.force = h->d_force; da.counters = h->d_counters;
+        da.c = pc; da.vsf = h->d_vsf.p; da.bw = h->d_bw.p; da.wu = h->d_wu; da.force = h->d_force; da.counters = h->d_counters;
         const size_t sm = (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4));
         const int rows = pc.row_end-pc.row_begin;
         if (rows > 0) {
+            begin(K_DERIV);
             if (cutoff) k_deriv<true><<<rows, PAIR_THREADS, sm, s>>>(da);
             else k_deriv<false><<<rows, PAIR_THREADS, sm, s>>>(da);
+            end(K_DERIV);
         }
-        mark(K_GAMMA);
+    }
+    if (v1 && (phase_mask & PH_GAMMA)) {
         GammaArgs gm{};
-        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.wu = h->d_wu.p; gm.vS = h->d_vS.p;
-        gm.own_begin = pc.row_begin*TILE; gm.own_end = pc.row_end*TILE;
+        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.wu = h->d_wu; gm.vS = h->d_vS.p;
         gm.force = h->d_force; gm.scratch = h->d_gamma_scratch.p; gm.scratch_stride = (size_t) 5*h->tree_cap*sizeof(float);
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
+        begin(K_GAMMA);
         k_tree_gamma<<<h->gamma_grid, TREE_THREADS, 0, s>>>(gm);
-    } else mark(K_GAMMA);
-    mark(K_FINISH);
-    if (phase_mask & 8) {
+        end(K_GAMMA);
+    }
+    if (phase_mask & PH_FINISH) {
         FinishArgs fa{};
         fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.force = h->d_force; fa.scalars = h->d_scalars;
+        fa.status = h->d_ctrl+CW_STATUS;
         fa.padded_n = sink ? sink->padded_n : 0;
         if (sink && sink->ptr) {
             if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;
@@ -312,11 +371,14 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
             else fa.out_f64 = (double*) sink->ptr;
         }
         fa.energy_accum = sink ? sink->d_energy : nullptr;
+        begin(K_FINISH);
         k_finish<<<(h->np+255)/256, 256, 0, s>>>(fa);
+        end(K_FINISH);
     }
-    if (timed) CK(cudaEventRecord(h->ev[K_COUNT], s));
     CK(cudaGetLastError());
 }
+
+constexpr int PH_ALL = PH_TREE|PH_BORN|PH_GB|PH_DERIV|PH_GAMMA|PH_FINISH;
 
 // read back status + scalars (synchronises the stream); returns the status bits
 int fetch_status(agbnp_b200* h, cudaStream_t s) {
@@ -326,21 +388,37 @@ int fetch_status(agbnp_b200* h, cudaStream_t s) {
     return h->h_ctrl[CW_STATUS];
 }
 
-// grow whatever overflowed; returns false if a limit was hit
-bool grow(agbnp_b200* h, int status) {
-    if (status & ST_NBR_OVERFLOW) { if (h->nbrmax >= 1024) return false; h->nbrmax *= 2; }
-    if (status & ST_NODE_OVERFLOW) { if (h->tree_cap >= 16384) return false; h->tree_cap *= 2; }
+void set_tree_smem(agbnp_b200* h) {
+    const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax);
+    if (smem > 200*1024) throw CudaFail{"level-2 neighbor capacity does not fit in shared memory"};
+    CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+}
+
+// grow whatever overflowed; returns false if a limit was hit.  ctrl = the evaluation's control words (host copy).
+bool grow(agbnp_b200* h, const int* ctrl) {
+    const int status = ctrl[CW_STATUS];
+    CK(cudaDeviceSynchronize());                       // buffers below may still be in use by queued evaluations
     if (status & ST_NBR_OVERFLOW) {
-        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax);
-        if (smem > 200*1024) return false;
-        CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        if (h->nbrmax >= 1024) return false;
+        h->nbrmax *= 2;
+        set_tree_smem(h);
     }
-    if (status & ST_NODE_OVERFLOW) alloc_tree_scratch(h);
+    if (status & ST_NODE_OVERFLOW) { if (h->tree_cap >= 16384) return false; h->tree_cap *= 2; alloc_tree_scratch(h); }
     if (status & ST_TREE_OVERFLOW) {
-        const int need = h->h_ctrl[CW_TREE_CURSOR];
+        const int need = ctrl[CW_TREE_CURSOR];
         alloc_store(h, std::max(need + need/4 + 4096, h->st.cap*2));
     }
     return true;
+}
+
+// keep headroom so that an asynchronous evaluation practically never overflows: grow when a high-water mark of a
+// completed evaluation exceeds 3/4 of its capacity
+void grow_ahead(agbnp_b200* h, const int* ctrl) {
+    int fake[CW_COUNT] = {};
+    if (ctrl[CW_MAX_NBR]*4 > h->nbrmax*3 && h->nbrmax < 1024) fake[CW_STATUS] |= ST_NBR_OVERFLOW;
+    if (ctrl[CW_MAX_NODES]*4 > h->tree_cap*3 && h->tree_cap < 16384) fake[CW_STATUS] |= ST_NODE_OVERFLOW;
+    if ((long long) ctrl[CW_TREE_CURSOR]*8 > (long long) h->st.cap*7) { fake[CW_STATUS] |= ST_TREE_OVERFLOW; fake[CW_TREE_CURSOR] = ctrl[CW_TREE_CURSOR]; }
+    if (fake[CW_STATUS]) grow(h, fake);
 }
 
 void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_posq_in, cudaStream_t s) {
@@ -353,25 +431,73 @@ void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_pos
             CK(cudaStreamSynchronize(s));
             host_xyz = tmp.data(); stride = 4;
         }
+        CK(cudaDeviceSynchronize());                   // queued evaluations still read the arrays about to be replaced
         build_order(h, host_xyz, stride, s);
     }
     if (h->params_dirty) upload_static(h, s);
 }
 
+// synchronous evaluation: everything is enqueued at once (the finish kernel checks the status word on the device), one
+// synchronisation reads status + energy; on overflow the capacities are grown and the evaluation re-runs, so the
+// caller's sink only ever receives forces of a complete evaluation.
 int run_checked(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
     for (int attempt = 0; attempt < 8; attempt++) {
-        // forces are only delivered to the caller's sink by a run that did not overflow: run phases first, finish after
-        enqueue(h, d_posq_in, s, 7, nullptr, false);
+        enqueue(h, d_posq_in, s, PH_ALL, sink);
         const int status = fetch_status(h, s);
         if (status == 0) {
-            enqueue(h, d_posq_in, s, 8, sink, false);
             h->evals_since_sort++; h->total_evals++;
+            grow_ahead(h, h->h_ctrl);
             return AGBNP_B200_OK;
         }
-        if (!grow(h, status)) { h->err = "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")"; return AGBNP_B200_ERR_CAPACITY; }
+        if (!grow(h, h->h_ctrl)) { h->err = "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")"; return AGBNP_B200_ERR_CAPACITY; }
     }
     h->err = "agbnp_b200: capacity growth did not converge";
     return AGBNP_B200_ERR_CAPACITY;
+}
+
+// retire the deferred status of asynchronous evaluation `k` (waits for it if still running)
+int async_retire(agbnp_b200* h, long long k) {
+    const int slot = (int) (k % agbnp_b200::ASYNC_DEPTH);
+    if (!h->async_pending[slot]) return AGBNP_B200_OK;
+    CK(cudaEventSynchronize(h->async_ev[slot]));
+    h->async_pending[slot] = false;
+    const int* ctrl = h->h_async + slot*CW_COUNT;
+    if (ctrl[CW_STATUS] != 0) {
+        const bool ok = grow(h, ctrl);
+        h->async_fault = true;
+        h->err = std::string("agbnp_b200: asynchronous evaluation ") + std::to_string(k) + " overflowed an internal capacity (status "
+               + std::to_string(ctrl[CW_STATUS]) + "); its forces and energy were NOT delivered" + (ok ? "; capacities grown, re-issue it" : "");
+        return AGBNP_B200_ERR_CAPACITY;
+    }
+    grow_ahead(h, ctrl);
+    return AGBNP_B200_OK;
+}
+
+// asynchronous evaluation: returns after enqueueing.  The status words travel to pinned memory behind the kernels and
+// are checked ASYNC_DEPTH-1 evaluations later (or by agbnp_b200_synchronize).
+int run_async(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
+    const long long k = h->async_issued;
+    if (k >= agbnp_b200::ASYNC_DEPTH-1) {
+        const int rc = async_retire(h, k-(agbnp_b200::ASYNC_DEPTH-1));
+        if (rc != AGBNP_B200_OK) return rc;
+    }
+    enqueue(h, d_posq_in, s, PH_ALL, sink);
+    const int slot = (int) (k % agbnp_b200::ASYNC_DEPTH);
+    CK(cudaMemcpyAsync(h->h_async + slot*CW_COUNT, h->d_ctrl, sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->async_ev[slot], s));
+    h->async_pending[slot] = true;
+    h->async_issued++;
+    h->evals_since_sort++; h->total_evals++;
+    return AGBNP_B200_OK;
+}
+
+int async_drain(agbnp_b200* h) {
+    int rc = AGBNP_B200_OK;
+    for (long long k = std::max(0ll, h->async_issued-agbnp_b200::ASYNC_DEPTH); k < h->async_issued; k++) {
+        const int r = async_retire(h, k);
+        if (r != AGBNP_B200_OK) rc = r;
+    }
+    return rc;
 }
 
 } // namespace
@@ -426,12 +552,13 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         h->num_sm = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         for (auto& e2 : h->ev) CK(cudaEventCreate(&e2));
+        for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->have_events = true;
+        CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
         h->tree_grid = h->num_sm*2;
         h->gamma_grid = h->num_sm*4;
         h->gb_grid = h->num_sm*3;
-        CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) (TREE_WARPS*tree_smem_per_warp(h->nbrmax))));
+        set_tree_smem(h);
         const size_t tab_bytes = (size_t) h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener*I4_INTERVALS*sizeof(float4);
         const int pair_smem = (int) (tab_bytes + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4)));
         if (pair_smem > 200*1024) throw CudaFail{"I4 tables do not fit in shared memory (too many radius classes)"};
@@ -476,17 +603,25 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
     try {
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = h->own_stream;
+        if (async_drain(h) != AGBNP_B200_OK) return AGBNP_B200_ERR_CAPACITY;
         for (int i = 0; i < h->n; i++)
             h->h_posq[i] = make_float4((float) pos[3*i], (float) pos[3*i+1], (float) pos[3*i+2], 0.f);
         CK(cudaMemcpyAsync(h->d_posq_in.p, h->h_posq, sizeof(float4)*h->n, cudaMemcpyHostToDevice, s));
         prepare(h, (const float*) h->h_posq, 4, nullptr, s);
         ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
-        const int rc = run_checked(h, h->d_posq_in.p, s, &sink);
-        if (rc != AGBNP_B200_OK) return rc;
-        if (include_forces && forces)
-            CK(cudaMemcpyAsync(h->h_force, h->d_force_out.p, sizeof(double)*3*h->n, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        for (int attempt = 0; ; attempt++) {
+            enqueue(h, h->d_posq_in.p, s, PH_ALL, &sink);
+            if (include_forces && forces)
+                CK(cudaMemcpyAsync(h->h_force, h->d_force_out.p, sizeof(double)*3*h->n, cudaMemcpyDeviceToHost, s));
+            const int status = fetch_status(h, s);          // the one synchronisation of the call
+            if (status == 0) break;
+            if (attempt >= 8 || !grow(h, h->h_ctrl)) {
+                h->err = "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")";
+                return AGBNP_B200_ERR_CAPACITY;
+            }
+        }
+        h->evals_since_sort++; h->total_evals++;
+        grow_ahead(h, h->h_ctrl);
         if (include_forces && forces) for (int i = 0; i < 3*h->n; i++) forces[i] += h->h_force[i];
         if (energy) *energy = include_energy ? h->h_scal[SC_SPARE0] : 0.0;
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
@@ -502,62 +637,67 @@ int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, v
         cudaStream_t s = (cudaStream_t) stream;
         prepare(h, nullptr, 0, d_posq, s);
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
+        if (!h_energy) return run_async(h, (const float4*) d_posq, s, &sink);
+        if (async_drain(h) != AGBNP_B200_OK) return AGBNP_B200_ERR_CAPACITY;
         const int rc = run_checked(h, (const float4*) d_posq, s, &sink);
         if (rc != AGBNP_B200_OK) return rc;
-        if (h_energy) {
-            CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            *h_energy = h->h_scal[SC_SPARE0];
-        }
+        *h_energy = h->h_scal[SC_SPARE0];
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
 
-int agbnp_b200_time_device(agbnp_b200* h, const void* d_posq, int repeats, float* ms_per_eval) {
-    if (!h || !d_posq || repeats < 1 || !ms_per_eval) return AGBNP_B200_ERR_ARG;
+int agbnp_b200_synchronize(agbnp_b200* h, void* stream) {
+    if (!h) return AGBNP_B200_ERR_ARG;
     try {
         CK(cudaSetDevice(h->cfg.device));
-        cudaStream_t s = h->own_stream;
-        prepare(h, nullptr, 0, d_posq, s);
-        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
-        int rc = run_checked(h, (const float4*) d_posq, s, &sink);       // settles capacities
-        if (rc != AGBNP_B200_OK) return rc;
-        CK(cudaEventRecord(h->ev[0], s));
-        for (int i = 0; i < repeats; i++) enqueue(h, (const float4*) d_posq, s, 15, &sink, false);
-        CK(cudaEventRecord(h->ev[1], s));
-        const int status = fetch_status(h, s);
-        if (status != 0) { h->err = "agbnp_b200_time_device: capacity overflow during timing"; return AGBNP_B200_ERR_CAPACITY; }
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-        *ms_per_eval = ms/repeats;
-        h->total_evals += repeats;
+        CK(cudaStreamSynchronize((cudaStream_t) stream));
+        return async_drain(h);
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+}
+
+int agbnp_b200_profile(agbnp_b200* h, unsigned kernel_mask) {
+    if (!h) return AGBNP_B200_ERR_ARG;
+    h->prof_mask = kernel_mask;
+    h->prof_used = 0;
+    h->prof_recs.clear();
     return AGBNP_B200_OK;
 }
 
-int agbnp_b200_kernel_times(agbnp_b200* h, int repeats, const void* d_posq, float* ms_out, int max_kernels, const char** names) {
-    if (!h || !d_posq || repeats < 1 || !ms_out) return AGBNP_B200_ERR_ARG;
+int agbnp_b200_profile_read(agbnp_b200* h, double* ms_sum, int* launches, int max_kernels, const char** names) {
+    if (!h || !ms_sum || !launches) return AGBNP_B200_ERR_ARG;
     if (names) *names = kKernelNames;
     try {
         CK(cudaSetDevice(h->cfg.device));
-        cudaStream_t s = h->own_stream;
-        prepare(h, nullptr, 0, d_posq, s);
-        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
-        int rc = run_checked(h, (const float4*) d_posq, s, &sink);
-        if (rc != AGBNP_B200_OK) return rc;
-        std::vector<double> acc(K_COUNT, 0.0);
-        for (int i = 0; i < repeats; i++) {
-            enqueue(h, (const float4*) d_posq, s, 15, &sink, true);
-            CK(cudaStreamSynchronize(s));
-            for (int k = 0; k < K_COUNT; k++) {
-                float ms = 0;
-                CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k+1]));
-                acc[k] += ms;
-            }
+        CK(cudaDeviceSynchronize());
+        for (int k = 0; k < max_kernels; k++) { ms_sum[k] = 0.0; launches[k] = 0; }
+        for (const auto& r : h->prof_recs) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, h->prof_pool[r.a], h->prof_pool[r.b]));
+            if (r.id < max_kernels) { ms_sum[r.id] += ms; launches[r.id]++; }
         }
-        for (int k = 0; k < K_COUNT && k < max_kernels; k++) ms_out[k] = (float) (acc[k]/repeats);
+        h->prof_used = 0;
+        h->prof_recs.clear();
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return K_COUNT;
+}
+
+int agbnp_b200_measure_peaks(int device, double* out, int n_out) {
+    if (!out || n_out < 5) return AGBNP_B200_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return AGBNP_B200_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AGBNP_B200_ERR_CUDA;
+    cudaStream_t s; cudaEvent_t e0, e1; float* d_out = nullptr;
+    if (cudaStreamCreate(&s) != cudaSuccess) return AGBNP_B200_ERR_CUDA;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaMalloc((void**) &d_out, 64);
+    const int sm = prop.multiProcessorCount;
+    out[0] = run_peak<0>(sm, s, e0, e1, d_out);     // FFMA lanes/s
+    out[1] = run_peak<1>(sm, s, e0, e1, d_out);     // FFMA2 lanes/s
+    out[2] = run_peak<2>(sm, s, e0, e1, d_out);     // MUFU.EX2 /s
+    out[3] = run_peak<3>(sm, s, e0, e1, d_out);     // MUFU.RSQ /s
+    out[4] = run_peak<4>(sm, s, e0, e1, d_out);     // mixed instr lanes/s
+    const cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(d_out); cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+    return ce == cudaSuccess ? AGBNP_B200_OK : AGBNP_B200_ERR_CUDA;
 }
 
 int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
@@ -596,7 +736,7 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             for (int i = 0; i < n; i++) od[i] /= (-2.0*h->k.dielectric_factor);
             break;
         }
-        case AGBNP_B200_GET_DERIV_WU: need(sizeof(double)*n); per_atom_f(h->d_wu.p, od); break;
+        case AGBNP_B200_GET_DERIV_WU: need(sizeof(double)*n); per_atom_f(h->d_wu, od); break;
         case AGBNP_B200_GET_SCALARS: {
             need(sizeof(double)*8);
             double sc[SC_COUNT];
@@ -679,7 +819,8 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
 }
 
 int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* stream) {
-    if (!h || phase < 0 || phase > 2) return AGBNP_B200_ERR_ARG;
+    if (!h || phase < 0 || phase > 3) return AGBNP_B200_ERR_ARG;
+    static const int masks[4] = {PH_TREE, PH_BORN|PH_GB, PH_DERIV, PH_GAMMA};
     try {
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = (cudaStream_t) stream;
@@ -687,20 +828,18 @@ int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* s
             if (!d_posq) return AGBNP_B200_ERR_ARG;
             prepare(h, nullptr, 0, d_posq, s);
         }
-        enqueue(h, (const float4*) d_posq, s, 1 << phase, nullptr, false);
+        enqueue(h, (const float4*) d_posq, s, masks[phase], nullptr);
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
 
-int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes, int* own_begin, int* own_end) {
+int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes) {
     if (!h || !d_ptr || !bytes) return AGBNP_B200_ERR_ARG;
     if (!h->order_valid || h->params_dirty) { h->err = "agbnp_b200_shard_buffer: call shard_phase(0) first"; return AGBNP_B200_ERR_ARG; }
-    PairCommon pc = pair_common(h);
-    if (own_begin) *own_begin = pc.row_begin*TILE;
-    if (own_end) *own_end = pc.row_end*TILE;
     switch (which) {
-    case AGBNP_B200_BUF_BORN: *d_ptr = h->d_born.p; *bytes = sizeof(float)*h->np; break;
-    case AGBNP_B200_BUF_BW: *d_ptr = h->d_bw.p; *bytes = sizeof(float)*h->np; break;
+    case AGBNP_B200_BUF_SELFVOL: *d_ptr = h->d_svS; *bytes = sizeof(double)*2*h->np; break;
+    case AGBNP_B200_BUF_YQ: *d_ptr = h->d_yq; *bytes = sizeof(float)*h->np; break;
+    case AGBNP_B200_BUF_WU: *d_ptr = h->d_wu; *bytes = sizeof(float)*h->np; break;
     case AGBNP_B200_BUF_FORCE: *d_ptr = h->d_force; *bytes = sizeof(unsigned long long)*3*h->np; break;
     case AGBNP_B200_BUF_ENERGY: *d_ptr = h->d_scalars; *bytes = sizeof(double)*SC_COUNT; break;
     default: return AGBNP_B200_ERR_ARG;
@@ -715,15 +854,21 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = (cudaStream_t) stream;
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
-        enqueue(h, nullptr, s, 8, &sink, false);
-        const int status = fetch_status(h, s);
-        if (status != 0) { h->err = "agbnp_b200_shard_finish: capacity overflow (status " + std::to_string(status) + ")"; return AGBNP_B200_ERR_CAPACITY; }
-        CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (h_energy) *h_energy = h->h_scal[SC_SPARE0];
+        enqueue(h, nullptr, s, PH_FINISH, &sink);
         h->evals_since_sort++; h->total_evals++;
+        if (!h_energy) return AGBNP_B200_OK;        // asynchronous: status is checked by the next synchronous finish
+        const int status = fetch_status(h, s);
+        if (status != 0) {
+            const bool ok = grow(h, h->h_ctrl);
+            h->err = "agbnp_b200_shard_finish: capacity overflow (status " + std::to_string(status) + ")" + (ok ? "; capacities grown, re-run the evaluation" : "");
+            return AGBNP_B200_ERR_CAPACITY;
+        }
+        grow_ahead(h, h->h_ctrl);
+        *h_energy = h->h_scal[SC_SPARE0];
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
+
+long long agbnp_b200_launch_count(const agbnp_b200* h) { return h ? h->launches : -1; }
 
 } // extern "C"

@@ -101,6 +101,7 @@ struct BornArgs {
     unsigned long long* counters;
     float kdiel;                // dielectric_factor
     float hb_radius;
+    int own_row_begin, own_row_end;   // rows whose per-atom energies / counters this shard reports (the pass itself is replicated)
 };
 
 template <bool CUTOFF>
@@ -184,10 +185,12 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_born(BornArgs A) {
             A.born[a] = 1.f; A.bfp[a] = 0.f; A.vsf[a] = 0.f; A.brw[a] = 0.f;
         }
         const double es = warp_sum((double) eself), ev = warp_sum((double) evdw);
-        if (lane == 0) { atomicAdd(&A.scalars[SC_EGB], es); atomicAdd(&A.scalars[SC_EVDW], ev); }
+        if (lane == 0 && rowb >= A.own_row_begin && rowb < A.own_row_end) {
+            atomicAdd(&A.scalars[SC_EGB], es); atomicAdd(&A.scalars[SC_EVDW], ev);
+        }
     }
     npair = (unsigned long long) warp_sum((double) npair);
-    if (lane == 0 && npair) atomicAdd(&A.counters[CT_PQ], npair);
+    if (lane == 0 && npair && rowb >= A.own_row_begin && rowb < A.own_row_end) atomicAdd(&A.counters[CT_PQ], npair);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -498,12 +501,14 @@ struct FinishArgs {
     double* out_f64;                    // internal: double[3n] interleaved, = (host path)
     int padded_n;
     double* scalars;                    // SC_* terms
+    const int* status;                  // capacity-overflow bits of this evaluation: nothing is delivered unless 0
     double* energy_accum;               // optional device accumulator (+=)
     double* energy_out;                 // optional device/pinned-mapped slot (=)
 };
 
 __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (A.status && *A.status != 0) return;
     if (k == 0) {
         const double e = A.scalars[SC_EVOL_L] + A.scalars[SC_EVOL_S] + A.scalars[SC_EGB] + A.scalars[SC_EVDW];
         A.scalars[SC_SPARE0] = e;

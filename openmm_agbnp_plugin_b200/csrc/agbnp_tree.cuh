@@ -57,6 +57,8 @@ struct TreeArgs {
     TreeStore st;
     int* work_counter;
     int* status;
+    int shard_rank, shard_count;      // roots are dealt to shards block-cyclically (blocks of 32 sorted heavy atoms)
+    int *hw_nbr, *hw_nodes;           // high-water marks: level-2 neighbors / nodes of one root
 };
 
 __host__ __device__ inline size_t tree_scratch_bytes(int cap) {
@@ -139,12 +141,17 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
 
     double eL_tot = 0, eS_tot = 0, vsumL = 0, vsumS = 0;     // per-lane partial sums, reduced at the end
     unsigned long long c2_tot = 0, c3_tot = 0, m_tot = 0;
+    int hw_nn = 0, hw_slots = 0;
 
     for (;;) {
         int r = 0;
         if (lane == 0) r = atomicAdd(A.work_counter, 1);
         r = __shfl_sync(FULL, r, 0);
-        if (r >= A.nh) break;
+        if (A.shard_count > 1) {
+            r = ((r >> 5)*A.shard_count + A.shard_rank)*TILE + (r & 31);
+            if (r >= A.nhb*TILE) break;
+            if (r >= A.nh) continue;
+        } else if (r >= A.nh) break;
 
         const float4 pr = A.posq[r];
         const int orig_r = A.orig[r];
@@ -181,6 +188,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
                 nn += __popc(am);
             }
         }
+        hw_nn = max(hw_nn, nn);
         if (nn > nbrmax) {
             if (lane == 0) atomicOr(A.status, ST_NBR_OVERFLOW);
             continue;
@@ -337,6 +345,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
         if (lane == 0) lvs[level+1] = nslots;
         __syncwarp();
         const int nlev = level;
+        hw_slots = max(hw_slots, nslots);
         m_tot += (lane == 0) ? (unsigned long long) (nslots-1) : 0ull;
 
         // ---- fused bottom-up sweep for both radius sets (gaussvol.cpp:400-487) ----
@@ -441,6 +450,8 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
         atomicAdd(&A.counters[CT_C2], c2_tot);
         atomicAdd(&A.counters[CT_C3], c3_tot);
         atomicAdd(&A.counters[CT_M], m_tot);
+        atomicMax(A.hw_nbr, hw_nn);
+        atomicMax(A.hw_nodes, hw_slots);
     }
 }
 
@@ -448,14 +459,13 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
 // k_tree_gamma: S10+S11 merged -- deposit nu_i = (W_i+U_i)/V_i on the stored tree (rescan_tree_g, gaussvol.cpp:330-372),
 // run the energy-gradient up-sweep (gaussvol.cpp:400-487) and add force = -gradient
 // (ReferenceAGBNPKernels.cpp:718-747; the merge of the W and U passes is exact because the sweep is linear in nu).
-// nu_lo..nu_hi restricts nu to the atoms a shard owns (multi-GPU: partial forces are all-reduced afterwards).
+// Multi-GPU: each shard stores and sweeps only the subtrees of the roots it owns; the partial forces are all-reduced.
 // ---------------------------------------------------------------------------------------------------------------
 struct GammaArgs {
     int nh, np;
     TreeStore st;
     const float* wu;            // [np] W_i + U_i
     const double* vS;           // atomic volumes, vdW radii
-    int own_begin, own_end;     // sorted-index range of atoms whose nu is deposited
     unsigned long long* force;
     unsigned char* scratch;     // per-warp float[5*cap]: gam, f', p'x, p'y, p'z
     size_t scratch_stride;
@@ -486,8 +496,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_gamma(GammaArgs A) {
             const int b = lvs[lev], e = lev == nlev ? cnt : lvs[lev+1];
             for (int sl = b+lane; sl < e; sl += 32) {
                 const int ja = A.st.atom[off+sl];
-                float nu = 0.f;
-                if (ja >= A.own_begin && ja < A.own_end) nu = (float) ((double) A.wu[ja]/A.vS[ja]);
+                const float nu = (float) ((double) A.wu[ja]/A.vS[ja]);
                 const int p = A.st.parent[off+sl];
                 gam[sl] = (p >= 0 ? gam[p] : 0.f) + nu;
             }

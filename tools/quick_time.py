@@ -15,6 +15,7 @@ from openmm_agbnp_plugin_b200 import systems, _lib  # noqa: E402
 
 names = sys.argv[1:] or ["trpcage", "rnaseh", "2clr", "hivrt"]
 L = _lib.lib()
+REP = 50
 for nm in names:
     for method, cutoff in ((0, 1.0), (1, 1.2)):
         s = systems.load(nm)
@@ -26,19 +27,34 @@ for nm in names:
         posq = torch.zeros((n, 4), dtype=torch.float32)
         posq[:, :3] = torch.from_numpy(pos.astype(np.float32))
         d = posq.cuda()
-        ms = C.c_float(0)
-        rc = L.agbnp_b200_time_device(ctx.kernel.handle, C.c_void_p(d.data_ptr()), 50, C.byref(ms))
-        assert rc == 0, L.agbnp_b200_last_error(ctx.kernel.handle)
-        kt = (C.c_float * 16)()
-        names_p = C.c_char_p()
-        nk = L.agbnp_b200_kernel_times(ctx.kernel.handle, 20, C.c_void_p(d.data_ptr()), kt, 16, C.byref(names_p))
+        frc = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+        st = torch.cuda.current_stream()
+        h = ctx.kernel.handle
+
+        def run(k):
+            for _ in range(k):
+                rc = L.agbnp_b200_execute_device(h, d.data_ptr(), st.cuda_stream, frc.data_ptr(), 0, n, None, None)
+                assert rc == 0, L.agbnp_b200_last_error(h)
+        run(5)
+        assert L.agbnp_b200_synchronize(h, st.cuda_stream) == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); run(REP); e1.record(st)
+        assert L.agbnp_b200_synchronize(h, st.cuda_stream) == 0
+        ms = e0.elapsed_time(e1) / REP
+        L.agbnp_b200_profile(h, 0xffffffff)
+        run(20)
+        sums = (C.c_double * 16)(); cnt = (C.c_int * 16)(); names_p = C.c_char_p()
+        nk = L.agbnp_b200_profile_read(h, sums, cnt, 16, C.byref(names_p))
+        L.agbnp_b200_profile(h, 0)
         kn = names_p.value.decode().split("\n")
         t2 = time.time()
         for _ in range(20):
             ctx.calcForcesAndEnergy()
         t3 = time.time()
         sc = ctx.kernel.get("SCALARS")
+        wc = ctx.kernel.get("WORK_COUNTERS")
         print("%s N=%d method=%d E=%.4f first=%.1fms device=%.3f ms/eval host_e2e=%.3f ms/eval nodes=%d" %
-              (nm, n, method, e, (t1 - t0) * 1e3, ms.value, (t3 - t2) / 20 * 1e3, sc[7]))
-        print("   " + "  ".join("%s=%.1fus" % (kn[i], kt[i] * 1e3) for i in range(nk)))
+              (nm, n, method, e, (t1 - t0) * 1e3, ms, (t3 - t2) / 20 * 1e3, sc[7]))
+        print("   " + "  ".join("%s=%.1fus" % (kn[i], sums[i] / max(cnt[i], 1) * 1e3) for i in range(nk)))
+        print("   counters: P_gb=%.4g P_q=%.4g C2=%.4g C3=%.4g M=%.4g tiles_gb=%.4g tiles_q=%.4g" % tuple(wc[:7]))
         ctx.kernel.close()
