@@ -75,12 +75,13 @@ struct agbnp_b200 {
     DevBuf<int2> d_units;
     int nunits = 0;
     // per-evaluation arrays
-    DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in;
+    DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in, d_gbj;
     DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bw;
     DevBuf<unsigned char> d_slab;           // zeroed every evaluation
     double *d_svS = nullptr, *d_svL = nullptr, *d_scalars = nullptr;
     unsigned long long *d_force = nullptr, *d_counters = nullptr;
-    float *d_yq = nullptr, *d_wu = nullptr;
+    float4* d_gbacc = nullptr;              // GB pair force + Y per atom (zeroed slab)
+    float* d_wu = nullptr;
     int* d_root_cnt = nullptr;
     int* d_ctrl = nullptr;
     size_t slab_bytes = 0;
@@ -203,19 +204,19 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     CK(cudaStreamSynchronize(s));      // the host vectors above go out of scope
     // per-evaluation arrays
     if (h->d_posq.n < (size_t) np) {
-        h->d_posq.alloc(np); h->d_bbc.alloc(h->nb); h->d_bbh.alloc(h->nb);
+        h->d_posq.alloc(np); h->d_bbc.alloc(h->nb); h->d_bbh.alloc(h->nb); h->d_gbj.alloc((size_t) 3*np);
         h->d_vsf.alloc(np); h->d_born.alloc(np); h->d_bfp.alloc(np); h->d_brw.alloc(np); h->d_bw.alloc(np);
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o += (bytes+255)/256*256; return r; };
         const size_t o_svS = take(sizeof(double)*np), o_svL = take(sizeof(double)*np), o_force = take(sizeof(unsigned long long)*3*np);
-        const size_t o_yq = take(sizeof(float)*np), o_scal = take(sizeof(double)*SC_COUNT), o_cnt = take(sizeof(unsigned long long)*CT_COUNT);
+        const size_t o_yq = take(sizeof(float4)*np), o_scal = take(sizeof(double)*SC_COUNT), o_cnt = take(sizeof(unsigned long long)*CT_COUNT);
         const size_t o_ctrl = take(sizeof(int)*CW_COUNT);
         const size_t o_wu = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->nhp);
         h->slab_bytes = o;
         h->d_slab.alloc(o);
         unsigned char* b = h->d_slab.p;
         h->d_svS = (double*) (b+o_svS); h->d_svL = (double*) (b+o_svL); h->d_force = (unsigned long long*) (b+o_force);
-        h->d_yq = (float*) (b+o_yq); h->d_scalars = (double*) (b+o_scal); h->d_counters = (unsigned long long*) (b+o_cnt);
+        h->d_gbacc = (float4*) (b+o_yq); h->d_scalars = (double*) (b+o_scal); h->d_counters = (unsigned long long*) (b+o_cnt);
         h->d_ctrl = (int*) (b+o_ctrl);
         h->d_wu = (float*) (b+o_wu); h->d_root_cnt = (int*) (b+o_rcnt);
         h->d_root_off.alloc(h->nhp); h->d_root_lvs.alloc((size_t) h->nhp*MAX_LEVELS);
@@ -313,6 +314,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
             ba.scalars = h->d_scalars; ba.counters = h->d_counters;
             ba.kdiel = (float) h->k.dielectric_factor; ba.hb_radius = (float) h->k.hb_radius;
             ba.own_row_begin = pc.row_begin; ba.own_row_end = pc.row_end;
+            ba.gbj = h->d_gbj.p; ba.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
             const size_t sm = (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(int)+sizeof(float));
             const int rows = h->nb;
             if (rows > 0) {
@@ -325,10 +327,9 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     }
     if (v1 && (phase_mask & PH_GB)) {
         GBArgs ga{};
-        ga.c = pc; ga.born = h->d_born.p; ga.units = h->d_units.p; ga.nunits = h->nunits;
+        ga.c = pc; ga.gbj = h->d_gbj.p; ga.units = h->d_units.p; ga.nunits = h->nunits;
         ga.shard_rank = h->cfg.shard_rank; ga.shard_count = h->cfg.shard_count;
-        ga.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
-        ga.yq = h->d_yq; ga.force = h->d_force; ga.scalars = h->d_scalars; ga.counters = h->d_counters;
+        ga.gbacc = h->d_gbacc; ga.scalars = h->d_scalars; ga.counters = h->d_counters;
         ga.work_counter = h->d_ctrl+CW_WORK_GB;
         begin(K_GB);
         if (cutoff) k_gb<true><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
@@ -336,7 +337,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         end(K_GB);
     }
     if (v1 && (phase_mask & PH_DERIV)) {
-        BwArgs wa{h->np, h->d_posq.p, h->d_yq, h->d_born.p, h->d_bfp.p, h->d_brw.p, (float) h->k.dielectric_factor, h->d_bw.p};
+        BwArgs wa{h->np, h->d_posq.p, h->d_gbacc, h->d_born.p, h->d_bfp.p, h->d_brw.p, (float) h->k.dielectric_factor, h->d_bw.p,
+                  h->d_force, pc.row_begin*TILE, pc.row_end*TILE};
         begin(K_BW);
         k_bw<<<(h->np+255)/256, 256, 0, s>>>(wa);
         end(K_BW);
@@ -557,7 +559,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
         h->tree_grid = h->num_sm*2;
         h->gamma_grid = h->num_sm*4;
-        h->gb_grid = h->num_sm*3;
+        h->gb_grid = h->num_sm*4;
         set_tree_smem(h);
         const size_t tab_bytes = (size_t) h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener*I4_INTERVALS*sizeof(float4);
         const int pair_smem = (int) (tab_bytes + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4)));
@@ -732,8 +734,10 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
         case AGBNP_B200_GET_BORN_RADIUS: need(sizeof(double)*n); per_atom_f(h->d_born.p, od); break;
         case AGBNP_B200_GET_VOLUME_SCALING: need(sizeof(double)*n); per_atom_f(h->d_vsf.p, od); break;
         case AGBNP_B200_GET_DERIV_Y: {
-            need(sizeof(double)*n); per_atom_f(h->d_yq, od);
-            for (int i = 0; i < n; i++) od[i] /= (-2.0*h->k.dielectric_factor);
+            need(sizeof(double)*n);
+            std::vector<float4> t(np);
+            CK(cudaMemcpy(t.data(), h->d_gbacc, sizeof(float4)*np, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) od[h->orig[k]] = t[k].w/(-2.0*h->k.dielectric_factor);
             break;
         }
         case AGBNP_B200_GET_DERIV_WU: need(sizeof(double)*n); per_atom_f(h->d_wu, od); break;
@@ -838,7 +842,7 @@ int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* byte
     if (!h->order_valid || h->params_dirty) { h->err = "agbnp_b200_shard_buffer: call shard_phase(0) first"; return AGBNP_B200_ERR_ARG; }
     switch (which) {
     case AGBNP_B200_BUF_SELFVOL: *d_ptr = h->d_svS; *bytes = sizeof(double)*2*h->np; break;
-    case AGBNP_B200_BUF_YQ: *d_ptr = h->d_yq; *bytes = sizeof(float)*h->np; break;
+    case AGBNP_B200_BUF_YQ: *d_ptr = h->d_gbacc; *bytes = sizeof(float4)*h->np; break;
     case AGBNP_B200_BUF_WU: *d_ptr = h->d_wu; *bytes = sizeof(float)*h->np; break;
     case AGBNP_B200_BUF_FORCE: *d_ptr = h->d_force; *bytes = sizeof(unsigned long long)*3*h->np; break;
     case AGBNP_B200_BUF_ENERGY: *d_ptr = h->d_scalars; *bytes = sizeof(double)*SC_COUNT; break;

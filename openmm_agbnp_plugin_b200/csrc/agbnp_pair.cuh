@@ -16,7 +16,7 @@ namespace agbnp_b200_impl {
 constexpr int PAIR_THREADS = 256;       // Born / derivative kernels: 8 warps share one row block
 constexpr int PAIR_WARPS = PAIR_THREADS/32;
 constexpr int GB_THREADS = 128;
-constexpr int GB_CHUNK = 16;            // column tiles per GB work unit
+constexpr int GB_CHUNK = 8;             // column tiles per GB work unit
 constexpr int I4_INTERVALS = 15;        // AGBNP_I4LOOKUP_NA - 1
 constexpr float PIFAC = 0.07957747154594767f;   // 1/(4 pi)
 
@@ -97,6 +97,8 @@ struct BornArgs {
     float* born;                // out: B_i
     float* bfp;                 // out: d swf / d beta
     float* brw;                 // out
+    float4* gbj;                // out [3*np]: GB atom records in broadcast form (see k_gb)
+    float qscale;               // sqrt(-2k)
     double* scalars;
     unsigned long long* counters;
     float kdiel;                // dielectric_factor
@@ -184,6 +186,14 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_born(BornArgs A) {
         } else {
             A.born[a] = 1.f; A.bfp[a] = 0.f; A.vsf[a] = 0.f; A.brw[a] = 0.f;
         }
+        {
+            const float br = A.born[a];
+            const float qs = pa.w*A.qscale, ib = 0.60056120439322491f/br;   // sqrt(log2(e)/4)/B
+            float4* rec = A.gbj + 3*(size_t) a;
+            rec[0] = make_float4(pa.x, pa.x, pa.y, pa.y);
+            rec[1] = make_float4(pa.z, pa.z, qs, qs);
+            rec[2] = make_float4(br, br, ib, ib);
+        }
         const double es = warp_sum((double) eself), ev = warp_sum((double) evdw);
         if (lane == 0 && rowb >= A.own_row_begin && rowb < A.own_row_end) {
             atomicAdd(&A.scalars[SC_EGB], es); atomicAdd(&A.scalars[SC_EVDW], ev);
@@ -195,37 +205,123 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_born(BornArgs A) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_gb: GB pair energy, direct force and Y accumulators over symmetric 32x32 tiles
-// (ReferenceAGBNPKernels.cpp:476-498).  Charges are pre-scaled by sqrt(-2k) so that q_i q_j carries the GB prefactor.
+// (ReferenceAGBNPKernels.cpp:476-498), in packed FP32x2 arithmetic (fma.rn.f32x2 -> FFMA2 on sm_100a).
+//
+// The pass is bound by FP32 issue: one pair costs 27 FP32 operations + 2 MUFU (ex2, rsqrt).  Scalar code spends an
+// issue slot per operation; here every arithmetic instruction handles the pairs (i0,j) and (i1,j) of two row atoms at
+// once, which halves the issue slots of the FP32 part and leaves the FMA pipe itself as the limit.
+//   lane grid 4 (li) x 8 (lj): a lane owns 8 row atoms (4 packed pairs) for a whole work unit and 4 column atoms per
+//   tile; column atoms come from `gbj`, written by the Born kernel in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib}
+//   so that three 16-byte loads land directly in aligned register pairs;
+//   column-side sums are reduce-scattered over the 4 lanes that share them (12 shuffles per tile) and leave as ONE
+//   vector atomic (red.global.add.v4.f32) per lane and tile; row-side sums are flushed once per work unit.
+// Charges are pre-scaled by sqrt(-2k), so q_i q_j carries the GB prefactor; ib = sqrt(log2(e)/4)/B, so that
+// exp(-d2/(4 B_i B_j)) = ex2(-d2 ib_i ib_j).
 // ---------------------------------------------------------------------------------------------------------------
 struct GBArgs {
     PairCommon c;
-    const float* born;
-    const int2* units;          // (row block, first column block); NoCutoff: precomputed triangular cover
+    const float4* gbj;          // [3*np] broadcast-form GB atom records
+    const int2* units;          // (row block, first column block): triangular cover in chunks of GB_CHUNK column tiles
     int nunits;
     int shard_rank, shard_count;
-    float qscale;               // sqrt(-2k)
-    float* yq;                  // out: sum_j (-2k q_i q_j)(bb + d2/4) e f^3
-    unsigned long long* force;
+    float4* gbacc;              // out [np]: fx, fy, fz (GB pair force), Y_i*(-2k)
     double* scalars;
     unsigned long long* counters;
     int* work_counter;
 };
 
-struct GBAtom { float x, y, z, q, b, ib; };
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-__device__ __forceinline__ GBAtom gb_load(const float4* posq, const float* born, int idx, float qscale) {
-    const float4 p = posq[idx];
-    const float b = born[idx];
-    GBAtom r;
-    r.x = p.x; r.y = p.y; r.z = p.z; r.q = p.w*qscale; r.b = b;
-    r.ib = 0.60056120439322491f/b;        // sqrt(0.25*log2(e))/B : ib_i*ib_j*d2 = d2/(4 B_i B_j) in base-2 exponent units
-    return r;
+// one 32x32 tile: 4 column atoms x 4 packed row pairs per lane
+template <bool CUTOFF, bool DIAG>
+__device__ __forceinline__ void gb_tile(const GBArgs& A, int cb, int li, int lj,
+                                        const float2 (&nx)[4], const float2 (&ny)[4], const float2 (&nz)[4],
+                                        const float2 (&qi)[4], const float2 (&bi)[4], const float2 (&nib)[4],
+                                        float2 (&fi)[4][4], float2& e2, unsigned& npair) {
+    const float2 m025 = make_float2(-0.25f, -0.25f), p025 = make_float2(0.25f, 0.25f);
+    const float2 half = make_float2(-0.5f, -0.5f), three_half = make_float2(1.5f, 1.5f);
+    const float2 cut2 = make_float2(A.c.cut2, A.c.cut2);
+    float sj[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        const int jl = lj*4 + n;                                  // column atom within the tile
+        const float4* rec = A.gbj + 3*(size_t) (cb*TILE + jl);
+        const float4 r0 = __ldg(rec), r1 = __ldg(rec+1), r2 = __ldg(rec+2);
+        const float2 xj = make_float2(r0.x, r0.y), yj = make_float2(r0.z, r0.w), zj = make_float2(r1.x, r1.y);
+        const float2 qj = make_float2(r1.z, r1.w), bj = make_float2(r2.x, r2.y), ibj = make_float2(r2.z, r2.w);
+        float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax, aY = ax;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const float2 dx = __fadd2_rn(xj, nx[m]), dy = __fadd2_rn(yj, ny[m]), dz = __fadd2_rn(zj, nz[m]);
+            float2 d2;
+            if (CUTOFF) d2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));   // membership rule: no contraction
+            else d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            const float2 bb = __fmul2_rn(bi[m], bj);
+            const float2 arg = __fmul2_rn(d2, __fmul2_rn(nib[m], ibj));
+            const float2 et = make_float2(fast_ex2(arg.x), fast_ex2(arg.y));
+            const float2 t = __ffma2_rn(bb, et, d2);
+            const float2 f = make_float2(fast_rsqrt(t.x), fast_rsqrt(t.y));
+            float2 qq = __fmul2_rn(qi[m], qj);
+            if (DIAG) {                                           // pairs i < j only (also removes i == j)
+                const int i0 = li*8 + 2*m;
+                qq.x = i0 < jl ? qq.x : 0.f;
+                qq.y = i0+1 < jl ? qq.y : 0.f;
+            }
+            if (CUTOFF) {
+                const bool k0 = d2.x < cut2.x, k1 = d2.y < cut2.y;
+                qq.x = k0 ? qq.x : 0.f;
+                qq.y = k1 ? qq.y : 0.f;
+                if (DIAG) npair += (k0 && li*8 + 2*m < jl) + (k1 && li*8 + 2*m+1 < jl);
+                else npair += (unsigned) k0 + (unsigned) k1;
+            }
+            const float2 qf = __fmul2_rn(qq, f);
+            const float2 ff = __fmul2_rn(f, f);
+            // energy with one Newton step on the reciprocal square root: f (3/2 - t f^2 / 2); MUFU.RSQ alone carries a
+            // ~4e-7 mean relative bias that the 1e8-term pair sum does not average out
+            const float2 corr = __ffma2_rn(__fmul2_rn(t, ff), half, three_half);
+            e2 = __ffma2_rn(qf, corr, e2);
+            const float2 g = __fmul2_rn(qf, ff);
+            const float2 hh = __fmul2_rn(g, et);
+            const float2 mw = __ffma2_rn(m025, hh, g);            // -2 k q_i q_j (1 - e/4) f^3
+            const float2 yt = __fmul2_rn(hh, __ffma2_rn(p025, d2, bb));
+            fi[m][0] = __ffma2_rn(dx, mw, fi[m][0]); fi[m][1] = __ffma2_rn(dy, mw, fi[m][1]); fi[m][2] = __ffma2_rn(dz, mw, fi[m][2]);
+            fi[m][3] = __fadd2_rn(fi[m][3], yt);
+            ax = __ffma2_rn(dx, mw, ax); ay = __ffma2_rn(dy, mw, ay); az = __ffma2_rn(dz, mw, az);
+            aY = __fadd2_rn(aY, yt);
+        }
+        sj[n][0] = -(ax.x+ax.y); sj[n][1] = -(ay.x+ay.y); sj[n][2] = -(az.x+az.y); sj[n][3] = aY.x+aY.y;
+    }
+    // reduce-scatter the column-side sums over the 4 lanes sharing lj (lane bits 3,4): 8 + 4 shuffles, after which
+    // lane (li,lj) owns column atom lj*4 + li
+    float h2[2][4], h1[4];
+    {
+        const bool up = li & 2;
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float send = up ? sj[n][c] : sj[n+2][c];
+                const float keep = up ? sj[n+2][c] : sj[n][c];
+                h2[n][c] = keep + __shfl_xor_sync(FULL, send, 16);
+            }
+    }
+    {
+        const bool up = li & 1;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float send = up ? h2[0][c] : h2[1][c];
+            const float keep = up ? h2[1][c] : h2[0][c];
+            h1[c] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+    }
+    atomicAdd(&A.gbacc[cb*TILE + lj*4 + li], make_float4(h1[0], h1[1], h1[2], h1[3]));
 }
 
 template <bool CUTOFF>
-__global__ void __launch_bounds__(GB_THREADS) k_gb(GBArgs A) {
+__global__ void __launch_bounds__(GB_THREADS, 3) k_gb(GBArgs A) {
     const int lane = threadIdx.x & 31;
-    const int li = lane >> 2, lj = lane & 3;          // 8 x 4 lane grid: 4 i-atoms (li*4..) x 8 j-atoms (lj*8..) per lane
+    const int li = lane >> 3, lj = lane & 7;
     double e_acc = 0.0;
     unsigned long long npair = 0, ntile = 0;
     for (;;) {
@@ -237,125 +333,70 @@ __global__ void __launch_bounds__(GB_THREADS) k_gb(GBArgs A) {
         const int2 un = A.units[u];
         const int ra = un.x;
         const int cend = min(un.y+GB_CHUNK, A.c.nb);
-        GBAtom ai[4];
-        float fi[4][4];                                // fx, fy, fz, Y per i-atom
+        // row atoms: 4 packed pairs (even atom in .x, odd atom in .y); positions negated, ib negated
+        float2 nx[4], ny[4], nz[4], qi[4], bi[4], nib[4], fi[4][4];
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-            ai[m] = gb_load(A.c.posq, A.born, ra*TILE + li*4+m, A.qscale);
-            fi[m][0] = fi[m][1] = fi[m][2] = fi[m][3] = 0.f;
+            const float4* r = A.gbj + 3*(size_t) (ra*TILE + li*8 + 2*m);
+            const float4 a0 = __ldg(r), a1 = __ldg(r+1), a2 = __ldg(r+2), b0 = __ldg(r+3), b1 = __ldg(r+4), b2 = __ldg(r+5);
+            nx[m] = make_float2(-a0.x, -b0.x); ny[m] = make_float2(-a0.z, -b0.z); nz[m] = make_float2(-a1.x, -b1.x);
+            qi[m] = make_float2(a1.z, b1.z); bi[m] = make_float2(a2.x, b2.x); nib[m] = make_float2(-a2.z, -b2.z);
+#pragma unroll
+            for (int c = 0; c < 4; c++) fi[m][c] = make_float2(0.f, 0.f);
         }
         const float4 ca = A.c.bbc[ra], ha = A.c.bbh[ra];
+        float2 e2 = make_float2(0.f, 0.f);
+        unsigned np32 = 0;
         for (int cb = un.y; cb < cend; cb++) {
             if (CUTOFF && box_box_dist2(ca, ha, A.c.bbc[cb], A.c.bbh[cb]) >= A.c.cut2) continue;
             ntile++;
-            const bool diag = cb == ra;
-            float fj[8][4];
-            float e_tile = 0.f;
-#pragma unroll
-            for (int n = 0; n < 8; n++) {
-                const GBAtom aj = gb_load(A.c.posq, A.born, cb*TILE + lj*8+n, A.qscale);
-                fj[n][0] = fj[n][1] = fj[n][2] = fj[n][3] = 0.f;
-#pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const float dx = aj.x-ai[m].x, dy = aj.y-ai[m].y, dz = aj.z-ai[m].z;
-                    float d2;
-                    bool ok = true;
-                    if (CUTOFF) { d2 = dist2_exact(dx, dy, dz); ok = d2 < A.c.cut2; }
-                    else d2 = dx*dx + dy*dy + dz*dz;
-                    if (diag) ok = ok && (li*4+m < lj*8+n);
-                    const float bb = ai[m].b*aj.b;
-                    const float et = exp2f(-d2*(ai[m].ib*aj.ib));
-                    const float fgb = rsqrtf(fmaf(bb, et, d2));
-                    float qq = ai[m].q*aj.q;                      // -2k q_i q_j
-                    if (CUTOFF || diag) qq = ok ? qq : 0.f;
-                    e_tile = fmaf(qq, fgb, e_tile);               // -(pair energy)
-                    const float f3 = fgb*fgb*fgb;
-                    const float qf3 = qq*f3;
-                    const float mw = qf3*fmaf(-0.25f, et, 1.f);   // = -2 k q_i q_j (1 - e/4) f^3 with the sign folded
-                    fi[m][0] = fmaf(dx, mw, fi[m][0]); fi[m][1] = fmaf(dy, mw, fi[m][1]); fi[m][2] = fmaf(dz, mw, fi[m][2]);
-                    fj[n][0] = fmaf(-dx, mw, fj[n][0]); fj[n][1] = fmaf(-dy, mw, fj[n][1]); fj[n][2] = fmaf(-dz, mw, fj[n][2]);
-                    const float yt = qf3*et*fmaf(0.25f, d2, bb);
-                    fi[m][3] += yt; fj[n][3] += yt;
-                    if (CUTOFF || diag) npair += ok ? 1 : 0;
-                }
+            if (cb == ra) gb_tile<CUTOFF, true>(A, cb, li, lj, nx, ny, nz, qi, bi, nib, fi, e2, np32);
+            else {
+                gb_tile<CUTOFF, false>(A, cb, li, lj, nx, ny, nz, qi, bi, nib, fi, e2, np32);
+                if (!CUTOFF) np32 += 32;
             }
-            if (!CUTOFF && !diag) npair += 32;
-            e_acc += (double) e_tile;
-            // reduce-scatter the j-side partial sums over the 8 lanes sharing lj: 16 + 8 + 4 shuffles, after which
-            // lane (li,lj) owns the 4 sums of j-atom lj*8+li
-            float h4[4][4], h2[2][4], h1[4];
-            {
-                const bool up = li & 4;
+            if (!CUTOFF && cb == ra && lane < 16) np32 += 31;      // 496 = 16*31 pairs in a diagonal tile
+        }
+        e_acc += (double) e2.x + (double) e2.y;
+        npair += np32;
+        // row side: reduce-scatter over the 8 lanes sharing li (lane bits 0..2): 16 + 8 + 4 shuffles; lane (li,lj) ends
+        // with row atom li*8 + lj
+        float v4[4][4], v2[2][4], v1[4];
+        {
+            const bool up = lj & 4;
 #pragma unroll
-                for (int n = 0; n < 4; n++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const float send = up ? fj[n][c] : fj[n+4][c];
-                        const float keep = up ? fj[n+4][c] : fj[n][c];
-                        h4[n][c] = keep + __shfl_xor_sync(FULL, send, 16);
-                    }
-            }
-            {
-                const bool up = li & 2;
-#pragma unroll
-                for (int n = 0; n < 2; n++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const float send = up ? h4[n][c] : h4[n+2][c];
-                        const float keep = up ? h4[n+2][c] : h4[n][c];
-                        h2[n][c] = keep + __shfl_xor_sync(FULL, send, 8);
-                    }
-            }
-            {
-                const bool up = li & 1;
+            for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    const float send = up ? h2[0][c] : h2[1][c];
-                    const float keep = up ? h2[1][c] : h2[0][c];
-                    h1[c] = keep + __shfl_xor_sync(FULL, send, 4);
+                    // atom a (0..3) and atom a+4: pair index a>>1 / (a+4)>>1, half a&1
+                    const float lo = (a & 1) ? fi[a >> 1][c].y : fi[a >> 1][c].x;
+                    const float hi = (a & 1) ? fi[(a+4) >> 1][c].y : fi[(a+4) >> 1][c].x;
+                    const float send = up ? lo : hi;
+                    const float keep = up ? hi : lo;
+                    v4[a][c] = keep + __shfl_xor_sync(FULL, send, 4);
                 }
-            }
-            {
-                const int j = cb*TILE + lj*8 + li;      // bits of li select 4/2/1 -> atom index li within the lj group
-                if (h1[0] != 0.f || h1[1] != 0.f || h1[2] != 0.f) {
-                    add_force_fixed(&A.force[j], h1[0]);
-                    add_force_fixed(&A.force[(size_t) A.c.np+j], h1[1]);
-                    add_force_fixed(&A.force[2*(size_t) A.c.np+j], h1[2]);
-                }
-                if (h1[3] != 0.f) atomicAdd(&A.yq[j], h1[3]);
-            }
         }
-        // i-side: reduce-scatter over the 4 lanes sharing li (8 + 4 shuffles); lane (li,lj) ends with i-atom li*4+lj
-        float g2[2][4], g1[4];
         {
             const bool up = lj & 2;
 #pragma unroll
-            for (int m = 0; m < 2; m++)
+            for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    const float send = up ? fi[m][c] : fi[m+2][c];
-                    const float keep = up ? fi[m+2][c] : fi[m][c];
-                    g2[m][c] = keep + __shfl_xor_sync(FULL, send, 2);
+                    const float send = up ? v4[a][c] : v4[a+2][c];
+                    const float keep = up ? v4[a+2][c] : v4[a][c];
+                    v2[a][c] = keep + __shfl_xor_sync(FULL, send, 2);
                 }
         }
         {
             const bool up = lj & 1;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const float send = up ? g2[0][c] : g2[1][c];
-                const float keep = up ? g2[1][c] : g2[0][c];
-                g1[c] = keep + __shfl_xor_sync(FULL, send, 1);
+                const float send = up ? v2[0][c] : v2[1][c];
+                const float keep = up ? v2[1][c] : v2[0][c];
+                v1[c] = keep + __shfl_xor_sync(FULL, send, 1);
             }
         }
-        {
-            const int i = ra*TILE + li*4 + lj;
-            if (g1[0] != 0.f || g1[1] != 0.f || g1[2] != 0.f) {
-                add_force_fixed(&A.force[i], g1[0]);
-                add_force_fixed(&A.force[(size_t) A.c.np+i], g1[1]);
-                add_force_fixed(&A.force[2*(size_t) A.c.np+i], g1[2]);
-            }
-            if (g1[3] != 0.f) atomicAdd(&A.yq[i], g1[3]);
-        }
+        atomicAdd(&A.gbacc[ra*TILE + li*8 + lj], make_float4(v1[0], v1[1], v1[2], v1[3]));
     }
     e_acc = warp_sum(e_acc);
     npair = (unsigned long long) warp_sum((double) npair);
@@ -367,22 +408,33 @@ __global__ void __launch_bounds__(GB_THREADS) k_gb(GBArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_bw: bw_i = brw_i + bru_i, bru_i = -(k/4pi)(q_i^2 + Y_i B_i) fp_i   (ReferenceAGBNPKernels.cpp:537-542)
+// k_bw: bw_i = brw_i + bru_i, bru_i = -(k/4pi)(q_i^2 + Y_i B_i) fp_i   (ReferenceAGBNPKernels.cpp:537-542); folds the
+// GB pair force of the atoms this shard reports into the fixed-point force accumulator
 // ---------------------------------------------------------------------------------------------------------------
 struct BwArgs {
     int np;
     const float4* posq;
-    const float *yq, *born, *bfp, *brw;
+    const float4* gbacc;
+    const float *born, *bfp, *brw;
     float kdiel;
     float* bw;
+    unsigned long long* force;
+    int own_begin, own_end;     // sorted-index range whose GB force this shard adds (gbacc is all-reduced before)
 };
 
 __global__ void __launch_bounds__(256) k_bw(BwArgs A) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= A.np) return;
     const float q = A.posq[i].w;
-    const float y = A.yq[i]/(-2.f*A.kdiel);
+    const float4 g = A.gbacc[i];
+    const float y = g.w/(-2.f*A.kdiel);
     A.bw[i] = A.brw[i] - PIFAC*A.kdiel*(q*q + y*A.born[i])*A.bfp[i];
+    if (i >= A.own_begin && i < A.own_end) {
+        // the only writer of these entries at this point of the stream: plain read-modify-write
+        A.force[i] += (unsigned long long) (long long) (g.x*4294967296.0f);
+        A.force[(size_t) A.np+i] += (unsigned long long) (long long) (g.y*4294967296.0f);
+        A.force[2*(size_t) A.np+i] += (unsigned long long) (long long) (g.z*4294967296.0f);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
