@@ -44,11 +44,11 @@ template <class T> struct DevBuf {
     ~DevBuf() { release(); }
 };
 
-enum KernelId { K_ZERO = 0, K_PREP, K_TREE, K_BORN, K_GB, K_BW, K_DERIV, K_GAMMA, K_FINISH, K_COUNT };
-const char* const kKernelNames = "memset_accum\nk_prep\nk_tree\nk_born\nk_gb\nk_bw\nk_deriv\nk_tree_gamma\nk_finish";
+enum KernelId { K_ZERO = 0, K_PREP, K_TREE, K_BORN, K_GB, K_BW, K_DERIV, K_GAMMA, K_FINISH, K_BORNFIN, K_COUNT };
+const char* const kKernelNames = "memset_accum\nk_prep\nk_tree\nk_born\nk_gb\nk_bw\nk_deriv\nk_tree_gamma\nk_finish\nk_born_finish";
 
 // control words inside the zeroed slab
-enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_MAX_NBR, CW_MAX_NODES, CW_COUNT = 8 };
+enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_MAX_NBR, CW_MAX_NODES, CW_WORK_BORN, CW_WORK_DERIV, CW_COUNT = 12 };
 
 } // namespace
 
@@ -63,6 +63,7 @@ struct agbnp_b200 {
     bool params_dirty = true, order_valid = false;
     long long evals_since_sort = 0, total_evals = 0;
     std::vector<int> orig;                  // sorted -> caller (size np, -1 padding)
+    std::vector<float> box_lo, box_hi;      // block bounding boxes at sort time (host; unit ordering only)
 
     // static sorted arrays
     DevBuf<int> d_orig;
@@ -71,9 +72,9 @@ struct agbnp_b200 {
     DevBuf<unsigned char> d_rcbin, d_ts;
     DevBuf<signed char> d_tj;
     DevBuf<float> d_rc2, d_rc2max;
-    DevBuf<float4> d_i4;
-    DevBuf<int2> d_units;
-    int nunits = 0;
+    DevBuf<float4> d_i4v, d_i4d;
+    DevBuf<int2> d_units, d_pq_units;
+    int nunits = 0, npq_units = 0;
     // per-evaluation arrays
     DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in, d_gbj;
     DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bw;
@@ -81,14 +82,15 @@ struct agbnp_b200 {
     double *d_svS = nullptr, *d_svL = nullptr, *d_scalars = nullptr;
     unsigned long long *d_force = nullptr, *d_counters = nullptr;
     float4* d_gbacc = nullptr;              // GB pair force + Y per atom (zeroed slab)
-    float* d_wu = nullptr;
+    float4* d_dacc = nullptr;               // derivative-pass force + (W+U) per atom (zeroed slab)
+    float* d_bsum = nullptr;                // Born-radius pair sums (zeroed slab)
     int* d_root_cnt = nullptr;
     int* d_ctrl = nullptr;
     size_t slab_bytes = 0;
     DevBuf<double> d_force_out;             // double[3n] for the host path
     // tree
     int tree_cap = 768, nbrmax = 128;
-    int tree_grid = 0, gamma_grid = 0, gb_grid = 0;
+    int tree_grid = 0, gamma_grid = 0, gb_grid = 0, pq_grid = 0;
     DevBuf<unsigned char> d_tree_scratch, d_gamma_scratch;
     TreeStore st{};
     DevBuf<int> d_root_off, d_st_atom;
@@ -167,6 +169,50 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
     h->params_dirty = true;
     h->evals_since_sort = 0;
     (void) s;
+    // block bounding boxes at sort time: used only to ORDER and PACK the work units of the range-limited pair passes
+    // (heaviest first, far-apart block pairs packed several per unit); membership is decided on the device every evaluation
+    h->box_lo.assign((size_t) 3*h->nb, 3.0e38f); h->box_hi.assign((size_t) 3*h->nb, -3.0e38f);
+    for (int k = 0; k < h->np; k++) {
+        const int o = h->orig[k];
+        if (o < 0) continue;
+        for (int c = 0; c < 3; c++) {
+            const float v = xyz[(size_t) o*stride+c];
+            float& lo = h->box_lo[(size_t) 3*(k/TILE)+c]; float& hi = h->box_hi[(size_t) 3*(k/TILE)+c];
+            lo = std::min(lo, v); hi = std::max(hi, v);
+        }
+    }
+}
+
+// work units of k_born / k_deriv: (row block, first column block | count << 20), see agbnp_pair.cuh
+void build_pq_units(agbnp_b200* h, std::vector<int2>& out) {
+    const bool cutoff = h->cfg.nonbonded_method == AGBNP_B200_CUTOFF_NONPERIODIC;
+    const double lim = cutoff ? std::min(h->k.i4_maxa, h->cfg.cutoff) : h->k.i4_maxa;
+    struct U { int ra, cb0, n; float cost; };
+    std::vector<U> us;
+    auto box_dist = [&](int a, int b) {
+        double d2 = 0;
+        for (int c = 0; c < 3; c++) {
+            const double g = std::max(0.0, std::max((double) h->box_lo[3*a+c]-h->box_hi[3*b+c], (double) h->box_lo[3*b+c]-h->box_hi[3*a+c]));
+            d2 += g*g;
+        }
+        return std::sqrt(d2);
+    };
+    for (int ra = 0; ra < h->nb; ra++) {
+        U cur{ra, 0, 0, 0.f};
+        for (int cb = ra < h->nhb ? ra : 0; cb < h->nhb; cb++) {
+            const double d = box_dist(ra, cb);
+            double f = std::min(1.0, std::max(0.0, (lim-d)/1.0 + 0.3));
+            float cost = 0.02f + (float) (f*f)*((ra < h->nhb && cb != ra) ? 2.f : 1.f);
+            if (!(d < 1e30)) cost = 0.02f;                  // a block of padding only
+            if (cur.n == 0) cur.cb0 = cb;
+            cur.n++; cur.cost += cost;
+            if (cur.cost >= 1.0f || cur.n == PQ_CHUNK) { us.push_back(cur); cur.n = 0; cur.cost = 0.f; }
+        }
+        if (cur.n) us.push_back(cur);
+    }
+    std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+    out.clear();
+    for (const U& u : us) out.push_back(make_int2(u.ra, u.cb0 | (u.n << 20)));
 }
 
 void upload_static(agbnp_b200* h, cudaStream_t s) {
@@ -191,16 +237,32 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s);
     h->d_rcbin.upload(rcbin, s); h->d_ts.upload(ts, s); h->d_tj.upload(tj, s);
     h->d_rc2.upload(sp.rc2, s); h->d_rc2max.upload(sp.rc2max, s);
-    std::vector<float4> i4(sp.i4.packed.size()/4);
-    for (size_t i = 0; i < i4.size(); i++)
-        i4[i] = make_float4(sp.i4.packed[4*i], sp.i4.packed[4*i+1], sp.i4.packed[4*i+2], sp.i4.packed[4*i+3]);
-    h->d_i4.upload(i4, s);
+    // I4 splines in power form around the left knot (see agbnp_pair.cuh): with zl = y2_k h^2/6, zu = y2_{k+1} h^2/6,
+    //   y(fr) = yl + fr [(yu-yl) - 2 zl - zu] + fr^2 [3 zl] + fr^3 [zu - zl]
+    {
+        const I4Tables& t = sp.i4;
+        const int ntab = t.ntypes_screened*t.ntypes_screener, ni = t.nodes-1;
+        std::vector<float4> tv((size_t) ntab*ni), td((size_t) ntab*ni);
+        for (int tb = 0; tb < ntab; tb++) for (int k = 0; k < ni; k++) {
+            const double yl = t.y[(size_t) tb*t.nodes+k], yu = t.y[(size_t) tb*t.nodes+k+1];
+            const double zl = t.y2[(size_t) tb*t.nodes+k]*t.h*t.h/6.0, zu = t.y2[(size_t) tb*t.nodes+k+1]*t.h*t.h/6.0;
+            const double v0 = yl, v1 = (yu-yl) - 2.0*zl - zu, v2 = 3.0*zl, v3 = zu-zl;
+            tv[(size_t) tb*ni+k] = make_float4((float) v0, (float) v1, (float) v2, (float) v3);
+            td[(size_t) tb*ni+k] = make_float4((float) (v1/t.h), (float) (2.0*v2/t.h), (float) (3.0*v3/t.h), 0.f);
+        }
+        h->d_i4v.upload(tv, s); h->d_i4d.upload(td, s);
+    }
     // GB work units: triangular cover of the block-pair matrix in chunks of GB_CHUNK column tiles
     std::vector<int2> units;
     for (int ra = 0; ra < h->nb; ra++)
         for (int c = ra; c < h->nb; c += GB_CHUNK) units.push_back(make_int2(ra, c));
     h->nunits = (int) units.size();
     h->d_units.upload(units, s);
+    // range-limited pair passes: heavy rows x heavy columns cb >= ra, then hydrogen rows x heavy columns (agbnp_pair.cuh)
+    std::vector<int2> pq;
+    build_pq_units(h, pq);
+    h->npq_units = (int) pq.size();
+    h->d_pq_units.upload(pq, s);
     CK(cudaStreamSynchronize(s));      // the host vectors above go out of scope
     // per-evaluation arrays
     if (h->d_posq.n < (size_t) np) {
@@ -211,14 +273,14 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         const size_t o_svS = take(sizeof(double)*np), o_svL = take(sizeof(double)*np), o_force = take(sizeof(unsigned long long)*3*np);
         const size_t o_yq = take(sizeof(float4)*np), o_scal = take(sizeof(double)*SC_COUNT), o_cnt = take(sizeof(unsigned long long)*CT_COUNT);
         const size_t o_ctrl = take(sizeof(int)*CW_COUNT);
-        const size_t o_wu = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->nhp);
+        const size_t o_dacc = take(sizeof(float4)*np), o_bsum = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->nhp);
         h->slab_bytes = o;
         h->d_slab.alloc(o);
         unsigned char* b = h->d_slab.p;
         h->d_svS = (double*) (b+o_svS); h->d_svL = (double*) (b+o_svL); h->d_force = (unsigned long long*) (b+o_force);
         h->d_gbacc = (float4*) (b+o_yq); h->d_scalars = (double*) (b+o_scal); h->d_counters = (unsigned long long*) (b+o_cnt);
         h->d_ctrl = (int*) (b+o_ctrl);
-        h->d_wu = (float*) (b+o_wu); h->d_root_cnt = (int*) (b+o_rcnt);
+        h->d_dacc = (float4*) (b+o_dacc); h->d_bsum = (float*) (b+o_bsum); h->d_root_cnt = (int*) (b+o_rcnt);
         h->d_root_off.alloc(h->nhp); h->d_root_lvs.alloc((size_t) h->nhp*MAX_LEVELS);
         if (h->st.cap == 0) alloc_store(h, std::max(4096, 160*h->nh + 4096));
         else alloc_store(h, h->st.cap);
@@ -230,9 +292,10 @@ PairCommon pair_common(agbnp_b200* h) {
     PairCommon c;
     c.np = h->np; c.nhb = h->nhb; c.nb = h->nb;
     c.posq = h->d_posq.p; c.orig = h->d_orig.p; c.bbc = h->d_bbc.p; c.bbh = h->d_bbh.p;
-    c.ts = h->d_ts.p; c.tj = h->d_tj.p; c.i4 = h->d_i4.p;
+    c.ts = h->d_ts.p; c.tj = h->d_tj.p; c.i4v = h->d_i4v.p; c.i4d = h->d_i4d.p;
     c.ntj = h->sp.i4.ntypes_screener;
     c.ntables = h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener;
+    c.tab_smem = (size_t) c.ntables*I4_INTERVALS*sizeof(float4) <= 24*1024;     // both tables + atom staging stay under 64 KB
     c.inv_h = (float) (1.0/h->sp.i4.h);
     c.range2 = (float) (h->k.i4_maxa*h->k.i4_maxa);
     const float cut = (float) h->cfg.cutoff;
@@ -304,26 +367,28 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         k_tree<<<h->tree_grid, TREE_THREADS, smem, s>>>(ta);
         end(K_TREE);
     }
-    if (phase_mask & PH_BORN) {
-        if (v1) {
-            BornArgs ba{};
-            // the Born pass is replicated on every shard (cheap; saves an exchange)
-            ba.c = pc; ba.c.row_begin = 0; ba.c.row_end = h->nb;
-            ba.svS = h->d_svS; ba.vS = h->d_vS.p; ba.radius = h->d_radius.p; ba.alpha = h->d_alpha.p;
-            ba.vsf = h->d_vsf.p; ba.born = h->d_born.p; ba.bfp = h->d_bfp.p; ba.brw = h->d_brw.p;
-            ba.scalars = h->d_scalars; ba.counters = h->d_counters;
-            ba.kdiel = (float) h->k.dielectric_factor; ba.hb_radius = (float) h->k.hb_radius;
-            ba.own_row_begin = pc.row_begin; ba.own_row_end = pc.row_end;
-            ba.gbj = h->d_gbj.p; ba.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
-            const size_t sm = (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(int)+sizeof(float));
-            const int rows = h->nb;
-            if (rows > 0) {
-                begin(K_BORN);
-                if (cutoff) k_born<true><<<rows, PAIR_THREADS, sm, s>>>(ba);
-                else k_born<false><<<rows, PAIR_THREADS, sm, s>>>(ba);
-                end(K_BORN);
-            }
-        }
+    const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
+    if (v1 && (phase_mask & PH_BORN)) {
+        // the Born pass is replicated on every shard (cheap; saves an exchange)
+        BornArgs ba{};
+        ba.c = pc;
+        ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, 1};
+        ba.svS = h->d_svS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
+        const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
+        begin(K_BORN);
+        if (cutoff) k_born<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
+        else k_born<false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
+        end(K_BORN);
+        BornFinishArgs bf{};
+        bf.np = h->np; bf.posq = h->d_posq.p; bf.orig = h->d_orig.p; bf.bsum = h->d_bsum; bf.svS = h->d_svS; bf.vS = h->d_vS.p;
+        bf.radius = h->d_radius.p; bf.alpha = h->d_alpha.p;
+        bf.vsf = h->d_vsf.p; bf.born = h->d_born.p; bf.bfp = h->d_bfp.p; bf.brw = h->d_brw.p; bf.gbj = h->d_gbj.p;
+        bf.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
+        bf.kdiel = (float) h->k.dielectric_factor; bf.hb_radius = (float) h->k.hb_radius;
+        bf.scalars = h->d_scalars; bf.own_begin = pc.row_begin*TILE; bf.own_end = pc.row_end*TILE;
+        begin(K_BORNFIN);
+        k_born_finish<<<(h->np+255)/256, 256, 0, s>>>(bf);
+        end(K_BORNFIN);
     }
     if (v1 && (phase_mask & PH_GB)) {
         GBArgs ga{};
@@ -337,25 +402,23 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         end(K_GB);
     }
     if (v1 && (phase_mask & PH_DERIV)) {
-        BwArgs wa{h->np, h->d_posq.p, h->d_gbacc, h->d_born.p, h->d_bfp.p, h->d_brw.p, (float) h->k.dielectric_factor, h->d_bw.p,
-                  h->d_force, pc.row_begin*TILE, pc.row_end*TILE};
+        BwArgs wa{h->np, h->d_posq.p, h->d_gbacc, h->d_born.p, h->d_bfp.p, h->d_brw.p, (float) h->k.dielectric_factor, h->d_bw.p};
         begin(K_BW);
         k_bw<<<(h->np+255)/256, 256, 0, s>>>(wa);
         end(K_BW);
         DerivArgs da{};
-        da.c = pc; da.vsf = h->d_vsf.p; da.bw = h->d_bw.p; da.wu = h->d_wu; da.force = h->d_force; da.counters = h->d_counters;
-        const size_t sm = (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4));
-        const int rows = pc.row_end-pc.row_begin;
-        if (rows > 0) {
-            begin(K_DERIV);
-            if (cutoff) k_deriv<true><<<rows, PAIR_THREADS, sm, s>>>(da);
-            else k_deriv<false><<<rows, PAIR_THREADS, sm, s>>>(da);
-            end(K_DERIV);
-        }
+        da.c = pc;
+        da.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count};
+        da.vsf = h->d_vsf.p; da.bw = h->d_bw.p; da.dacc = h->d_dacc;
+        const size_t sm = 2*tab_bytes + PQ_WARPS*2*sizeof(DerivSmem);
+        begin(K_DERIV);
+        if (cutoff) k_deriv<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da);
+        else k_deriv<false><<<h->pq_grid, PQ_THREADS, sm, s>>>(da);
+        end(K_DERIV);
     }
     if (v1 && (phase_mask & PH_GAMMA)) {
         GammaArgs gm{};
-        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.wu = h->d_wu; gm.vS = h->d_vS.p;
+        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.dacc = h->d_dacc; gm.vS = h->d_vS.p;
         gm.force = h->d_force; gm.scratch = h->d_gamma_scratch.p; gm.scratch_stride = (size_t) 5*h->tree_cap*sizeof(float);
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
         begin(K_GAMMA);
@@ -366,6 +429,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         FinishArgs fa{};
         fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.force = h->d_force; fa.scalars = h->d_scalars;
         fa.status = h->d_ctrl+CW_STATUS;
+        if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; }
         fa.padded_n = sink ? sink->padded_n : 0;
         if (sink && sink->ptr) {
             if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;
@@ -560,10 +624,9 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         h->tree_grid = h->num_sm*2;
         h->gamma_grid = h->num_sm*4;
         h->gb_grid = h->num_sm*4;
+        h->pq_grid = h->num_sm*4;
         set_tree_smem(h);
-        const size_t tab_bytes = (size_t) h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener*I4_INTERVALS*sizeof(float4);
-        const int pair_smem = (int) (tab_bytes + PAIR_WARPS*TILE*(sizeof(float4)+sizeof(float2)+sizeof(float4)));
-        if (pair_smem > 200*1024) throw CudaFail{"I4 tables do not fit in shared memory (too many radius classes)"};
+        const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*2*sizeof(DerivSmem));
         CK(cudaFuncSetAttribute(k_born<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_deriv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
@@ -740,7 +803,13 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             for (int k = 0; k < np; k++) if (h->orig[k] >= 0) od[h->orig[k]] = t[k].w/(-2.0*h->k.dielectric_factor);
             break;
         }
-        case AGBNP_B200_GET_DERIV_WU: need(sizeof(double)*n); per_atom_f(h->d_wu, od); break;
+        case AGBNP_B200_GET_DERIV_WU: {
+            need(sizeof(double)*n);
+            std::vector<float4> t(np);
+            CK(cudaMemcpy(t.data(), h->d_dacc, sizeof(float4)*np, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) od[h->orig[k]] = t[k].w;
+            break;
+        }
         case AGBNP_B200_GET_SCALARS: {
             need(sizeof(double)*8);
             double sc[SC_COUNT];
@@ -843,7 +912,7 @@ int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* byte
     switch (which) {
     case AGBNP_B200_BUF_SELFVOL: *d_ptr = h->d_svS; *bytes = sizeof(double)*2*h->np; break;
     case AGBNP_B200_BUF_YQ: *d_ptr = h->d_gbacc; *bytes = sizeof(float4)*h->np; break;
-    case AGBNP_B200_BUF_WU: *d_ptr = h->d_wu; *bytes = sizeof(float)*h->np; break;
+    case AGBNP_B200_BUF_WU: *d_ptr = h->d_dacc; *bytes = sizeof(float4)*h->np; break;
     case AGBNP_B200_BUF_FORCE: *d_ptr = h->d_force; *bytes = sizeof(unsigned long long)*3*h->np; break;
     case AGBNP_B200_BUF_ENERGY: *d_ptr = h->d_scalars; *bytes = sizeof(double)*SC_COUNT; break;
     default: return AGBNP_B200_ERR_ARG;

@@ -3,9 +3,10 @@
 // Reference semantics: platforms/reference/src/ReferenceAGBNPKernels.cpp:421-586 (double loops over all pairs).
 // Decomposition here: atoms in blocks of 32 (sorted order, heavy first); passes bounded by the 2.0 nm table range or
 // by the cutoff cull block pairs on the fly with bounding boxes (no stored neighbor list); the Born and derivative
-// passes are written as pure row sums (every per-atom output has one owner, no atomics on the hot side); the GB pass,
-// which has no range limit without a cutoff, uses symmetric 32x32 register tiles (4 i-atoms x 8 j-atoms per lane),
-// warp-shuffle reduce-scatter of the partial sums and one fixed-point atomic per atom and component.
+// passes test each 32x32 tile once, keep the in-range pairs as per-lane bit masks and walk only those (see "Range-limited
+// pair passes" below); the GB pass, which has no range limit without a cutoff, uses symmetric 32x32 register tiles
+// (8 i-atoms x 4 j-atoms per lane) in packed FP32x2 arithmetic, warp-shuffle reduce-scatter of the partial sums and one
+// vector red.global per atom and tile.
 #ifndef AGBNP_PAIR_CUH_
 #define AGBNP_PAIR_CUH_
 
@@ -13,8 +14,6 @@
 
 namespace agbnp_b200_impl {
 
-constexpr int PAIR_THREADS = 256;       // Born / derivative kernels: 8 warps share one row block
-constexpr int PAIR_WARPS = PAIR_THREADS/32;
 constexpr int GB_THREADS = 128;
 constexpr int GB_CHUNK = 8;             // column tiles per GB work unit
 constexpr int I4_INTERVALS = 15;        // AGBNP_I4LOOKUP_NA - 1
@@ -58,15 +57,13 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
     }
 }
 
-// cubic-spline value / derivative from a packed interval (y_k, y_{k+1}, y2_k h^2/6, y2_{k+1} h^2/6); b = fraction in [0,1)
-__device__ __forceinline__ float spline_value(float4 c, float b) {
-    const float a = 1.f-b;
-    return a*c.x + b*c.y + (a*a*a-a)*c.z + (b*b*b-b)*c.w;
-}
-__device__ __forceinline__ float spline_deriv(float4 c, float b, float inv_h) {
-    const float a = 1.f-b;
-    return ((c.y-c.x) + ((1.f-3.f*a*a)*c.z + (3.f*b*b-1.f)*c.w))*inv_h;
-}
+// I4 splines in power form, one float4 pair per (table, interval): with fr = fraction of the interval in [0,1),
+//   Q(d)  = v.x + fr (v.y + fr (v.z + fr v.w))          (value table `tabv`)
+//   Q'(d) = w.x + fr (w.y + fr w.z)                      (derivative table `tabd`, 1/h folded in)
+// -- the natural cubic spline of AGBNPI4LookupTable (AGBNPUtils.cpp:102-130, AGBNPUtils.h:104-115) expanded around the
+// left knot on the host in double (agbnp_b200.cu: upload_static).
+__device__ __forceinline__ float spline_value(float4 v, float fr) { return fmaf(fr, fmaf(fr, fmaf(fr, v.w, v.z), v.y), v.x); }
+__device__ __forceinline__ float spline_deriv(float4 w, float fr) { return fmaf(fr, fmaf(fr, w.z, w.y), w.x); }
 
 struct PairCommon {
     int np, nhb, nb;            // padded atoms, heavy blocks, all blocks
@@ -75,132 +72,229 @@ struct PairCommon {
     const float4 *bbc, *bbh;
     const unsigned char* ts;    // screened radius type
     const signed char* tj;      // screener radius type, -1 hydrogens / padding
-    const float4* i4;           // packed tables
+    const float4* i4v;          // value tables  [ntables*15]
+    const float4* i4d;          // derivative tables
     int ntj, ntables;
+    int tab_smem;               // 1: tables are staged in shared memory; 0 (too many radius classes): read through L1
     float inv_h;
     float range2;               // (2.0 nm)^2 table range
     float cut2;                 // cutoff^2 (float product), used when CUTOFF
-    int row_begin, row_end;     // row blocks this shard owns
+    int row_begin, row_end;     // row blocks whose per-atom terms this shard reports
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_born: beta_i = 1/r_i - (1/4pi) sum_{j heavy, j != i, d < 2.0} s_j Q(d; type_i, type_j); B_i = 1/swf(beta_i)
-// (ReferenceAGBNPKernels.cpp:41-55,421-454) + the per-atom GB self energy (:477), vdW energy (:513-517), brw (:524-528)
+// Range-limited pair passes (Born radii S5, Born-radius derivatives S9).
+//
+// The reference loops over ORDERED pairs (i any, j heavy, d < 2.0 nm; ReferenceAGBNPKernels.cpp:437-450,557-586).  Here a
+// warp owns a work unit = (row block, chunk of PQ_CHUNK column blocks); for every column block whose bounding box is in
+// range it
+//   1. tests the 32x32 atom pairs ONCE: lane a scans the 32 column atoms (staged in shared memory) and keeps a 32-bit
+//      row mask; the ballot of each test, kept by lane b, is column atom b's mask of row atoms (the transposed matrix);
+//   2. row role: lane a walks the set bits of its row mask and accumulates everything atom a RECEIVES from those
+//      partners in registers;
+//   3. column role: lane b walks its column mask and accumulates what column atom b receives.
+// Steps 2/3 run the same code with the roles of "me" and "other" swapped, only on pairs that are in range (in-range
+// pairs are ~18% of the tested ones for the 2.0 nm range and 32-atom blocks, so walking masks instead of predicating
+// the 32x32 loop cuts the spline work by the lane-utilisation factor), and every sum lives in a register: no atomics
+// inside a tile.  Row sums leave once per unit, column sums once per tile, as one red.global per atom.
+// Units: heavy rows x heavy columns cb >= ra (both roles; the diagonal tile is handled by the row role alone) and
+// hydrogen rows x heavy columns (hydrogens never descreen, ReferenceAGBNPKernels.cpp:442,563).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PQ_CHUNK = 8;             // most column blocks one unit may cover (far-apart block pairs are packed)
+constexpr int PQ_THREADS = 256;
+constexpr int PQ_WARPS = PQ_THREADS/32;
+
+struct PairUnits {
+    const int2* units;          // (row block, first column block | number of column blocks << 20), heaviest first
+    int nunits;
+    int* work_counter;
+    int shard_rank, shard_count;    // units are dealt round-robin to shards (shard_count 1: all)
+};
+
+__device__ __forceinline__ float pq_dist2(bool exact, float dx, float dy, float dz) {
+    return exact ? dist2_exact(dx, dy, dz) : fmaf(dz, dz, fmaf(dy, dy, dx*dx));
+}
+
+// step 1: masks of in-range pairs of one tile.  s_cx/y/z: column atoms (SoA), (px,py,pz): this lane's row atom.
+template <bool CUTOFF>
+__device__ __forceinline__ void pq_masks(const float* s_cx, const float* s_cy, const float* s_cz, float px, float py, float pz,
+                                         float lim2, bool diag, int lane, unsigned& rowmask, unsigned& colmask) {
+    rowmask = 0; colmask = 0;
+#pragma unroll 8
+    for (int jj = 0; jj < TILE; jj++) {
+        const float dx = s_cx[jj]-px, dy = s_cy[jj]-py, dz = s_cz[jj]-pz;
+        const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
+        const bool ok = d2 < lim2 && !(diag && jj == lane);
+        const unsigned m = __ballot_sync(FULL, ok);
+        if (lane == jj) colmask = m;
+        rowmask |= (ok ? 1u : 0u) << jj;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_born: bsum_i = sum_{j heavy, j != i, d < 2.0} (s_j/4pi) Q(d; type_i, type_j)   (ReferenceAGBNPKernels.cpp:437-450)
 // ---------------------------------------------------------------------------------------------------------------
 struct BornArgs {
     PairCommon c;
+    PairUnits u;
     const double* svS;          // self volumes (vdW radii)
     const double* vS;           // atomic volumes (vdW radii)
-    const float* radius;        // sorted vdW radii
-    const float* alpha;         // sorted vdW alpha
-    float* vsf;                 // out: volume scaling factors s_i
-    float* born;                // out: B_i
-    float* bfp;                 // out: d swf / d beta
-    float* brw;                 // out
-    float4* gbj;                // out [3*np]: GB atom records in broadcast form (see k_gb)
-    float qscale;               // sqrt(-2k)
-    double* scalars;
+    float* bsum;                // out [np], zeroed slab
     unsigned long long* counters;
-    float kdiel;                // dielectric_factor
-    float hb_radius;
-    int own_row_begin, own_row_end;   // rows whose per-atom energies / counters this shard reports (the pass itself is replicated)
 };
 
-template <bool CUTOFF>
-__global__ void __launch_bounds__(PAIR_THREADS) k_born(BornArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* tab = (float4*) smem_raw;                                   // [ntables*15]
-    float4* s_pos = tab + A.c.ntables*I4_INTERVALS;                     // [PAIR_WARPS][32]  x,y,z, s_j/(4pi)
-    int* s_tj = (int*) (s_pos + PAIR_WARPS*TILE);                       // [PAIR_WARPS][32]
-    float* s_red = (float*) (s_tj + PAIR_WARPS*TILE);                   // [PAIR_WARPS][32]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < A.c.ntables*I4_INTERVALS; i += blockDim.x) tab[i] = A.c.i4[i];
-    __syncthreads();
+struct BornSmem { float x[TILE], y[TILE], z[TILE], w[TILE]; int tj[TILE]; };     // w = s_j/(4 pi), 0 for non-screeners
 
-    const int rowb = A.c.row_begin + blockIdx.x;
-    const int a = rowb*TILE+lane;
-    const float4 pa = A.c.posq[a];
-    const int tbase = (int) A.c.ts[a]*A.c.ntj*I4_INTERVALS;
-    const float4 ca = A.c.bbc[rowb], ha = A.c.bbh[rowb];
+// contribution of partner jj (valid = the pair exists; invalid slots run the same instructions on a harmless atom)
+template <bool CUTOFF>
+__device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o, int jj, bool valid, float px, float py, float pz,
+                                           int tbase, float inv_h, unsigned& npair) {
+    const int tj = o.tj[jj];
+    const float dx = o.x[jj]-px, dy = o.y[jj]-py, dz = o.z[jj]-pz;
+    const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
+    const float d = d2*rsqrtf(fmaxf(d2, 1e-20f));
+    const float t = d*inv_h;
+    const int k = min((int) t, I4_INTERVALS-1);
+    const bool use = valid && tj >= 0;
+    const float q = spline_value(tabv[tbase + max(tj, 0)*I4_INTERVALS + k], t-(float) k);
+    npair += use;
+    return use ? o.w[jj]*q : 0.f;
+}
+
+// everything atom "me" receives from the partners in `mask`; two partners per trip for instruction-level parallelism
+template <bool CUTOFF>
+__device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o, unsigned mask, float px, float py, float pz,
+                                           int tbase, float inv_h, unsigned& npair) {
+    float s0 = 0.f, s1 = 0.f;
+    while (mask) {
+        const int j0 = __ffs(mask)-1;
+        mask &= mask-1;
+        const bool two = mask != 0;
+        const int j1 = two ? __ffs(mask)-1 : j0;
+        mask &= mask-1;
+        s0 += born_term<CUTOFF>(tabv, o, j0, true, px, py, pz, tbase, inv_h, npair);
+        s1 += born_term<CUTOFF>(tabv, o, j1, two, px, py, pz, tbase, inv_h, npair);
+    }
+    return s0+s1;
+}
+
+__device__ __forceinline__ void born_load(const BornArgs& A, int blk, int lane, BornSmem& s) {
+    const int j = blk*TILE+lane;
+    const float4 p = A.c.posq[j];
+    const double vj = A.vS[j];
+    s.x[lane] = p.x; s.y[lane] = p.y; s.z[lane] = p.z;
+    s.w[lane] = vj > 0 ? PIFAC*((float) A.svS[j]/(float) vj) : 0.f;
+    s.tj[lane] = A.c.tj[j];
+}
+
+template <bool CUTOFF>
+__global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ntab = A.c.tab_smem ? A.c.ntables*I4_INTERVALS : 0;
+    float4* s_tabv = (float4*) smem_raw;                                // [ntables*15]
+    BornSmem* sm = (BornSmem*) (s_tabv + ntab);                         // [PQ_WARPS][2]: row block, column block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) s_tabv[i] = A.c.i4v[i];
+    __syncthreads();
+    const float4* tabv = A.c.tab_smem ? s_tabv : A.c.i4v;
+    BornSmem& R = sm[2*warp];
+    BornSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
-    float sum = 0.f;
-    unsigned long long npair = 0;
-    float4* my_pos = s_pos + warp*TILE;
-    int* my_tj = s_tj + warp*TILE;
-    for (int cb = warp; cb < A.c.nhb; cb += PAIR_WARPS) {
-        if (box_box_dist2(ca, ha, A.c.bbc[cb], A.c.bbh[cb]) >= lim2) continue;      // warp-uniform
-        const int j = cb*TILE+lane;
-        float4 pj = A.c.posq[j];
-        const double vj = A.vS[j];
-        pj.w = vj > 0 ? PIFAC*((float) A.svS[j]/(float) vj) : 0.f;
+    unsigned npair = 0;
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(A.u.work_counter, 1);
+        u = __shfl_sync(FULL, u, 0);
+        if (u >= A.u.nunits) break;
+        const int2 un = A.u.units[u];
+        const int ra = un.x;
+        const int cb0 = un.y & 0xfffff, nc = un.y >> 20;
+        bool hit = false;
+        if (lane < nc) hit = box_box_dist2(A.c.bbc[ra], A.c.bbh[ra], A.c.bbc[cb0+lane], A.c.bbh[cb0+lane]) < lim2;
+        unsigned hits = __ballot_sync(FULL, hit);
+        if (!hits) continue;
         __syncwarp();
-        my_pos[lane] = pj;
-        my_tj[lane] = A.c.tj[j];
-        __syncwarp();
-#pragma unroll 4
-        for (int jj = 0; jj < TILE; jj++) {
-            const float4 q = my_pos[jj];
-            const int tj = my_tj[jj];
-            const float dx = q.x-pa.x, dy = q.y-pa.y, dz = q.z-pa.z;
-            float d2;
-            bool ok;
-            if (CUTOFF) { d2 = dist2_exact(dx, dy, dz); ok = d2 < A.c.cut2 && d2 < A.c.range2; }
-            else { d2 = dx*dx + dy*dy + dz*dz; ok = d2 < A.c.range2; }
-            ok = ok && (cb*TILE+jj != a) && tj >= 0;
-            if (ok) {
-                const float d = d2*rsqrtf(fmaxf(d2, 1e-20f));
-                const float t = d*A.c.inv_h;
-                const int k = min((int) t, I4_INTERVALS-1);
-                const float4 c = tab[tbase + tj*I4_INTERVALS + k];
-                sum += q.w*spline_value(c, t-(float) k);
-                npair++;
+        born_load(A, ra, lane, R);
+        const bool row_heavy = ra < A.c.nhb;                 // hydrogen rows receive but never descreen
+        const float4 pa = A.c.posq[ra*TILE+lane];
+        const int tbase_a = (int) A.c.ts[ra*TILE+lane]*A.c.ntj*I4_INTERVALS;
+        float rsum = 0.f;
+        while (hits) {
+            const int cb = cb0 + __ffs(hits)-1;
+            hits &= hits-1;
+            const bool diag = cb == ra;
+            __syncwarp();
+            born_load(A, cb, lane, Cc);
+            __syncwarp();
+            unsigned rowmask, colmask;
+            pq_masks<CUTOFF>(Cc.x, Cc.y, Cc.z, pa.x, pa.y, pa.z, lim2, diag, lane, rowmask, colmask);
+            rsum += born_role<CUTOFF>(tabv, Cc, rowmask, pa.x, pa.y, pa.z, tbase_a, A.c.inv_h, npair);
+            if (!diag && row_heavy) {
+                const int b = cb*TILE+lane;
+                const int tbase_b = (int) A.c.ts[b]*A.c.ntj*I4_INTERVALS;
+                const float csum = born_role<CUTOFF>(tabv, R, colmask, Cc.x[lane], Cc.y[lane], Cc.z[lane], tbase_b, A.c.inv_h, npair);
+                if (csum != 0.f) atomicAdd(&A.bsum[b], csum);
             }
         }
+        if (rsum != 0.f) atomicAdd(&A.bsum[ra*TILE+lane], rsum);
     }
-    s_red[warp*TILE+lane] = sum;
-    __syncthreads();
-    if (warp == 0) {
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < PAIR_WARPS; w++) tot += s_red[w*TILE+lane];
-        float evdw = 0.f, eself = 0.f;
-        const bool real = A.c.orig[a] >= 0;
-        if (real) {
-            const float beta = 1.f/A.radius[a] - tot;
-            // agbnp_swf_invbr (ReferenceAGBNPKernels.cpp:41-55)
+    unsigned long long np64 = (unsigned long long) warp_sum((double) npair);
+    if (lane == 0 && np64 && A.u.shard_rank == 0) atomicAdd(&A.counters[CT_PQ], np64);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_born_finish: beta_i = 1/r_i - bsum_i; B_i = 1/swf(beta_i) (agbnp_swf_invbr, ReferenceAGBNPKernels.cpp:41-55,452-454),
+// volume scaling factors (:421-430), GB self energy (:477), vdW energy and brw (:513-528), GB atom records for k_gb
+// ---------------------------------------------------------------------------------------------------------------
+struct BornFinishArgs {
+    int np;
+    const float4* posq;
+    const int* orig;
+    const float* bsum;
+    const double *svS, *vS;
+    const float *radius, *alpha;
+    float *vsf, *born, *bfp, *brw;
+    float4* gbj;                // out [3*np]: GB atom records in broadcast form (see k_gb)
+    float qscale;               // sqrt(-2k)
+    float kdiel, hb_radius;
+    double* scalars;
+    int own_begin, own_end;     // sorted-index range whose per-atom energies this shard reports
+};
+
+__global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
+    const int a = blockIdx.x*blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    float evdw = 0.f, eself = 0.f;
+    if (a < A.np) {
+        const float4 pa = A.posq[a];
+        float br = 1.f;
+        if (A.orig[a] >= 0) {
+            const float beta = 1.f/A.radius[a] - A.bsum[a];
             const float ia = 0.5f, ia2 = 0.25f;          // 1/2.0, 1/2.0^2
             float t, fp;
             if (beta < 0.f) { t = ia; fp = 0.f; }
             else { t = sqrtf(ia2 + beta*beta); fp = beta/t; }
-            const float br = 1.f/t;
+            br = 1.f/t;
             A.born[a] = br;
             A.bfp[a] = fp;
             const double va = A.vS[a];
             A.vsf[a] = va > 0 ? (float) A.svS[a]/(float) va : 0.f;
             const float q = pa.w, al = A.alpha[a];
-            eself = A.kdiel*q*q/br;
             const float bh = br + A.hb_radius;
             const float bh3 = bh*bh*bh;
-            evdw = al/bh3;
+            if (a >= A.own_begin && a < A.own_end) { eself = A.kdiel*q*q/br; evdw = al/bh3; }
             A.brw[a] = -PIFAC*3.f*al*br*br*fp/(bh3*bh);
         } else {
             A.born[a] = 1.f; A.bfp[a] = 0.f; A.vsf[a] = 0.f; A.brw[a] = 0.f;
         }
-        {
-            const float br = A.born[a];
-            const float qs = pa.w*A.qscale, ib = 0.60056120439322491f/br;   // sqrt(log2(e)/4)/B
-            float4* rec = A.gbj + 3*(size_t) a;
-            rec[0] = make_float4(pa.x, pa.x, pa.y, pa.y);
-            rec[1] = make_float4(pa.z, pa.z, qs, qs);
-            rec[2] = make_float4(br, br, ib, ib);
-        }
-        const double es = warp_sum((double) eself), ev = warp_sum((double) evdw);
-        if (lane == 0 && rowb >= A.own_row_begin && rowb < A.own_row_end) {
-            atomicAdd(&A.scalars[SC_EGB], es); atomicAdd(&A.scalars[SC_EVDW], ev);
-        }
+        const float qs = pa.w*A.qscale, ib = 0.60056120439322491f/br;   // sqrt(log2(e)/4)/B
+        float4* rec = A.gbj + 3*(size_t) a;
+        rec[0] = make_float4(pa.x, pa.x, pa.y, pa.y);
+        rec[1] = make_float4(pa.z, pa.z, qs, qs);
+        rec[2] = make_float4(br, br, ib, ib);
     }
-    npair = (unsigned long long) warp_sum((double) npair);
-    if (lane == 0 && npair && rowb >= A.own_row_begin && rowb < A.own_row_end) atomicAdd(&A.counters[CT_PQ], npair);
+    const double es = warp_sum((double) eself), ev = warp_sum((double) evdw);
+    if (lane == 0 && (es != 0.0 || ev != 0.0)) { atomicAdd(&A.scalars[SC_EGB], es); atomicAdd(&A.scalars[SC_EVDW], ev); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -221,7 +315,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_born(BornArgs A) {
 struct GBArgs {
     PairCommon c;
     const float4* gbj;          // [3*np] broadcast-form GB atom records
-    const int2* units;          // (row block, first column block): triangular cover in chunks of GB_CHUNK column tiles
+    const int2* units;          // (row block, first column block | number of column blocks << 20), heaviest first: triangular cover in chunks of GB_CHUNK column tiles
     int nunits;
     int shard_rank, shard_count;
     float4* gbacc;              // out [np]: fx, fy, fz (GB pair force), Y_i*(-2k)
@@ -408,8 +502,7 @@ __global__ void __launch_bounds__(GB_THREADS, 3) k_gb(GBArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_bw: bw_i = brw_i + bru_i, bru_i = -(k/4pi)(q_i^2 + Y_i B_i) fp_i   (ReferenceAGBNPKernels.cpp:537-542); folds the
-// GB pair force of the atoms this shard reports into the fixed-point force accumulator
+// k_bw: bw_i = brw_i + bru_i, bru_i = -(k/4pi)(q_i^2 + Y_i B_i) fp_i   (ReferenceAGBNPKernels.cpp:537-542)
 // ---------------------------------------------------------------------------------------------------------------
 struct BwArgs {
     int np;
@@ -418,126 +511,139 @@ struct BwArgs {
     const float *born, *bfp, *brw;
     float kdiel;
     float* bw;
-    unsigned long long* force;
-    int own_begin, own_end;     // sorted-index range whose GB force this shard adds (gbacc is all-reduced before)
 };
 
 __global__ void __launch_bounds__(256) k_bw(BwArgs A) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= A.np) return;
     const float q = A.posq[i].w;
-    const float4 g = A.gbacc[i];
-    const float y = g.w/(-2.f*A.kdiel);
+    const float y = A.gbacc[i].w/(-2.f*A.kdiel);
     A.bw[i] = A.brw[i] - PIFAC*A.kdiel*(q*q + y*A.born[i])*A.bfp[i];
-    if (i >= A.own_begin && i < A.own_end) {
-        // the only writer of these entries at this point of the stream: plain read-modify-write
-        A.force[i] += (unsigned long long) (long long) (g.x*4294967296.0f);
-        A.force[(size_t) A.np+i] += (unsigned long long) (long long) (g.y*4294967296.0f);
-        A.force[2*(size_t) A.np+i] += (unsigned long long) (long long) (g.z*4294967296.0f);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_deriv: Born-radius derivative pass as a row sum (ReferenceAGBNPKernels.cpp:555-586).  For atom a and partner b
-// (d < 2.0, b != a), with D = r_b - r_a:
-//   F_a  += D/d [ heavy(b) bw_a s_b Q'(d; ts_a, tj_b)  +  heavy(a) bw_b s_a Q'(d; ts_b, tj_a) ]
-//   WU_a += heavy(a) bw_b Q(d; ts_b, tj_a)                      (W and U merged: both are linear in brw / bru)
-// which is the reference's ordered-pair loop regrouped by the atom that receives the contribution.
+// k_deriv: Born-radius derivative pass (ReferenceAGBNPKernels.cpp:555-586), regrouped by the atom that RECEIVES each
+// contribution.  For atom "me" and partner "o" (d < 2.0, o != me), with D = r_o - r_me:
+//   F_me  += D/d [ heavy(o) bw_me s_o Q'(d; ts_me, tj_o)  +  heavy(me) bw_o s_me Q'(d; ts_o, tj_me) ]
+//   WU_me += heavy(me) bw_o Q(d; ts_o, tj_me)                   (W and U merged: both are linear in brw / bru)
+// Same unit / mask / role structure as k_born.
 // ---------------------------------------------------------------------------------------------------------------
 struct DerivArgs {
     PairCommon c;
+    PairUnits u;
     const float* vsf;
     const float* bw;
-    float* wu;                  // out [np]
-    unsigned long long* force;
-    unsigned long long* counters;
+    float4* dacc;               // out [np]: fx, fy, fz, W+U (zeroed slab; float red.global)
 };
 
-template <bool CUTOFF>
-__global__ void __launch_bounds__(PAIR_THREADS) k_deriv(DerivArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* tab = (float4*) smem_raw;
-    float4* s_pos = tab + A.c.ntables*I4_INTERVALS;                     // x,y,z,s_b
-    float2* s_ex = (float2*) (s_pos + PAIR_WARPS*TILE);                 // bw_b, packed types
-    float4* s_red = (float4*) (s_ex + PAIR_WARPS*TILE);                 // [PAIR_WARPS][32]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < A.c.ntables*I4_INTERVALS; i += blockDim.x) tab[i] = A.c.i4[i];
-    __syncthreads();
+struct DerivSmem { float x[TILE], y[TILE], z[TILE], s[TILE], bw[TILE]; int pk[TILE]; };    // pk = ts | (tj & 0xff) << 8
 
-    const int rowb = A.c.row_begin + blockIdx.x;
-    const int a = rowb*TILE+lane;
-    const float4 pa = A.c.posq[a];
-    const int ts_a = A.c.ts[a];
-    const int tj_a = A.c.tj[a];
-    const bool hv_a = tj_a >= 0;
-    const float s_a = A.vsf[a], bw_a = A.bw[a];
-    const int base_a = ts_a*A.c.ntj*I4_INTERVALS;
-    const float4 ca = A.c.bbc[rowb], ha = A.c.bbh[rowb];
+struct DerivMe { float px, py, pz, s, bw; int base, tj; };
+
+template <bool CUTOFF>
+__device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tabd, const DerivSmem& o, int jj, bool valid,
+                                           const DerivMe& me, int ntj, float inv_h, float& fx, float& fy, float& fz, float& wu) {
+    const float dx = o.x[jj]-me.px, dy = o.y[jj]-me.py, dz = o.z[jj]-me.pz;
+    const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
+    const int pk = o.pk[jj];
+    const int ts_o = pk & 0xff;
+    const int tj_o = (int) (signed char) ((pk >> 8) & 0xff);
+    const float inv_d = rsqrtf(fmaxf(d2, 1e-20f));
+    const float d = d2*inv_d;
+    const float t = d*inv_h;
+    const int k = min((int) t, I4_INTERVALS-1);
+    const float fr = t-(float) k;
+    // o descreens me (needs heavy(o)); me descreens o (needs heavy(me))
+    const float q1 = spline_deriv(tabd[me.base + max(tj_o, 0)*I4_INTERVALS + k], fr);
+    const int ix = (ts_o*ntj + max(me.tj, 0))*I4_INTERVALS + k;
+    const float q2 = spline_deriv(tabd[ix], fr), v2 = spline_value(tabv[ix], fr);
+    const float bwo = (valid && me.tj >= 0) ? o.bw[jj] : 0.f;
+    float w = (valid && tj_o >= 0) ? me.bw*o.s[jj]*q1 : 0.f;
+    w = fmaf(bwo*me.s, q2, w)*inv_d;
+    wu = fmaf(bwo, v2, wu);
+    fx = fmaf(dx, w, fx); fy = fmaf(dy, w, fy); fz = fmaf(dz, w, fz);
+}
+
+template <bool CUTOFF>
+__device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* tabd, const DerivSmem& o, unsigned mask,
+                                             float px, float py, float pz, float s_me, float bw_me, int ts_me, int tj_me,
+                                             int ntj, float inv_h) {
+    float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
+    const DerivMe me{px, py, pz, s_me, bw_me, ts_me*ntj*I4_INTERVALS, tj_me};
+    while (mask) {
+        const int j0 = __ffs(mask)-1;
+        mask &= mask-1;
+        const bool two = mask != 0;
+        const int j1 = two ? __ffs(mask)-1 : j0;
+        mask &= mask-1;
+        deriv_term<CUTOFF>(tabv, tabd, o, j0, true, me, ntj, inv_h, fx0, fy0, fz0, wu0);
+        deriv_term<CUTOFF>(tabv, tabd, o, j1, two, me, ntj, inv_h, fx1, fy1, fz1, wu1);
+    }
+    return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
+}
+
+__device__ __forceinline__ void deriv_load(const DerivArgs& A, int blk, int lane, DerivSmem& s) {
+    const int j = blk*TILE+lane;
+    const float4 p = A.c.posq[j];
+    s.x[lane] = p.x; s.y[lane] = p.y; s.z[lane] = p.z;
+    s.s[lane] = A.vsf[j];
+    s.bw[lane] = A.bw[j];
+    s.pk[lane] = (int) A.c.ts[j] | (((int) A.c.tj[j] & 0xff) << 8);
+}
+
+template <bool CUTOFF>
+__global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ntab = A.c.tab_smem ? A.c.ntables*I4_INTERVALS : 0;
+    float4* s_tabv = (float4*) smem_raw;
+    float4* s_tabd = s_tabv + ntab;
+    DerivSmem* sm = (DerivSmem*) (s_tabd + ntab);                       // [PQ_WARPS][2]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) { s_tabv[i] = A.c.i4v[i]; s_tabd[i] = A.c.i4d[i]; }
+    __syncthreads();
+    const float4* tabv = A.c.tab_smem ? s_tabv : A.c.i4v;
+    const float4* tabd = A.c.tab_smem ? s_tabd : A.c.i4d;
+    DerivSmem& R = sm[2*warp];
+    DerivSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
-    // heavy rows see every column block (they descreen hydrogens too); hydrogen rows only heavy columns
-    const int ncol = rowb < A.c.nhb ? A.c.nb : A.c.nhb;
-    float fx = 0.f, fy = 0.f, fz = 0.f, wu = 0.f;
-    float4* my_pos = s_pos + warp*TILE;
-    float2* my_ex = s_ex + warp*TILE;
-    for (int cb = warp; cb < ncol; cb += PAIR_WARPS) {
-        if (box_box_dist2(ca, ha, A.c.bbc[cb], A.c.bbh[cb]) >= lim2) continue;
-        const int j = cb*TILE+lane;
-        float4 pj = A.c.posq[j];
-        pj.w = A.vsf[j];
-        const int pk = (int) A.c.ts[j] | (((int) A.c.tj[j] & 0xff) << 8);
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(A.u.work_counter, 1);
+        u = __shfl_sync(FULL, u, 0);
+        if (u >= A.u.nunits) break;
+        if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
+        const int2 un = A.u.units[u];
+        const int ra = un.x;
+        const int cb0 = un.y & 0xfffff, nc = un.y >> 20;
+        bool hit = false;
+        if (lane < nc) hit = box_box_dist2(A.c.bbc[ra], A.c.bbh[ra], A.c.bbc[cb0+lane], A.c.bbh[cb0+lane]) < lim2;
+        unsigned hits = __ballot_sync(FULL, hit);
+        if (!hits) continue;
         __syncwarp();
-        my_pos[lane] = pj;
-        my_ex[lane] = make_float2(A.bw[j], __int_as_float(pk));
-        __syncwarp();
-#pragma unroll 2
-        for (int jj = 0; jj < TILE; jj++) {
-            const float4 q = my_pos[jj];
-            const float2 ex = my_ex[jj];
-            const float dx = q.x-pa.x, dy = q.y-pa.y, dz = q.z-pa.z;
-            float d2;
-            bool ok;
-            if (CUTOFF) { d2 = dist2_exact(dx, dy, dz); ok = d2 < A.c.cut2 && d2 < A.c.range2; }
-            else { d2 = dx*dx + dy*dy + dz*dz; ok = d2 < A.c.range2; }
-            ok = ok && (cb*TILE+jj != a);
-            if (ok) {
-                const int pk2 = __float_as_int(ex.y);
-                const int ts_b = pk2 & 0xff;
-                const int tj_b = (int) (signed char) ((pk2 >> 8) & 0xff);
-                const float inv_d = rsqrtf(fmaxf(d2, 1e-20f));
-                const float d = d2*inv_d;
-                const float t = d*A.c.inv_h;
-                const int k = min((int) t, I4_INTERVALS-1);
-                const float fr = t-(float) k;
-                float w = 0.f;
-                if (tj_b >= 0) {                                    // b descreens a
-                    const float4 c1 = tab[base_a + tj_b*I4_INTERVALS + k];
-                    w = bw_a*q.w*spline_deriv(c1, fr, A.c.inv_h);
-                }
-                if (hv_a) {                                         // a descreens b
-                    const float4 c2 = tab[(ts_b*A.c.ntj + tj_a)*I4_INTERVALS + k];
-                    w += ex.x*s_a*spline_deriv(c2, fr, A.c.inv_h);
-                    wu += ex.x*spline_value(c2, fr);
-                }
-                w *= inv_d;
-                fx = fmaf(dx, w, fx); fy = fmaf(dy, w, fy); fz = fmaf(dz, w, fz);
+        deriv_load(A, ra, lane, R);
+        const int a = ra*TILE+lane;
+        const float px = R.x[lane], py = R.y[lane], pz = R.z[lane], s_a = R.s[lane], bw_a = R.bw[lane];
+        const int ts_a = A.c.ts[a], tj_a = A.c.tj[a];
+        float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+        while (hits) {
+            const int cb = cb0 + __ffs(hits)-1;
+            hits &= hits-1;
+            const bool diag = cb == ra;
+            __syncwarp();
+            deriv_load(A, cb, lane, Cc);
+            __syncwarp();
+            unsigned rowmask, colmask;
+            pq_masks<CUTOFF>(Cc.x, Cc.y, Cc.z, px, py, pz, lim2, diag, lane, rowmask, colmask);
+            const float4 r = deriv_role<CUTOFF>(tabv, tabd, Cc, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h);
+            racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
+            if (!diag) {
+                const int pk = Cc.pk[lane];
+                const float4 c = deriv_role<CUTOFF>(tabv, tabd, R, colmask, Cc.x[lane], Cc.y[lane], Cc.z[lane], Cc.s[lane], Cc.bw[lane],
+                                                    pk & 0xff, (int) (signed char) ((pk >> 8) & 0xff), A.c.ntj, A.c.inv_h);
+                if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], c);
             }
         }
-    }
-    s_red[warp*TILE+lane] = make_float4(fx, fy, fz, wu);
-    __syncthreads();
-    if (warp == 0) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int w = 0; w < PAIR_WARPS; w++) {
-            const float4 v = s_red[w*TILE+lane];
-            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-        }
-        A.wu[a] = t.w;
-        if (t.x != 0.f || t.y != 0.f || t.z != 0.f) {
-            add_force_fixed(&A.force[a], t.x);
-            add_force_fixed(&A.force[(size_t) A.c.np+a], t.y);
-            add_force_fixed(&A.force[2*(size_t) A.c.np+a], t.z);
-        }
+        atomicAdd(&A.dacc[a], racc);
     }
 }
 
@@ -547,7 +653,9 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_deriv(DerivArgs A) {
 struct FinishArgs {
     int np, n;
     const int* orig;
-    const unsigned long long* force;
+    const unsigned long long* force;    // fixed-point part: surface-tension (tree) forces
+    const float4* gbacc;                // float part: GB pair force (xyz)           -- null for version 0
+    const float4* dacc;                 // float part: Born-radius derivative force  -- null for version 0
     float* out_f32;                     // layout 0: float[3n] interleaved, +=
     unsigned long long* out_fixed;      // layout 1: OpenMM fixed point [3][padded_n], atomic +=
     double* out_f64;                    // internal: double[3n] interleaved, = (host path)
@@ -570,18 +678,18 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     if (k >= A.np) return;
     const int o = A.orig[k];
     if (o < 0) return;
-    const long long fx = (long long) A.force[k], fy = (long long) A.force[(size_t) A.np+k], fz = (long long) A.force[2*(size_t) A.np+k];
-    if (A.out_f64) {
-        A.out_f64[3*o+0] = (double) fx/FORCE_SCALE; A.out_f64[3*o+1] = (double) fy/FORCE_SCALE; A.out_f64[3*o+2] = (double) fz/FORCE_SCALE;
+    double fx = (double) (long long) A.force[k]/FORCE_SCALE, fy = (double) (long long) A.force[(size_t) A.np+k]/FORCE_SCALE,
+           fz = (double) (long long) A.force[2*(size_t) A.np+k]/FORCE_SCALE;
+    if (A.gbacc) {
+        const float4 g = A.gbacc[k], d = A.dacc[k];
+        fx += (double) g.x + (double) d.x; fy += (double) g.y + (double) d.y; fz += (double) g.z + (double) d.z;
     }
-    if (A.out_f32) {
-        A.out_f32[3*o+0] += (float) ((double) fx/FORCE_SCALE); A.out_f32[3*o+1] += (float) ((double) fy/FORCE_SCALE);
-        A.out_f32[3*o+2] += (float) ((double) fz/FORCE_SCALE);
-    }
+    if (A.out_f64) { A.out_f64[3*o+0] = fx; A.out_f64[3*o+1] = fy; A.out_f64[3*o+2] = fz; }
+    if (A.out_f32) { A.out_f32[3*o+0] += (float) fx; A.out_f32[3*o+1] += (float) fy; A.out_f32[3*o+2] += (float) fz; }
     if (A.out_fixed) {
-        atomicAdd(&A.out_fixed[o], (unsigned long long) fx);
-        atomicAdd(&A.out_fixed[(size_t) A.padded_n+o], (unsigned long long) fy);
-        atomicAdd(&A.out_fixed[2*(size_t) A.padded_n+o], (unsigned long long) fz);
+        atomicAdd(&A.out_fixed[o], (unsigned long long) (long long) (fx*FORCE_SCALE));
+        atomicAdd(&A.out_fixed[(size_t) A.padded_n+o], (unsigned long long) (long long) (fy*FORCE_SCALE));
+        atomicAdd(&A.out_fixed[2*(size_t) A.padded_n+o], (unsigned long long) (long long) (fz*FORCE_SCALE));
     }
 }
 

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
 struct GammaArgs {
     int nh, np;
     TreeStore st;
-    const float* wu;            // [np] W_i + U_i
+    const float4* dacc;         // [np] .w = W_i + U_i
     const double* vS;           // atomic volumes, vdW radii
     unsigned long long* force;
     unsigned char* scratch;     // per-warp float[5*cap]: gam, f', p'x, p'y, p'z
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_gamma(GammaArgs A) {
             const int b = lvs[lev], e = lev == nlev ? cnt : lvs[lev+1];
             for (int sl = b+lane; sl < e; sl += 32) {
                 const int ja = A.st.atom[off+sl];
-                const float nu = (float) ((double) A.wu[ja]/A.vS[ja]);
+                const float nu = (float) ((double) A.dacc[ja].w/A.vS[ja]);
                 const int p = A.st.parent[off+sl];
                 gam[sl] = (p >= 0 ? gam[p] : 0.f) + nu;
             }
