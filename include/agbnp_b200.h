@@ -145,18 +145,18 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);
  * Work split: overlap-tree roots are dealt block-cyclically (each shard builds, sweeps and stores only its subtrees);
  * the Born-radius pass is replicated (cheaper than an exchange); GB tile units and derivative-pass units are dealt
  * round-robin.
- *   phase 0: gather/sort, tree build + rescan + sweeps for the owned roots   -> all-reduce SELFVOL (2*np doubles)
+ *   phase 0: gather/sort, tree build + rescan + sweeps for the owned roots   -> all-reduce SELFVOL (8*np floats)
  *   phase 1: Born radii (all rows), GB pair pass for the owned tile units     -> all-reduce YQ      (4*np floats)
  *   phase 2: bru/brw (all atoms), derivative pass for the owned units         -> all-reduce WU      (4*np floats)
- *   phase 3: tree gamma sweep over the owned subtrees                         -> all-reduce FORCE (3*np int64, exact)
+ *   phase 3: tree gamma sweep over the owned subtrees                         -> all-reduce FORCE (4*np floats)
  *                                                                                 and ENERGY (8 doubles)
  *   finish : scatter forces to the caller's sink, total energy
  * With shard_count == 1 execute_* run all phases back to back. */
 int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* stream);
 typedef enum {
-    AGBNP_B200_BUF_SELFVOL = 0,  /* double[2*np]  partial self-volumes (vdW radii, then enlarged radii), internal order */
+    AGBNP_B200_BUF_SELFVOL = 0,  /* float[8*np]   per atom (gradient xyz, self-volume): enlarged radii, then vdW radii; internal order */
     AGBNP_B200_BUF_YQ = 1,       /* float[4*np]   partial GB pair force (xyz) and GB derivative accumulator Y (w) */
-    AGBNP_B200_BUF_FORCE = 2,    /* long long[3*np] fixed-point partial forces */
+    AGBNP_B200_BUF_FORCE = 2,    /* float[4*np]   partial forces of the W+U tree sweep (xyz, -) */
     AGBNP_B200_BUF_ENERGY = 3,   /* double[8]     partial energy scalars */
     AGBNP_B200_BUF_WU = 4        /* float[4*np]   partial derivative-pass force (xyz) and W+U (w) */
 } agbnp_b200_buffer;

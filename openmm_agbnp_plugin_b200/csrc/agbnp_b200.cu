@@ -48,7 +48,7 @@ enum KernelId { K_ZERO = 0, K_PREP, K_TREE, K_BORN, K_GB, K_BW, K_DERIV, K_GAMMA
 const char* const kKernelNames = "memset_accum\nk_prep\nk_tree\nk_born\nk_gb\nk_bw\nk_deriv\nk_tree_gamma\nk_finish\nk_born_finish";
 
 // control words inside the zeroed slab
-enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_MAX_NBR, CW_MAX_NODES, CW_WORK_BORN, CW_WORK_DERIV, CW_COUNT = 12 };
+enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_MAX_NBR, CW_MAX_NODES, CW_WORK_BORN, CW_WORK_DERIV, CW_MAX_WIDTH, CW_COUNT = 12 };
 
 } // namespace
 
@@ -79,8 +79,10 @@ struct agbnp_b200 {
     DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in, d_gbj;
     DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bw;
     DevBuf<unsigned char> d_slab;           // zeroed every evaluation
-    double *d_svS = nullptr, *d_svL = nullptr, *d_scalars = nullptr;
-    unsigned long long *d_force = nullptr, *d_counters = nullptr;
+    double* d_scalars = nullptr;
+    unsigned long long* d_counters = nullptr;
+    float4 *d_accL = nullptr, *d_accS = nullptr;   // tree: surface-tension gradient + self volume per atom (zeroed slab; accS follows accL)
+    float4* d_gacc = nullptr;               // force of the W+U tree sweep (zeroed slab)
     float4* d_gbacc = nullptr;              // GB pair force + Y per atom (zeroed slab)
     float4* d_dacc = nullptr;               // derivative-pass force + (W+U) per atom (zeroed slab)
     float* d_bsum = nullptr;                // Born-radius pair sums (zeroed slab)
@@ -89,9 +91,11 @@ struct agbnp_b200 {
     size_t slab_bytes = 0;
     DevBuf<double> d_force_out;             // double[3n] for the host path
     // tree
-    int tree_cap = 768, nbrmax = 128;
-    int tree_grid = 0, gamma_grid = 0, gb_grid = 0, pq_grid = 0;
-    DevBuf<unsigned char> d_tree_scratch, d_gamma_scratch;
+    // tree capacities (grown on overflow): nodes per root, nodes per level, level-2 neighbors per root
+    int tree_cap = 512, tree_wcap = 192, nbrmax = 64;
+    int tree_grid = 0, tree_warps = 4, gamma_grid = 0, gb_grid = 0, pq_grid = 0;
+    bool tree_work_global = false;          // work arrays too large for shared memory: per-warp global scratch instead
+    DevBuf<unsigned char> d_tree_stage, d_tree_work, d_gamma_scratch;
     TreeStore st{};
     DevBuf<int> d_root_off, d_st_atom;
     DevBuf<short> d_root_lvs, d_st_parent, d_st_cstart, d_st_ccount, d_st_rank;
@@ -120,6 +124,8 @@ struct agbnp_b200 {
     bool async_pending[ASYNC_DEPTH] = {};
     long long async_issued = 0;
     bool async_fault = false;
+    int ahead[16] = {};                     // capacities to grow before the next evaluation (grow_ahead)
+    bool ahead_pending = false;
 
     ~agbnp_b200() {
         if (h_posq) cudaFreeHost(h_posq);
@@ -147,8 +153,21 @@ void alloc_store(agbnp_b200* h, int cap) {
     s.root_off = h->d_root_off.p; s.root_cnt = h->d_root_cnt; s.root_lvs = h->d_root_lvs.p;
 }
 
+// choose the launch shape of k_tree for the current capacities and (re)allocate its per-warp buffers
 void alloc_tree_scratch(agbnp_b200* h) {
-    h->d_tree_scratch.alloc((size_t) h->tree_grid*TREE_WARPS*tree_scratch_bytes(h->tree_cap));
+    const size_t per_warp = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
+    const size_t smem_sm = 200*1024;                       // of 227 KB; leaves room for L1
+    // CTAs of 2 warps (warps never cooperate); 128 registers/thread bound the residency at 16 warps per SM
+    h->tree_warps = 2;
+    size_t ctas = std::min<size_t>(8, smem_sm/(h->tree_warps*per_warp + 1024));
+    h->tree_work_global = ctas < 2;                        // fewer than 4 warps per SM: shared memory no longer pays
+    if (h->tree_work_global) { h->tree_warps = 8; ctas = 2; }
+    h->tree_grid = h->num_sm*(int) ctas;
+    const size_t nwarps = (size_t) h->tree_grid*h->tree_warps;
+    h->d_tree_stage.alloc(nwarps*tree_stage_bytes(h->tree_cap));
+    if (h->tree_work_global) h->d_tree_work.alloc(nwarps*per_warp); else h->d_tree_work.release();
+    const size_t smem = h->tree_work_global ? 0 : h->tree_warps*per_warp;
+    CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
     h->d_gamma_scratch.alloc((size_t) h->gamma_grid*TREE_WARPS*5*h->tree_cap*sizeof(float));
 }
 
@@ -270,14 +289,14 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         h->d_vsf.alloc(np); h->d_born.alloc(np); h->d_bfp.alloc(np); h->d_brw.alloc(np); h->d_bw.alloc(np);
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o += (bytes+255)/256*256; return r; };
-        const size_t o_svS = take(sizeof(double)*np), o_svL = take(sizeof(double)*np), o_force = take(sizeof(unsigned long long)*3*np);
+        const size_t o_accL = take(sizeof(float4)*np*2), o_gacc = take(sizeof(float4)*np);
         const size_t o_yq = take(sizeof(float4)*np), o_scal = take(sizeof(double)*SC_COUNT), o_cnt = take(sizeof(unsigned long long)*CT_COUNT);
         const size_t o_ctrl = take(sizeof(int)*CW_COUNT);
         const size_t o_dacc = take(sizeof(float4)*np), o_bsum = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->nhp);
         h->slab_bytes = o;
         h->d_slab.alloc(o);
         unsigned char* b = h->d_slab.p;
-        h->d_svS = (double*) (b+o_svS); h->d_svL = (double*) (b+o_svL); h->d_force = (unsigned long long*) (b+o_force);
+        h->d_accL = (float4*) (b+o_accL); h->d_accS = h->d_accL+np; h->d_gacc = (float4*) (b+o_gacc);
         h->d_gbacc = (float4*) (b+o_yq); h->d_scalars = (double*) (b+o_scal); h->d_counters = (unsigned long long*) (b+o_cnt);
         h->d_ctrl = (int*) (b+o_ctrl);
         h->d_dacc = (float4*) (b+o_dacc); h->d_bsum = (float*) (b+o_bsum); h->d_root_cnt = (int*) (b+o_rcnt);
@@ -353,18 +372,22 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
         ta.volmina = h->k.volmina; ta.volminb = h->k.volminb; ta.min_gvol = h->k.min_gvol;
         ta.swd = 1.0/(h->k.volminb-h->k.volmina);
-        ta.inv_roffset = (float) (1.0/h->k.roffset);
+        // FP32 screen: |relative error| of the float overlap volume is < 1e-4 (positions within a subtree are < 2 nm from the
+        // root: 1e-7 nm rounding, exponent argument < 40, ex2.approx 2 ulp); 1e-3 leaves a factor 10
+        ta.screen = (float) (h->k.volmina*(1.0 - 1.0e-3));
         ta.max_order = h->k.max_order;
-        ta.scratch = h->d_tree_scratch.p; ta.scratch_stride = tree_scratch_bytes(h->tree_cap);
-        ta.cap = h->tree_cap; ta.nbrmax = h->nbrmax;
-        ta.svS = h->d_svS; ta.svL = h->d_svL; ta.force = h->d_force; ta.scalars = h->d_scalars; ta.counters = h->d_counters;
+        ta.cap = h->tree_cap; ta.wcap = h->tree_wcap; ta.nbrmax = h->nbrmax;
+        ta.stage = h->d_tree_stage.p; ta.stage_stride = tree_stage_bytes(h->tree_cap);
+        ta.wk_stride = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
+        ta.wk_global = h->tree_work_global ? h->d_tree_work.p : nullptr;
+        ta.accL = h->d_accL; ta.accS = h->d_accS; ta.scalars = h->d_scalars; ta.counters = h->d_counters;
         ta.st = h->st; ta.st.cursor = h->d_ctrl+CW_TREE_CURSOR;
         ta.work_counter = h->d_ctrl+CW_WORK_TREE; ta.status = h->d_ctrl+CW_STATUS;
         ta.shard_rank = h->cfg.shard_rank; ta.shard_count = h->cfg.shard_count;
-        ta.hw_nbr = h->d_ctrl+CW_MAX_NBR; ta.hw_nodes = h->d_ctrl+CW_MAX_NODES;
-        const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax);
+        ta.hw_nbr = h->d_ctrl+CW_MAX_NBR; ta.hw_nodes = h->d_ctrl+CW_MAX_NODES; ta.hw_width = h->d_ctrl+CW_MAX_WIDTH;
+        const size_t smem = h->tree_work_global ? 0 : h->tree_warps*ta.wk_stride;
         begin(K_TREE);
-        k_tree<<<h->tree_grid, TREE_THREADS, smem, s>>>(ta);
+        k_tree<<<h->tree_grid, 32*h->tree_warps, smem, s>>>(ta);
         end(K_TREE);
     }
     const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
@@ -373,14 +396,14 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         BornArgs ba{};
         ba.c = pc;
         ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, 1};
-        ba.svS = h->d_svS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
+        ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
         const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
         begin(K_BORN);
         if (cutoff) k_born<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
         else k_born<false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
         end(K_BORN);
         BornFinishArgs bf{};
-        bf.np = h->np; bf.posq = h->d_posq.p; bf.orig = h->d_orig.p; bf.bsum = h->d_bsum; bf.svS = h->d_svS; bf.vS = h->d_vS.p;
+        bf.np = h->np; bf.posq = h->d_posq.p; bf.orig = h->d_orig.p; bf.bsum = h->d_bsum; bf.accS = h->d_accS; bf.vS = h->d_vS.p;
         bf.radius = h->d_radius.p; bf.alpha = h->d_alpha.p;
         bf.vsf = h->d_vsf.p; bf.born = h->d_born.p; bf.bfp = h->d_bfp.p; bf.brw = h->d_brw.p; bf.gbj = h->d_gbj.p;
         bf.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
@@ -419,7 +442,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     if (v1 && (phase_mask & PH_GAMMA)) {
         GammaArgs gm{};
         gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.dacc = h->d_dacc; gm.vS = h->d_vS.p;
-        gm.force = h->d_force; gm.scratch = h->d_gamma_scratch.p; gm.scratch_stride = (size_t) 5*h->tree_cap*sizeof(float);
+        gm.gacc = h->d_gacc; gm.scratch = h->d_gamma_scratch.p; gm.scratch_stride = (size_t) 5*h->tree_cap*sizeof(float);
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
         begin(K_GAMMA);
         k_tree_gamma<<<h->gamma_grid, TREE_THREADS, 0, s>>>(gm);
@@ -427,9 +450,10 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     }
     if (phase_mask & PH_FINISH) {
         FinishArgs fa{};
-        fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.force = h->d_force; fa.scalars = h->d_scalars;
+        fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.accL = h->d_accL; fa.accS = h->d_accS; fa.scalars = h->d_scalars;
+        fa.inv_roffset = (float) (1.0/h->k.roffset);
         fa.status = h->d_ctrl+CW_STATUS;
-        if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; }
+        if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; }
         fa.padded_n = sink ? sink->padded_n : 0;
         if (sink && sink->ptr) {
             if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;
@@ -454,22 +478,19 @@ int fetch_status(agbnp_b200* h, cudaStream_t s) {
     return h->h_ctrl[CW_STATUS];
 }
 
-void set_tree_smem(agbnp_b200* h) {
-    const size_t smem = TREE_WARPS*tree_smem_per_warp(h->nbrmax);
-    if (smem > 200*1024) throw CudaFail{"level-2 neighbor capacity does not fit in shared memory"};
-    CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-}
-
 // grow whatever overflowed; returns false if a limit was hit.  ctrl = the evaluation's control words (host copy).
-bool grow(agbnp_b200* h, const int* ctrl) {
+bool grow(agbnp_b200* h, const int* ctrl, bool ahead = false) {
     const int status = ctrl[CW_STATUS];
     CK(cudaDeviceSynchronize());                       // buffers below may still be in use by queued evaluations
-    if (status & ST_NBR_OVERFLOW) {
-        if (h->nbrmax >= 1024) return false;
-        h->nbrmax *= 2;
-        set_tree_smem(h);
-    }
-    if (status & ST_NODE_OVERFLOW) { if (h->tree_cap >= 16384) return false; h->tree_cap *= 2; alloc_tree_scratch(h); }
+    bool tree = false;
+    // a real overflow doubles (its high-water mark is only a lower bound); growing ahead of need takes small steps so that
+    // the work arrays keep fitting in shared memory
+    auto bump = [ahead](int v, int seen) { return (std::max(ahead ? v + v/8 : 2*v, seen + seen/8) + 31)/32*32; };
+    if (status & ST_NBR_OVERFLOW) { if (h->nbrmax >= 1024) return false; h->nbrmax = std::min(1024, bump(h->nbrmax, ctrl[CW_MAX_NBR])); tree = true; }
+    if (status & ST_NODE_OVERFLOW) { if (h->tree_cap >= 16384) return false; h->tree_cap = std::min(16384, bump(h->tree_cap, ctrl[CW_MAX_NODES])); tree = true; }
+    if (status & ST_LEVEL_OVERFLOW) { if (h->tree_wcap >= 16384) return false; h->tree_wcap = std::min(16384, bump(h->tree_wcap, ctrl[CW_MAX_WIDTH])); tree = true; }
+    h->tree_wcap = std::min(h->tree_wcap, h->tree_cap);
+    if (tree) alloc_tree_scratch(h);
     if (status & ST_TREE_OVERFLOW) {
         const int need = ctrl[CW_TREE_CURSOR];
         alloc_store(h, std::max(need + need/4 + 4096, h->st.cap*2));
@@ -481,13 +502,18 @@ bool grow(agbnp_b200* h, const int* ctrl) {
 // completed evaluation exceeds 3/4 of its capacity
 void grow_ahead(agbnp_b200* h, const int* ctrl) {
     int fake[CW_COUNT] = {};
-    if (ctrl[CW_MAX_NBR]*4 > h->nbrmax*3 && h->nbrmax < 1024) fake[CW_STATUS] |= ST_NBR_OVERFLOW;
-    if (ctrl[CW_MAX_NODES]*4 > h->tree_cap*3 && h->tree_cap < 16384) fake[CW_STATUS] |= ST_NODE_OVERFLOW;
+    fake[CW_MAX_NBR] = ctrl[CW_MAX_NBR]; fake[CW_MAX_NODES] = ctrl[CW_MAX_NODES]; fake[CW_MAX_WIDTH] = ctrl[CW_MAX_WIDTH];
+    if (ctrl[CW_MAX_NBR]*10 > h->nbrmax*9 && h->nbrmax < 1024) fake[CW_STATUS] |= ST_NBR_OVERFLOW;
+    if (ctrl[CW_MAX_NODES]*10 > h->tree_cap*9 && h->tree_cap < 16384) fake[CW_STATUS] |= ST_NODE_OVERFLOW;
+    if (ctrl[CW_MAX_WIDTH]*10 > h->tree_wcap*9 && h->tree_wcap < h->tree_cap) fake[CW_STATUS] |= ST_LEVEL_OVERFLOW;
     if ((long long) ctrl[CW_TREE_CURSOR]*8 > (long long) h->st.cap*7) { fake[CW_STATUS] |= ST_TREE_OVERFLOW; fake[CW_TREE_CURSOR] = ctrl[CW_TREE_CURSOR]; }
-    if (fake[CW_STATUS]) grow(h, fake);
+    // applied at the start of the next evaluation (prepare): the buffers still hold this evaluation's by-products
+    // (agbnp_b200_get reads the stored tree)
+    if (fake[CW_STATUS]) { std::memcpy(h->ahead, fake, sizeof(fake)); h->ahead_pending = true; }
 }
 
 void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_posq_in, cudaStream_t s) {
+    if (h->ahead_pending) { h->ahead_pending = false; grow(h, h->ahead, true); }
     const int interval = h->cfg.reorder_interval > 0 ? h->cfg.reorder_interval : 500;
     if (!h->order_valid || h->evals_since_sort >= interval) {
         std::vector<float> tmp;
@@ -621,11 +647,9 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->have_events = true;
         CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
-        h->tree_grid = h->num_sm*2;
         h->gamma_grid = h->num_sm*4;
         h->gb_grid = h->num_sm*4;
         h->pq_grid = h->num_sm*4;
-        set_tree_smem(h);
         const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*2*sizeof(DerivSmem));
         CK(cudaFuncSetAttribute(k_born<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
@@ -773,10 +797,10 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
         CK(cudaDeviceSynchronize());
         const int n = h->n, np = h->np;
         auto need = [&](size_t b) { if (bytes < b) throw CudaFail{"agbnp_b200_get: output buffer too small"}; };
-        auto per_atom_d = [&](const double* dptr, double* out) {
-            std::vector<double> t(np);
-            CK(cudaMemcpy(t.data(), dptr, sizeof(double)*np, cudaMemcpyDeviceToHost));
-            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) out[h->orig[k]] = t[k];
+        auto per_atom_w = [&](const float4* dptr, double* out) {
+            std::vector<float4> t(np);
+            CK(cudaMemcpy(t.data(), dptr, sizeof(float4)*np, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) out[h->orig[k]] = t[k].w;
         };
         auto per_atom_f = [&](const float* dptr, double* out) {
             std::vector<float> t(np);
@@ -785,12 +809,12 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
         };
         double* od = (double*) host_out;
         switch (what) {
-        case AGBNP_B200_GET_SELF_VOLUME_VDW: need(sizeof(double)*n); per_atom_d(h->d_svS, od); break;
-        case AGBNP_B200_GET_SELF_VOLUME_LARGE: need(sizeof(double)*n); per_atom_d(h->d_svL, od); break;
+        case AGBNP_B200_GET_SELF_VOLUME_VDW: need(sizeof(double)*n); per_atom_w(h->d_accS, od); break;
+        case AGBNP_B200_GET_SELF_VOLUME_LARGE: need(sizeof(double)*n); per_atom_w(h->d_accL, od); break;
         case AGBNP_B200_GET_SURFACE_AREA: {
             need(sizeof(double)*n);
             std::vector<double> a(n), b(n);
-            per_atom_d(h->d_svL, a.data()); per_atom_d(h->d_svS, b.data());
+            per_atom_w(h->d_accL, a.data()); per_atom_w(h->d_accS, b.data());
             for (int i = 0; i < n; i++) od[i] = (a[i]-b[i])/h->k.roffset;
             break;
         }
@@ -816,7 +840,8 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             CK(cudaMemcpy(sc, h->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost));
             int cur = 0;
             CK(cudaMemcpy(&cur, h->d_ctrl+CW_TREE_CURSOR, sizeof(int), cudaMemcpyDeviceToHost));
-            od[0] = sc[SC_EVOL_L]; od[1] = sc[SC_EVOL_S]; od[2] = sc[SC_EGB]; od[3] = sc[SC_EVDW];
+            const double ir = (double) (float) (1.0/h->k.roffset);          // the factor k_finish applies
+            od[0] = sc[SC_EVOL_L]*ir; od[1] = -sc[SC_EVOL_S]*ir; od[2] = sc[SC_EGB]; od[3] = sc[SC_EVDW];
             od[4] = sc[SC_VOL_L]; od[5] = sc[SC_VOL_S]; od[6] = sc[SC_SPARE0]; od[7] = (double) (cur - h->nh);
             break;
         }
@@ -910,10 +935,10 @@ int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* byte
     if (!h || !d_ptr || !bytes) return AGBNP_B200_ERR_ARG;
     if (!h->order_valid || h->params_dirty) { h->err = "agbnp_b200_shard_buffer: call shard_phase(0) first"; return AGBNP_B200_ERR_ARG; }
     switch (which) {
-    case AGBNP_B200_BUF_SELFVOL: *d_ptr = h->d_svS; *bytes = sizeof(double)*2*h->np; break;
+    case AGBNP_B200_BUF_SELFVOL: *d_ptr = h->d_accL; *bytes = sizeof(float4)*2*h->np; break;
     case AGBNP_B200_BUF_YQ: *d_ptr = h->d_gbacc; *bytes = sizeof(float4)*h->np; break;
     case AGBNP_B200_BUF_WU: *d_ptr = h->d_dacc; *bytes = sizeof(float4)*h->np; break;
-    case AGBNP_B200_BUF_FORCE: *d_ptr = h->d_force; *bytes = sizeof(unsigned long long)*3*h->np; break;
+    case AGBNP_B200_BUF_FORCE: *d_ptr = h->d_gacc; *bytes = sizeof(float4)*h->np; break;
     case AGBNP_B200_BUF_ENERGY: *d_ptr = h->d_scalars; *bytes = sizeof(double)*SC_COUNT; break;
     default: return AGBNP_B200_ERR_ARG;
     }

@@ -137,7 +137,7 @@ __device__ __forceinline__ void pq_masks(const float* s_cx, const float* s_cy, c
 struct BornArgs {
     PairCommon c;
     PairUnits u;
-    const double* svS;          // self volumes (vdW radii)
+    const float4* accS;         // .w = self volumes (vdW radii), from k_tree
     const double* vS;           // atomic volumes (vdW radii)
     float* bsum;                // out [np], zeroed slab
     unsigned long long* counters;
@@ -183,7 +183,7 @@ __device__ __forceinline__ void born_load(const BornArgs& A, int blk, int lane, 
     const float4 p = A.c.posq[j];
     const double vj = A.vS[j];
     s.x[lane] = p.x; s.y[lane] = p.y; s.z[lane] = p.z;
-    s.w[lane] = vj > 0 ? PIFAC*((float) A.svS[j]/(float) vj) : 0.f;
+    s.w[lane] = vj > 0 ? PIFAC*(A.accS[j].w/(float) vj) : 0.f;
     s.tj[lane] = A.c.tj[j];
 }
 
@@ -251,7 +251,8 @@ struct BornFinishArgs {
     const float4* posq;
     const int* orig;
     const float* bsum;
-    const double *svS, *vS;
+    const float4* accS;
+    const double* vS;
     const float *radius, *alpha;
     float *vsf, *born, *bfp, *brw;
     float4* gbj;                // out [3*np]: GB atom records in broadcast form (see k_gb)
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
             A.born[a] = br;
             A.bfp[a] = fp;
             const double va = A.vS[a];
-            A.vsf[a] = va > 0 ? (float) A.svS[a]/(float) va : 0.f;
+            A.vsf[a] = va > 0 ? A.accS[a].w/(float) va : 0.f;
             const float q = pa.w, al = A.alpha[a];
             const float bh = br + A.hb_radius;
             const float bh3 = bh*bh*bh;
@@ -653,9 +654,11 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
 struct FinishArgs {
     int np, n;
     const int* orig;
-    const unsigned long long* force;    // fixed-point part: surface-tension (tree) forces
-    const float4* gbacc;                // float part: GB pair force (xyz)           -- null for version 0
-    const float4* dacc;                 // float part: Born-radius derivative force  -- null for version 0
+    const float4 *accL, *accS;          // surface-tension gradients of sum coef*gamma*vol (enlarged / vdW radii), from k_tree
+    const float4* gbacc;                // GB pair force (xyz)                              -- null for version 0
+    const float4* dacc;                 // Born-radius derivative pair force (xyz)          -- null for version 0
+    const float4* gacc;                 // force of the W+U tree sweep (xyz)                -- null for version 0
+    float inv_roffset;                  // nu = +gamma/roffset (enlarged radii), -gamma/roffset (vdW radii)
     float* out_f32;                     // layout 0: float[3n] interleaved, +=
     unsigned long long* out_fixed;      // layout 1: OpenMM fixed point [3][padded_n], atomic +=
     double* out_f64;                    // internal: double[3n] interleaved, = (host path)
@@ -670,7 +673,8 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
     if (A.status && *A.status != 0) return;
     if (k == 0) {
-        const double e = A.scalars[SC_EVOL_L] + A.scalars[SC_EVOL_S] + A.scalars[SC_EGB] + A.scalars[SC_EVDW];
+        // E1 + E2 (ReferenceAGBNPKernels.cpp:188,233,266) + GB + vdW
+        const double e = (A.scalars[SC_EVOL_L] - A.scalars[SC_EVOL_S])*(double) A.inv_roffset + A.scalars[SC_EGB] + A.scalars[SC_EVDW];
         A.scalars[SC_SPARE0] = e;
         if (A.energy_out) *A.energy_out = e;
         if (A.energy_accum) atomicAdd(A.energy_accum, e);
@@ -678,11 +682,14 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     if (k >= A.np) return;
     const int o = A.orig[k];
     if (o < 0) return;
-    double fx = (double) (long long) A.force[k]/FORCE_SCALE, fy = (double) (long long) A.force[(size_t) A.np+k]/FORCE_SCALE,
-           fz = (double) (long long) A.force[2*(size_t) A.np+k]/FORCE_SCALE;
+    // force = -gradient: -(grad_L - grad_S)/roffset
+    const float4 l = A.accL[k], s = A.accS[k];
+    double fx = ((double) s.x - (double) l.x)*(double) A.inv_roffset, fy = ((double) s.y - (double) l.y)*(double) A.inv_roffset,
+           fz = ((double) s.z - (double) l.z)*(double) A.inv_roffset;
     if (A.gbacc) {
-        const float4 g = A.gbacc[k], d = A.dacc[k];
-        fx += (double) g.x + (double) d.x; fy += (double) g.y + (double) d.y; fz += (double) g.z + (double) d.z;
+        const float4 g = A.gbacc[k], d = A.dacc[k], t = A.gacc[k];
+        fx += (double) g.x + (double) d.x + (double) t.x; fy += (double) g.y + (double) d.y + (double) t.y;
+        fz += (double) g.z + (double) d.z + (double) t.z;
     }
     if (A.out_f64) { A.out_f64[3*o+0] = fx; A.out_f64[3*o+1] = fy; A.out_f64[3*o+2] = fz; }
     if (A.out_f32) { A.out_f32[3*o+0] += (float) fx; A.out_f32[3*o+1] += (float) fy; A.out_f32[3*o+2] += (float) fz; }

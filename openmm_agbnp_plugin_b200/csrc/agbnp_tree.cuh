@@ -5,11 +5,19 @@
 //     lowest-index atom is that atom) is owned by ONE WARP, which builds it breadth-first, level by level
 //     (candidate enumeration by warp prefix sums, acceptance compaction by ballots), so subtrees never communicate;
 //   * the large-radius build (S1), the vdW-radius rescan (S3) and both up-sweeps (S2, second half of S3) are fused:
-//     a node's vdW-radius Gaussian is computed when the node is created, and one bottom-up pass yields both energies,
-//     both sets of self-volumes and the combined surface-tension force;
+//     a node's vdW-radius Gaussian is computed when the node is created, and two bottom-up passes over the finished
+//     subtree yield both sets of self-volumes and both surface-tension gradients (the energies need no tree
+//     accumulation: E = sum over nodes of coef * gamma_1..n * volume);
 //   * topology-deciding arithmetic (overlap volume, inclusion threshold, sibling sort key) is FP64 with the expression
 //     structure of gaussvol.cpp:60-93; everything fed to energies/forces downstream is rounded to FP32.
-// Only what the later "gamma" sweep (S10+S11 merged, linear in nu) needs is persisted to HBM (TreeStore).
+// Memory plan per warp:
+//   shared memory  -- everything on the dependent chain of the build: level-2 neighbor list, per-node parent/atom/child
+//                     ranges (shorts), and for the level being expanded the candidate prefix sums, sort keys and sibling
+//                     permutation.  (If a system needs capacities that
+//                     do not fit, the same code runs with these arrays in a per-warp global scratch: TreeArgs::wk_global.)
+//   global staging -- streamed, coalesced, one round trip per level: the nodes' Gaussians (read once by their children's
+//                     candidates), the per-node sweep records and the children-to-parent sums of the sweeps.
+// Only what the later "gamma" sweep (S10+S11 merged, linear in nu) needs is persisted compactly (TreeStore).
 #ifndef AGBNP_TREE_CUH_
 #define AGBNP_TREE_CUH_
 
@@ -17,9 +25,12 @@
 
 namespace agbnp_b200_impl {
 
-constexpr int TREE_THREADS = 256;
+constexpr int TREE_THREADS = 256;   // k_tree_gamma
 constexpr int TREE_WARPS = TREE_THREADS/32;
 constexpr int MAX_LEVELS = 10;      // level index 1..8 used (MAX_ORDER 8)
+#ifndef SCREEN_UNROLL
+#define SCREEN_UNROLL 1             // candidates per lane and trip of the FP32 screen (measured: 1 is fastest on B200)
+#endif
 
 // persisted per-node records (SoA) for the gamma sweep and for the topology dump
 struct TreeStore {
@@ -33,6 +44,15 @@ struct TreeStore {
     short *parent, *cstart, *ccount, *rank;       // slots relative to the subtree start; rank among siblings
 };
 
+// a node's two Gaussians (enlarged / vdW radii) in the root's frame: positions are relative to the root atom
+struct __align__(16) NodeGauss {
+    double aL, vL, xL, yL, zL;
+    double aS, vS, xS, yS, zS;
+    float4 f0;               // (aL, vL, xL, yL) rounded to float: all the FP32 screen reads
+    float4 f1;               // (zL rounded to float, gamma_1..n, -, -)
+};
+static_assert(sizeof(NodeGauss) == 112, "NodeGauss layout");
+
 struct TreeArgs {
     int nh, nhb, np;
     const float4* posq;
@@ -45,30 +65,35 @@ struct TreeArgs {
     const float* rc2max;
     int nbins;
     double volmina, volminb, min_gvol, swd;
-    float inv_roffset;
+    float screen;                     // FP32 screen threshold: VOLMINA less the screen's error margin
     int max_order;
-    unsigned char* scratch;
-    size_t scratch_stride;
-    int cap, nbrmax;
-    double *svS, *svL;
-    unsigned long long* force;        // [3][np] fixed point
+    int cap, wcap, nbrmax;            // capacities: nodes per root, nodes per level, level-2 neighbors per root
+    unsigned char* stage;             // per-warp global staging (tree_stage_bytes(cap) each)
+    size_t stage_stride;
+    unsigned char* wk_global;         // per-warp work arrays in global memory, or nullptr = shared memory
+    size_t wk_stride;
+    float4 *accL, *accS;              // [np] out: (gradient x,y,z of sum coef*gamma*vol, self volume), enlarged / vdW radii
     double* scalars;
     unsigned long long* counters;
     TreeStore st;
     int* work_counter;
     int* status;
     int shard_rank, shard_count;      // roots are dealt to shards block-cyclically (blocks of 32 sorted heavy atoms)
-    int *hw_nbr, *hw_nodes;           // high-water marks: level-2 neighbors / nodes of one root
+    int *hw_nbr, *hw_nodes, *hw_width;   // high-water marks: level-2 neighbors / nodes / widest level of one root
 };
 
-__host__ __device__ inline size_t tree_scratch_bytes(int cap) {
-    size_t b = (size_t) cap*(11*sizeof(double) + 24*sizeof(float) + sizeof(int) + 6*sizeof(short) + 1) + 2*sizeof(int);
-    return (b + 255) & ~(size_t) 255;
-}
-__host__ __device__ inline size_t tree_smem_per_warp(int nbrmax) {
-    size_t b = (size_t) nbrmax*3*sizeof(double) + (size_t) 5*(nbrmax+1)*sizeof(float) + (size_t) nbrmax*sizeof(int)
-             + (size_t) (MAX_LEVELS+2)*sizeof(int);
+__host__ __device__ inline size_t tree_work_bytes(int nbrmax, int cap, int wcap) {
+    size_t b = (size_t) wcap*sizeof(double)                   // key
+             + (size_t) (wcap+2)*sizeof(int)                  // pref
+             + (size_t) wcap*sizeof(int)                      // cand
+             + (size_t) nbrmax*6*sizeof(float)                // nbx, nby, nbz, nba, nbv, nbi
+             + (size_t) (MAX_LEVELS+2)*sizeof(int)            // lvs
+             + (size_t) (4*cap + 2*wcap)*sizeof(short);       // parent, nbr, cstart, ccount, perm, gend
     return (b + 15) & ~(size_t) 15;
+}
+__host__ __device__ inline size_t tree_stage_bytes(int cap) {
+    size_t b = (size_t) cap*(sizeof(NodeGauss) + 8*sizeof(float4) + sizeof(short));
+    return (b + 255) & ~(size_t) 255;
 }
 
 // polynomial switching function and derivative (gaussvol.cpp:18-41)
@@ -94,54 +119,140 @@ __device__ __forceinline__ double overlap_volume(double a1, double v1, double a2
     return (v1*v2)*(u*sqrt(u))*ef;
 }
 
-struct TreeScratch {
-    double *gLa, *gLv, *gLx, *gLy, *gLz, *gSa, *gSv, *gSx, *gSy, *gSz, *key;
-    float *sfpL, *dvvL, *dLx, *dLy, *dLz, *volS, *sfpS, *dvvS, *dSx, *dSy, *dSz, *gam;
-    float *aEL, *afL, *apLx, *apLy, *apLz, *apsL, *aES, *afS, *apSx, *apSy, *apSz, *apsS;
-    int* pref;               // [cap+2] exclusive prefix of candidate counts of the level being expanded
-    short *parent, *nbr, *cstart, *ccount, *perm, *gend;
-    unsigned char* lvl;
-    __device__ void bind(unsigned char* base, int cap) {
-        double* d = (double*) base;
-        gLa = d; gLv = d+cap; gLx = d+2*cap; gLy = d+3*cap; gLz = d+4*cap;
-        gSa = d+5*cap; gSv = d+6*cap; gSx = d+7*cap; gSy = d+8*cap; gSz = d+9*cap; key = d+10*cap;
-        float* f = (float*) (d+11*(size_t) cap);
-        sfpL = f; dvvL = f+cap; dLx = f+2*cap; dLy = f+3*cap; dLz = f+4*cap; volS = f+5*cap; sfpS = f+6*cap;
-        dvvS = f+7*cap; dSx = f+8*cap; dSy = f+9*cap; dSz = f+10*cap; gam = f+11*cap;
-        float* a = f+12*(size_t) cap;
-        aEL = a; afL = a+cap; apLx = a+2*cap; apLy = a+3*cap; apLz = a+4*cap; apsL = a+5*cap;
-        aES = a+6*cap; afS = a+7*cap; apSx = a+8*cap; apSy = a+9*cap; apSz = a+10*cap; apsS = a+11*cap;
-        pref = (int*) (a+12*(size_t) cap);
-        short* s = (short*) (pref + (cap+2 - (cap & 1)));      // keeps 4-byte alignment irrelevant for shorts; even count
-        parent = s; nbr = s+cap; cstart = s+2*cap; ccount = s+3*cap; perm = s+4*cap; gend = s+5*cap;
-        lvl = (unsigned char*) (s+6*(size_t) cap);
+// per-warp work arrays (shared memory, or global scratch for oversize capacities)
+struct TreeWork {
+    double* key;             // [wcap] sort key (switched volume) of the level being created
+    int* pref;               // [wcap+1] exclusive prefix of candidate counts of the level being expanded
+    int* cand;               // [wcap] candidates that passed the FP32 screen: parent slot | neighbor index << 16
+    float *nbx, *nby, *nbz;  // [nbrmax] level-2 candidate positions (absolute, float as given)
+    float *nba, *nbv;        // [nbrmax] their enlarged-radius Gaussian exponent / volume rounded to float (screen only)
+    int* nbi;                // [nbrmax] their sorted atom indices
+    int* lvs;                // [MAX_LEVELS+2] first slot of each level
+    short *parent, *nbr, *cstart, *ccount;   // [cap]
+    short *perm, *gend;      // [wcap] sorted position -> slot, end of the sibling group (both relative to the level start)
+    __device__ void bind(unsigned char* base, int nbrmax, int cap, int wcap) {
+        key = (double*) base;
+        pref = (int*) (key+wcap);
+        cand = pref+wcap+2;
+        nbx = (float*) (cand+wcap); nby = nbx+nbrmax; nbz = nby+nbrmax; nba = nbz+nbrmax; nbv = nba+nbrmax;
+        nbi = (int*) (nbv+nbrmax);
+        lvs = nbi+nbrmax;
+        parent = (short*) (lvs+MAX_LEVELS+2); nbr = parent+cap; cstart = nbr+cap; ccount = cstart+cap;
+        perm = ccount+cap; gend = perm+wcap;
     }
 };
 
+// segmented inclusive scan step: lanes with equal key are contiguous; adds the value `d` lanes below if it belongs to the
+// same segment
+__device__ __forceinline__ void seg_step(float (&v)[10], bool take, int d) {
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+        const float t = __shfl_up_sync(FULL, v[c], d);
+        if (take) v[c] += t;
+    }
+}
+
+__device__ __forceinline__ void hu_store(float4* hu, int node, const float (&v)[10]) {
+    hu[4*node] = make_float4(v[0], v[1], v[2], v[3]);
+    hu[4*node+1] = make_float4(v[4], v[5], v[6], v[7]);
+    hu[4*node+2] = make_float4(v[8], v[9], 0.f, 0.f);
+}
+
+// the bottom-up sweep over a finished subtree, both radius sets at once (gaussvol.cpp:400-487): self-volumes and the
+// gradients of sum coef*gamma*vol w.r.t. every atom of the subtree, added to accL/accS[atom] as one vector red.global
+// per node and radius set.   sw[2*sl] = (vol, sfp, dvv1, a_i/a_1i), sw[2*sl+1] = (dv1 x, y, z, gamma_1..n).
+// A node hands (psi, dvv1 F, dv1 F + P a_1/a_1i) to its parent (gaussvol.cpp:476-484).  Siblings are contiguous, so the
+// sums over a parent's children are a segmented warp scan over the child level; the last child of each parent stores
+// the totals into hu[4*parent ..] (global staging, one plain store per parent, read back one level later).
+__device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL, const float4* swS, float4* hu, int nlev, int r, int lane,
+                                           float4* accL, float4* accS) {
+    for (int lev = nlev; lev >= 1; lev--) {
+        const int b = W.lvs[lev], e = W.lvs[lev+1];
+        const float coefp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
+        int carry_key = -2;                         // parent whose children run across the chunk boundary
+        float carry[10];
+#pragma unroll
+        for (int c = 0; c < 10; c++) carry[c] = 0.f;
+        for (int s0 = b; s0 < e; s0 += 32) {
+            const int sl = s0+lane;
+            const bool valid = sl < e;
+            int key = -3-lane;                      // distinct per lane: never merges
+            float v[10];
+#pragma unroll
+            for (int c = 0; c < 10; c++) v[c] = 0.f;
+            if (valid) {
+                const float4 l0 = swL[2*sl], l1 = swL[2*sl+1], s0v = swS[2*sl], s1v = swS[2*sl+1];
+                float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, h2 = h0;
+                if (W.ccount[sl] > 0) { h0 = hu[4*sl]; h1 = hu[4*sl+1]; h2 = hu[4*sl+2]; }
+                const int ia = W.nbr[sl];
+                const int ja = ia == 0 ? r : W.nbi[ia-1];
+                key = W.parent[sl];
+                {   // enlarged radii
+                    const float ps = coefp*l0.x + h0.x, F = coefp*l0.y*l1.w + h0.y, px = h0.z, py = h0.w, pz = h1.x;
+                    const float c2a = l0.w, c2b = 1.f-l0.w;
+                    // gradient w.r.t. the node's last atom (gaussvol.cpp:467-474)
+                    atomicAdd(&accL[ja], make_float4(fmaf(px, c2a, -l1.x*F), fmaf(py, c2a, -l1.y*F), fmaf(pz, c2a, -l1.z*F), ps));
+                    v[0] = ps; v[1] = l0.z*F; v[2] = fmaf(px, c2b, l1.x*F); v[3] = fmaf(py, c2b, l1.y*F); v[4] = fmaf(pz, c2b, l1.z*F);
+                }
+                {   // vdW radii
+                    const float ps = coefp*s0v.x + h1.y, F = coefp*s0v.y*s1v.w + h1.z, px = h1.w, py = h2.x, pz = h2.y;
+                    const float c2a = s0v.w, c2b = 1.f-s0v.w;
+                    atomicAdd(&accS[ja], make_float4(fmaf(px, c2a, -s1v.x*F), fmaf(py, c2a, -s1v.y*F), fmaf(pz, c2a, -s1v.z*F), ps));
+                    v[5] = ps; v[6] = s0v.z*F; v[7] = fmaf(px, c2b, s1v.x*F); v[8] = fmaf(py, c2b, s1v.y*F); v[9] = fmaf(pz, c2b, s1v.z*F);
+                }
+            }
+            if (lev == 1) break;                    // the root hands nothing up
+            // children of the carried parent continue in this chunk?
+            const int key0 = __shfl_sync(FULL, key, 0);
+            if (carry_key >= 0) {
+                if (key0 == carry_key) {
+                    if (lane == 0) {
+#pragma unroll
+                        for (int c = 0; c < 10; c++) v[c] += carry[c];
+                    }
+                } else if (lane == 0) hu_store(hu, carry_key, carry);
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int ku = __shfl_up_sync(FULL, key, d);
+                seg_step(v, lane >= d && ku == key, d);
+            }
+            const int kn = __shfl_down_sync(FULL, key, 1);
+            const bool tail = valid && (lane == 31 || kn != key);
+            const int last = min(31, e-1-s0);       // last valid lane of this chunk: its segment may continue
+            if (tail && lane != last) hu_store(hu, key, v);
+            carry_key = __shfl_sync(FULL, key, last);
+#pragma unroll
+            for (int c = 0; c < 10; c++) carry[c] = __shfl_sync(FULL, v[c], last);
+        }
+        if (lev > 1 && carry_key >= 0 && lane == 0) hu_store(hu, carry_key, carry);
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// k_tree: build + vdW rescan + fused up-sweep for every heavy root atom (reference S1-S3:
+// k_tree: build + vdW rescan + up-sweeps for every heavy root atom (reference S1-S3:
 // gaussvol.cpp:103-250,254-327,389-519,589-606; ReferenceAGBNPKernels.cpp:290-380)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
+__global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nbrmax = A.nbrmax, cap = A.cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int nbrmax = A.nbrmax, cap = A.cap, wcap = A.wcap;
+    const int gwarp = blockIdx.x*nwarp + warp;
 
-    unsigned char* sm = smem_raw + (size_t) warp*tree_smem_per_warp(nbrmax);
-    double* nb_x = (double*) sm;
-    double* nb_y = nb_x+nbrmax;
-    double* nb_z = nb_y+nbrmax;
-    float* acc = (float*) (nb_z+nbrmax);            // [5][nbrmax+1]: svS, svL, gx, gy, gz; index 0 = root, 1+k = neighbor k
-    int* nb_idx = (int*) (acc+5*(nbrmax+1));
-    int* lvs = nb_idx+nbrmax;                       // [MAX_LEVELS+2]
-    const int accs = nbrmax+1;
-
-    TreeScratch S;
-    S.bind(A.scratch + (size_t) (blockIdx.x*TREE_WARPS+warp)*A.scratch_stride, cap);
+    TreeWork W;
+    W.bind(A.wk_global ? A.wk_global + (size_t) gwarp*A.wk_stride : smem_raw + (size_t) warp*tree_work_bytes(nbrmax, cap, wcap),
+           nbrmax, cap, wcap);
+    unsigned char* stage = A.stage + (size_t) gwarp*A.stage_stride;
+    NodeGauss* G = (NodeGauss*) stage;
+    float4* swL = (float4*) (G+cap);
+    float4* swS = swL + 2*(size_t) cap;
+    float4* hu = swS + 2*(size_t) cap;              // sweep hand-up sums, 4 float4 per node
+    short* rk = (short*) (hu + 4*(size_t) cap);
 
     double eL_tot = 0, eS_tot = 0, vsumL = 0, vsumS = 0;     // per-lane partial sums, reduced at the end
     unsigned long long c2_tot = 0, c3_tot = 0, m_tot = 0;
-    int hw_nn = 0, hw_slots = 0;
+    int hw_nn = 0, hw_slots = 0, hw_w = 0;
 
     for (;;) {
         int r = 0;
@@ -157,7 +268,6 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
         const int orig_r = A.orig[r];
         const int rb = A.rcbin[r];
         const float rcmax = A.rc2max[rb];
-        for (int i = lane; i < 5*accs; i += 32) acc[i] = 0.f;
 
         // ---- level-2 candidate list: heavy atoms later in the caller's order within the conservative pair radius ----
         int nn = 0;
@@ -179,10 +289,8 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
                 if (ok) {
                     const int p = nn + __popc(am & lanemask_lt());
                     if (p < nbrmax) {
-                        nb_idx[p] = j;
-                        nb_x[p] = (double) pj.x - (double) pr.x;      // exact in double
-                        nb_y[p] = (double) pj.y - (double) pr.y;
-                        nb_z[p] = (double) pj.z - (double) pr.z;
+                        W.nbi[p] = j; W.nbx[p] = pj.x; W.nby[p] = pj.y; W.nbz[p] = pj.z;
+                        W.nba[p] = (float) A.aL[j]; W.nbv[p] = (float) A.vL[j];
                     }
                 }
                 nn += __popc(am);
@@ -195,16 +303,20 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
         }
 
         // ---- slot 0: the root atom (gaussvol.cpp:130-148) ----
+        const float gam_r = A.gamma[r];
         if (lane == 0) {
-            S.gLa[0] = A.aL[r]; S.gLv[0] = A.vL[r]; S.gLx[0] = S.gLy[0] = S.gLz[0] = 0.0;
-            S.gSa[0] = A.aS[r]; S.gSv[0] = A.vS[r]; S.gSx[0] = S.gSy[0] = S.gSz[0] = 0.0;
-            S.key[0] = A.vL[r];
-            S.sfpL[0] = 1.f; S.dvvL[0] = 1.f; S.dLx[0] = S.dLy[0] = S.dLz[0] = 0.f;
-            S.volS[0] = (float) A.vS[r]; S.sfpS[0] = 1.f; S.dvvS[0] = 1.f; S.dSx[0] = S.dSy[0] = S.dSz[0] = 0.f;
-            S.gam[0] = A.gamma[r];
-            S.parent[0] = -1; S.nbr[0] = 0; S.cstart[0] = 0; S.ccount[0] = 0; S.perm[0] = 0; S.gend[0] = 1;
-            S.lvl[0] = 1;
-            lvs[1] = 0;
+            NodeGauss g;
+            g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
+            g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
+            g.f0 = make_float4((float) g.aL, (float) g.vL, 0.f, 0.f); g.f1 = make_float4(0.f, gam_r, 0.f, 0.f);
+            G[0] = g;
+            swL[0] = make_float4((float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            swS[0] = make_float4((float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            rk[0] = 0;
+            W.parent[0] = -1; W.nbr[0] = 0; W.cstart[0] = 1; W.ccount[0] = 0; W.perm[0] = 0; W.gend[0] = 1;
+            W.lvs[1] = 0;
+            eL_tot += (double) (gam_r*(float) g.vL); eS_tot += (double) (gam_r*(float) g.vS);
+            vsumL += (double) (float) g.vL; vsumS += (double) (float) g.vS;
         }
         __syncwarp();
 
@@ -212,21 +324,22 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
         int nslots = 1, ls = 0, le = 1, level = 1;
         bool failed = false;
         while (level < A.max_order) {           // a node at level >= MAX_ORDER gets no children (gaussvol.cpp:211)
-            int T, width = le-ls;
+            int T;
+            const int width = le-ls;
             if (level == 1) {
                 T = nn;
             } else {
-                // candidates of node at sorted position t: its younger siblings t+1 .. gend[t]-1 (gaussvol.cpp:221)
+                // candidates of the node at sorted position t: its younger siblings t+1 .. gend[t]-1 (gaussvol.cpp:221)
                 int carry = 0;
                 for (int t0 = 0; t0 < width; t0 += 32) {
                     const int t = t0+lane;
                     int c = 0;
-                    if (t < width) c = (int) S.gend[ls+t] - (ls+t) - 1;
+                    if (t < width) c = (int) W.gend[t] - t - 1;
                     const int inc = warp_incl_scan(c);
-                    if (t < width) S.pref[t] = carry + inc - c;
+                    if (t < width) W.pref[t] = carry + inc - c;
                     carry += __shfl_sync(FULL, inc, 31);
                 }
-                if (lane == 0) S.pref[width] = carry;
+                if (lane == 0) W.pref[width] = carry;
                 T = carry;
                 __syncwarp();
             }
@@ -234,30 +347,82 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
             else c3_tot += (lane == 0) ? (unsigned long long) T : 0ull;
 
             const int new_start = nslots;
-            for (int k0 = 0; k0 < T; k0 += 32) {
-                const int k = k0+lane;
-                const bool valid = k < T;
-                int p = 0, kn = k;
-                if (valid && level > 1) {
-                    int lo = 0, hi = width-1;
-                    while (lo < hi) {
-                        const int mid = (lo+hi+1) >> 1;
-                        if (S.pref[mid] <= k) lo = mid; else hi = mid-1;
+            const float cf = ((level+1) & 1) ? 1.f : -1.f;
+            const float coefp = cf/(float) (level+1);
+            // ---- phase A: FP32 screen of all T candidates.  A candidate whose FP32 overlap volume is below VOLMINA by
+            // more than the screen's error margin is certainly rejected by the exact test (s = 0 below VOLMINA,
+            // gaussvol.cpp:26-29,233); everything else goes, in candidate order, to the exact FP64 phase.
+            int nmaybe = 0;
+            const int nsteps = width > 1 ? 32 - __clz(width-1) : 0;      // binary-search trips (warp-uniform)
+            for (int k0 = 0; k0 < T; k0 += 32*SCREEN_UNROLL) {           // several candidates per lane in flight: the loads overlap
+                bool mb[SCREEN_UNROLL];
+                int pkv[SCREEN_UNROLL];
+#pragma unroll
+                for (int q4 = 0; q4 < SCREEN_UNROLL; q4++) {
+                    const int k = k0 + 32*q4 + lane;
+                    const bool valid = k < T;
+                    int p = 0, kn = k;
+                    if (level > 1) {
+                        int lo = 0, hi = width-1;
+                        for (int it = 0; it < nsteps; it++) {
+                            const int mid = (lo+hi+1) >> 1;
+                            if (W.pref[mid] <= k) lo = mid; else hi = mid-1;
+                        }
+                        const int u = min(lo + 1 + (k - W.pref[lo]), width-1);
+                        p = ls + W.perm[lo];
+                        kn = (int) W.nbr[ls + W.perm[u]] - 1;
                     }
-                    const int tpos = ls+lo;
-                    const int u = tpos + 1 + (k - S.pref[lo]);
-                    p = S.perm[tpos];
-                    kn = (int) S.nbr[S.perm[u]] - 1;
+                    kn = valid ? kn : 0;
+                    const float4 f0 = G[p].f0;                            // aL, vL, xL, yL rounded to float
+                    const float z1 = G[p].f1.x;
+                    const float a2 = W.nba[kn], v2 = W.nbv[kn];
+                    const float dx = (W.nbx[kn]-pr.x)-f0.z, dy = (W.nby[kn]-pr.y)-f0.w, dz = (W.nbz[kn]-pr.z)-z1;
+                    const float d2 = dx*dx + dy*dy + dz*dz;
+                    const float df = __fdividef(f0.x*a2, f0.x+a2);
+                    const float u = df*0.318309886f;
+                    const float est = f0.y*v2*(u*sqrtf(u))*__expf(-df*d2);
+                    mb[q4] = valid && est > A.screen;
+                    pkv[q4] = p | (kn << 16);
                 }
+#pragma unroll
+                for (int q4 = 0; q4 < SCREEN_UNROLL; q4++) {
+                    const unsigned mm = __ballot_sync(FULL, mb[q4]);
+                    if (mb[q4]) {
+                        const int q = nmaybe + __popc(mm & lanemask_lt());
+                        if (q < wcap) W.cand[q] = pkv[q4];
+                    }
+                    nmaybe += __popc(mm);
+                }
+            }
+            if (nmaybe > wcap) { hw_w = max(hw_w, nmaybe); if (lane == 0) atomicOr(A.status, ST_LEVEL_OVERFLOW); failed = true; break; }
+            __syncwarp();
+
+            // ---- phase B: exact FP64 evaluation of the screened candidates; accepted ones become nodes ----
+            for (int k0 = 0; k0 < nmaybe; k0 += 32) {
+                const int k = k0+lane;
+                const bool valid = k < nmaybe;
+                int p = 0, kn = 0;
                 bool accept = false;
                 double gvol = 0, df = 0, deltai = 0, s = 0, sp = 0, a1 = 0, v1 = 0, x1 = 0, y1 = 0, z1 = 0, a2 = 0, x2 = 0, y2 = 0, z2 = 0;
                 int j = 0;
+                double b1 = 0, w1 = 0, u1 = 0, q1 = 0, r1 = 0, b2 = 0, w2 = 0;
+                float gam = 0.f;
                 if (valid) {
-                    j = nb_idx[kn];
-                    a1 = S.gLa[p]; v1 = S.gLv[p]; x1 = S.gLx[p]; y1 = S.gLy[p]; z1 = S.gLz[p];
+                    const int pk = W.cand[k];
+                    p = pk & 0xffff; kn = pk >> 16;
+                    j = W.nbi[kn];
+                    const NodeGauss* gp = G+p;
+                    a1 = gp->aL; v1 = gp->vL; x1 = gp->xL; y1 = gp->yL; z1 = gp->zL;
                     a2 = A.aL[j];
                     const double v2 = A.vL[j];
-                    x2 = nb_x[kn]; y2 = nb_y[kn]; z2 = nb_z[kn];
+                    // the vdW-radius side is only needed for accepted candidates, but loading it here costs one memory
+                    // round trip instead of two
+                    b1 = gp->aS; w1 = gp->vS; u1 = gp->xS; q1 = gp->yS; r1 = gp->zS;
+                    b2 = A.aS[j]; w2 = A.vS[j];
+                    gam = gp->f1.y + A.gamma[j];                          // gaussvol.cpp:244
+                    x2 = (double) W.nbx[kn] - (double) pr.x;              // exact in double
+                    y2 = (double) W.nby[kn] - (double) pr.y;
+                    z2 = (double) W.nbz[kn] - (double) pr.z;
                     const double dx = x2-x1, dy = y2-y1, dz = z2-z1;
                     const double d2 = dx*dx + dy*dy + dz*dz;
                     gvol = overlap_volume(a1, v1, a2, v2, d2, deltai, df);
@@ -267,56 +432,58 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
                 const unsigned am = __ballot_sync(FULL, accept);
                 if (accept) {
                     const int slot = nslots + __popc(am & lanemask_lt());
-                    if (slot < cap) {
+                    if (slot < cap && slot-new_start < wcap) {
+                        NodeGauss g;
                         // enlarged radii: topology + up-sweep data (gaussvol.cpp:234-245)
-                        S.gLa[slot] = a1+a2; S.gLv[slot] = gvol;
-                        S.gLx[slot] = (x1*a1 + x2*a2)*deltai;
-                        S.gLy[slot] = (y1*a1 + y2*a2)*deltai;
-                        S.gLz[slot] = (z1*a1 + z2*a2)*deltai;
-                        S.key[slot] = s*gvol;
-                        S.sfpL[slot] = (float) (sp*gvol + s);
-                        S.dvvL[slot] = (float) (v1 > 0 ? gvol/v1 : 0.0);
+                        g.aL = a1+a2; g.vL = gvol;
+                        g.xL = (x1*a1 + x2*a2)*deltai; g.yL = (y1*a1 + y2*a2)*deltai; g.zL = (z1*a1 + z2*a2)*deltai;
+                        const double keyv = s*gvol;
+                        W.key[slot-new_start] = keyv;
                         const double mL = 2.0*df*gvol;                        // -dVdr
-                        S.dLx[slot] = (float) ((x2-x1)*mL); S.dLy[slot] = (float) ((y2-y1)*mL); S.dLz[slot] = (float) ((z2-z1)*mL);
+                        const float vl = (float) keyv;
+                        swL[2*slot] = make_float4(vl, (float) (sp*gvol + s), (float) (v1 > 0 ? gvol/v1 : 0.0), (float) a2/(float) g.aL);
+                        swL[2*slot+1] = make_float4((float) ((x2-x1)*mL), (float) ((y2-y1)*mL), (float) ((z2-z1)*mL), gam);
                         // vdW radii on the same topology (rescan, gaussvol.cpp:261-279)
-                        const double b1 = S.gSa[p], w1 = S.gSv[p], u1 = S.gSx[p], q1 = S.gSy[p], r1 = S.gSz[p];
-                        const double b2 = A.aS[j], w2 = A.vS[j];
                         const double ex = x2-u1, ey = y2-q1, ez = z2-r1;
                         double dS, dfS, sS, spS;
                         const double gS = overlap_volume(b1, w1, b2, w2, ex*ex + ey*ey + ez*ez, dS, dfS);
                         pol_switch(gS, A.volmina, A.volminb, A.swd, sS, spS);
-                        S.gSa[slot] = b1+b2; S.gSv[slot] = gS;
-                        S.gSx[slot] = (u1*b1 + x2*b2)*dS;
-                        S.gSy[slot] = (q1*b1 + y2*b2)*dS;
-                        S.gSz[slot] = (r1*b1 + z2*b2)*dS;
-                        S.volS[slot] = (float) (sS*gS);
-                        S.sfpS[slot] = (float) (spS*gS + sS);
-                        S.dvvS[slot] = (float) (w1 > 0 ? gS/w1 : 0.0);
+                        g.aS = b1+b2; g.vS = gS;
+                        g.xS = (u1*b1 + x2*b2)*dS; g.yS = (q1*b1 + y2*b2)*dS; g.zS = (r1*b1 + z2*b2)*dS;
+                        g.f0 = make_float4((float) g.aL, (float) g.vL, (float) g.xL, (float) g.yL);
+                        g.f1 = make_float4((float) g.zL, gam, 0.f, 0.f);
+                        G[slot] = g;
                         const double mS = 2.0*dfS*gS;
-                        S.dSx[slot] = (float) (ex*mS); S.dSy[slot] = (float) (ey*mS); S.dSz[slot] = (float) (ez*mS);
-                        S.gam[slot] = S.gam[p] + A.gamma[j];                  // gaussvol.cpp:244
-                        S.parent[slot] = (short) p; S.nbr[slot] = (short) (kn+1);
-                        S.cstart[slot] = 0; S.ccount[slot] = 0;
-                        S.lvl[slot] = (unsigned char) (level+1);
+                        const float vs = (float) (sS*gS);
+                        swS[2*slot] = make_float4(vs, (float) (spS*gS + sS), (float) (w1 > 0 ? gS/w1 : 0.0), (float) b2/(float) g.aS);
+                        swS[2*slot+1] = make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam);
+                        W.parent[slot] = (short) p; W.nbr[slot] = (short) (kn+1);
+                        W.cstart[slot] = 0; W.ccount[slot] = 0;
+                        // energies and volumes need no tree accumulation (gaussvol.cpp:425-433 summed over the subtree)
+                        const float cg = coefp*gam;
+                        eL_tot += (double) (cg*vl); eS_tot += (double) (cg*vs);
+                        vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
                     }
                 }
                 nslots += __popc(am);
             }
+            hw_slots = max(hw_slots, nslots); hw_w = max(hw_w, nslots-new_start);
             if (nslots > cap) { if (lane == 0) atomicOr(A.status, ST_NODE_OVERFLOW); failed = true; break; }
+            if (nslots-new_start > wcap) { if (lane == 0) atomicOr(A.status, ST_LEVEL_OVERFLOW); failed = true; break; }
             __syncwarp();
             if (nslots == new_start) break;
 
             // children ranges of the parents (children of one parent are contiguous: candidates are enumerated parent-major)
             for (int s0 = new_start; s0 < nslots; s0 += 32) {
                 const int sl = s0+lane;
-                if (sl < nslots && (sl == new_start || S.parent[sl] != S.parent[sl-1])) S.cstart[S.parent[sl]] = (short) sl;
+                if (sl < nslots && (sl == new_start || W.parent[sl] != W.parent[sl-1])) W.cstart[W.parent[sl]] = (short) sl;
             }
             __syncwarp();
             for (int s0 = new_start; s0 < nslots; s0 += 32) {
                 const int sl = s0+lane;
-                if (sl < nslots && (sl == nslots-1 || S.parent[sl+1] != S.parent[sl])) {
-                    const int p = S.parent[sl];
-                    S.ccount[p] = (short) (sl+1 - S.cstart[p]);
+                if (sl < nslots && (sl == nslots-1 || W.parent[sl+1] != W.parent[sl])) {
+                    const int p = W.parent[sl];
+                    W.ccount[p] = (short) (sl+1 - W.cstart[p]);
                 }
             }
             __syncwarp();
@@ -325,91 +492,32 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
             for (int s0 = new_start; s0 < nslots; s0 += 32) {
                 const int sl = s0+lane;
                 if (sl < nslots) {
-                    const int p = S.parent[sl];
-                    const int cs = S.cstart[p], ce = cs + S.ccount[p];
-                    const double kv = S.key[sl];
+                    const int p = W.parent[sl];
+                    const int cs = (int) W.cstart[p] - new_start, ce = cs + W.ccount[p];
+                    const int me = sl-new_start;
+                    const double kv = W.key[me];
                     int rank = 0;
                     for (int y = cs; y < ce; y++) {
-                        const double ky = S.key[y];
-                        rank += (ky > kv) || (ky == kv && y < sl);
+                        const double ky = W.key[y];
+                        rank += (ky > kv) || (ky == kv && y < me);
                     }
-                    S.perm[cs+rank] = (short) sl;
-                    S.gend[cs+rank] = (short) ce;
+                    W.perm[cs+rank] = (short) me;
+                    W.gend[cs+rank] = (short) ce;
+                    rk[sl] = (short) rank;
                 }
             }
             __syncwarp();
             ls = new_start; le = nslots; level++;
-            if (lane == 0) lvs[level] = new_start;
+            if (lane == 0) W.lvs[level] = new_start;
         }
         if (failed) continue;
-        if (lane == 0) lvs[level+1] = nslots;
+        if (lane == 0) W.lvs[level+1] = nslots;
         __syncwarp();
         const int nlev = level;
-        hw_slots = max(hw_slots, nslots);
         m_tot += (lane == 0) ? (unsigned long long) (nslots-1) : 0ull;
 
-        // ---- fused bottom-up sweep for both radius sets (gaussvol.cpp:400-487) ----
-        float eL_root = 0.f, eS_root = 0.f;
-        for (int lev = nlev; lev >= 1; lev--) {
-            const int b = lvs[lev], e = lvs[lev+1];
-            const float cf = (lev & 1) ? 1.f : -1.f;
-            const float coefp = cf/(float) lev;
-            for (int s0 = b; s0 < e; s0 += 32) {
-                const int sl = s0+lane;
-                if (sl < e) {
-                    const float g = S.gam[sl];
-                    const float vl = (float) S.key[sl], vs = S.volS[sl];
-                    float EL = coefp*g*vl, fL = coefp*S.sfpL[sl]*g, pLx = 0.f, pLy = 0.f, pLz = 0.f, psL = coefp*vl;
-                    float ES = coefp*g*vs, fS = coefp*S.sfpS[sl]*g, pSx = 0.f, pSy = 0.f, pSz = 0.f, psS = coefp*vs;
-                    const int cs = S.cstart[sl], ce = cs + S.ccount[sl];
-                    for (int c = cs; c < ce; c++) {
-                        EL += S.aEL[c]; fL += S.afL[c]; pLx += S.apLx[c]; pLy += S.apLy[c]; pLz += S.apLz[c]; psL += S.apsL[c];
-                        ES += S.aES[c]; fS += S.afS[c]; pSx += S.apSx[c]; pSy += S.apSy[c]; pSz += S.apSz[c]; psS += S.apsS[c];
-                    }
-                    const int ia = S.nbr[sl];
-                    const int ja = ia == 0 ? r : nb_idx[ia-1];
-                    const float a1iL = (float) S.gLa[sl], a1iS = (float) S.gSa[sl];
-                    const float aiL = (float) A.aL[ja], aiS = (float) A.aS[ja];
-                    const float c2aL = aiL/a1iL, c2bL = (a1iL-aiL)/a1iL;
-                    const float c2aS = aiS/a1iS, c2bS = (a1iS-aiS)/a1iS;
-                    const float dlx = S.dLx[sl], dly = S.dLy[sl], dlz = S.dLz[sl];
-                    const float dsx = S.dSx[sl], dsy = S.dSy[sl], dsz = S.dSz[sl];
-                    // gradient of (E_L - E_S) w.r.t. the node's last atom (gaussvol.cpp:467-474)
-                    atomicAdd(&acc[0*accs+ia], psS);
-                    atomicAdd(&acc[1*accs+ia], psL);
-                    atomicAdd(&acc[2*accs+ia], (-dlx*fL + pLx*c2aL) - (-dsx*fS + pSx*c2aS));
-                    atomicAdd(&acc[3*accs+ia], (-dly*fL + pLy*c2aL) - (-dsy*fS + pSy*c2aS));
-                    atomicAdd(&acc[4*accs+ia], (-dlz*fL + pLz*c2aL) - (-dsz*fS + pSz*c2aS));
-                    // hand the subtree sums to the parent (gaussvol.cpp:476-484)
-                    S.aEL[sl] = EL; S.apsL[sl] = psL;
-                    S.apLx[sl] = dlx*fL + pLx*c2bL; S.apLy[sl] = dly*fL + pLy*c2bL; S.apLz[sl] = dlz*fL + pLz*c2bL;
-                    S.afL[sl] = S.dvvL[sl]*fL;
-                    S.aES[sl] = ES; S.apsS[sl] = psS;
-                    S.apSx[sl] = dsx*fS + pSx*c2bS; S.apSy[sl] = dsy*fS + pSy*c2bS; S.apSz[sl] = dsz*fS + pSz*c2bS;
-                    S.afS[sl] = S.dvvS[sl]*fS;
-                    vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
-                    if (sl == 0) { eL_root = EL; eS_root = ES; }
-                }
-            }
-            __syncwarp();
-        }
-        // E1 uses nu = +gamma/roffset, E2 uses nu = -gamma/roffset (ReferenceAGBNPKernels.cpp:297,364)
-        eL_tot += (double) eL_root*(double) A.inv_roffset;
-        eS_tot -= (double) eS_root*(double) A.inv_roffset;
-
-        // ---- flush per-atom sums: self-volumes and the surface-tension force (force = -gradient) ----
-        for (int i = lane; i <= nn; i += 32) {
-            const int j = i == 0 ? r : nb_idx[i-1];
-            const float s0 = acc[0*accs+i], s1 = acc[1*accs+i];
-            if (s0 != 0.f) atomicAdd(&A.svS[j], (double) s0);
-            if (s1 != 0.f) atomicAdd(&A.svL[j], (double) s1);
-            const float gx = acc[2*accs+i], gy = acc[3*accs+i], gz = acc[4*accs+i];
-            if (gx != 0.f || gy != 0.f || gz != 0.f) {
-                add_force_fixed(&A.force[j], -gx*A.inv_roffset);
-                add_force_fixed(&A.force[(size_t) A.np+j], -gy*A.inv_roffset);
-                add_force_fixed(&A.force[2*(size_t) A.np+j], -gz*A.inv_roffset);
-            }
-        }
+        // ---- bottom-up sweep, both radius sets (gaussvol.cpp:400-487) ----
+        tree_sweep(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS);
 
         // ---- persist what the gamma sweep needs ----
         int off = 0;
@@ -419,23 +527,24 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
             if (lane == 0) atomicOr(A.status, ST_TREE_OVERFLOW);
         } else {
             if (lane == 0) { A.st.root_off[r] = off; A.st.root_cnt[r] = nslots; }
-            if (lane <= nlev+1 && lane >= 1) A.st.root_lvs[r*MAX_LEVELS+lane] = (short) lvs[lane];
-            for (int sl = lane; sl < nslots; sl += 32) {
-                const int lev = S.lvl[sl];
-                const float coefp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
-                const int ia = S.nbr[sl];
-                const int ja = ia == 0 ? r : nb_idx[ia-1];
-                const float a1iS = (float) S.gSa[sl], aiS = (float) A.aS[ja];
-                const int o = off+sl;
-                A.st.cs[o] = coefp*S.sfpS[sl];
-                A.st.dvv[o] = S.dvvS[sl];
-                A.st.dx[o] = S.dSx[sl]; A.st.dy[o] = S.dSy[sl]; A.st.dz[o] = S.dSz[sl];
-                A.st.c2a[o] = aiS/a1iS; A.st.c2b[o] = (a1iS-aiS)/a1iS;
-                A.st.atom[o] = ja;
-                A.st.parent[o] = S.parent[sl]; A.st.cstart[o] = S.cstart[sl]; A.st.ccount[o] = S.ccount[sl];
-                const int ps = S.perm[sl];                                  // node at sorted position sl
-                if (sl > 0) A.st.rank[off+ps] = (short) (sl - S.cstart[S.parent[ps]]);
-                else A.st.rank[off] = 0;
+            if (lane <= nlev+1 && lane >= 1) A.st.root_lvs[r*MAX_LEVELS+lane] = (short) W.lvs[lane];
+            int lev = 1, lend = W.lvs[2];
+            for (int s0 = 0; s0 < nslots; s0 += 32) {
+                const int sl = s0+lane;
+                if (sl < nslots) {
+                    while (sl >= lend) { lev++; lend = W.lvs[lev+1]; }
+                    const float cp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
+                    const float4 q0 = swS[2*sl], q1 = swS[2*sl+1];
+                    const int ia = W.nbr[sl];
+                    const int o = off+sl;
+                    A.st.cs[o] = cp*q0.y;
+                    A.st.dvv[o] = q0.z;
+                    A.st.dx[o] = q1.x; A.st.dy[o] = q1.y; A.st.dz[o] = q1.z;
+                    A.st.c2a[o] = q0.w; A.st.c2b[o] = 1.f-q0.w;
+                    A.st.atom[o] = ia == 0 ? r : W.nbi[ia-1];
+                    A.st.parent[o] = W.parent[sl]; A.st.cstart[o] = W.cstart[sl]; A.st.ccount[o] = W.ccount[sl];
+                    A.st.rank[o] = rk[sl];
+                }
             }
         }
         __syncwarp();
@@ -443,6 +552,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
 
     eL_tot = warp_sum(eL_tot); eS_tot = warp_sum(eS_tot); vsumL = warp_sum(vsumL); vsumS = warp_sum(vsumS);
     if (lane == 0) {
+        // raw sums of coef*gamma*vol; nu = +-gamma/roffset (ReferenceAGBNPKernels.cpp:297,364) is applied in k_finish
         atomicAdd(&A.scalars[SC_EVOL_L], eL_tot);
         atomicAdd(&A.scalars[SC_EVOL_S], eS_tot);
         atomicAdd(&A.scalars[SC_VOL_L], vsumL);
@@ -452,6 +562,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) k_tree(TreeArgs A) {
         atomicAdd(&A.counters[CT_M], m_tot);
         atomicMax(A.hw_nbr, hw_nn);
         atomicMax(A.hw_nodes, hw_slots);
+        atomicMax(A.hw_width, hw_w);
     }
 }
 
@@ -466,7 +577,7 @@ struct GammaArgs {
     TreeStore st;
     const float4* dacc;         // [np] .w = W_i + U_i
     const double* vS;           // atomic volumes, vdW radii
-    unsigned long long* force;
+    float4* gacc;               // [np] out: force x,y,z (w unused)
     unsigned char* scratch;     // per-warp float[5*cap]: gam, f', p'x, p'y, p'z
     size_t scratch_stride;
     int cap;
@@ -514,11 +625,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_gamma(GammaArgs A) {
                 const float c2a = A.st.c2a[o], c2b = A.st.c2b[o];
                 const float gx = -dx*f + px*c2a, gy = -dy*f + py*c2a, gz = -dz*f + pz*c2a;
                 const int ja = A.st.atom[o];
-                if (gx != 0.f || gy != 0.f || gz != 0.f) {
-                    add_force_fixed(&A.force[ja], -gx);
-                    add_force_fixed(&A.force[(size_t) A.np+ja], -gy);
-                    add_force_fixed(&A.force[2*(size_t) A.np+ja], -gz);
-                }
+                if (gx != 0.f || gy != 0.f || gz != 0.f) atomicAdd(&A.gacc[ja], make_float4(-gx, -gy, -gz, 0.f));
                 apx[sl] = dx*f + px*c2b; apy[sl] = dy*f + py*c2b; apz[sl] = dz*f + pz*c2b;
                 af[sl] = A.st.dvv[o]*f;
             }

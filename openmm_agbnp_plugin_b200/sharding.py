@@ -3,10 +3,10 @@ NVSwitch) for the exchanges between the phases the C-ABI exposes (include/agbnp_
 SURVEY.md section 8e).  Nothing here computes energies or forces.
 
     positions  --broadcast from the rank that owns them-->  every rank
-    phase 0    overlap trees of the owned roots           -> all-reduce  partial self-volumes   (2*np doubles)
-    phase 1    Born radii (replicated) + owned GB tiles   -> all-reduce  partial Y              (np floats)
-    phase 2    bru/brw + derivative pass, owned rows      -> all-reduce  W+U                    (np floats)
-    phase 3    tree gamma sweep, owned subtrees           -> all-reduce  forces (3*np int64, exact) + energies (8 doubles)
+    phase 0    overlap trees of the owned roots           -> all-reduce  partial surface-tension gradients + self-volumes (2 x np float4)
+    phase 1    Born radii (replicated) + owned GB tiles   -> all-reduce  partial GB force + Y   (np float4)
+    phase 2    bru/brw + derivative pass, owned units     -> all-reduce  partial force + W+U    (np float4)
+    phase 3    tree gamma sweep, owned subtrees           -> all-reduce  partial forces (np float4) + energies (8 doubles)
     finish     scatter forces into the caller's sink, total energy
 
 The evaluator below is written against a small "shard kernel" protocol (phase / buffer / finish) so that the exchange
@@ -36,8 +36,8 @@ class _DevPtr:
 class CudaShardKernel:
     """The C-ABI shard entry points of one handle, with the exchange buffers exposed as torch tensors."""
 
-    _TYPES = dict(SELFVOL=("<f8", 8, torch.float64), YQ=("<f4", 4, torch.float32), WU=("<f4", 4, torch.float32),
-                  FORCE=("<i8", 8, torch.int64), ENERGY=("<f8", 8, torch.float64))
+    _TYPES = dict(SELFVOL=("<f4", 4, torch.float32), YQ=("<f4", 4, torch.float32), WU=("<f4", 4, torch.float32),
+                  FORCE=("<f4", 4, torch.float32), ENERGY=("<f8", 8, torch.float64))
 
     def __init__(self, force, device, shard_rank, shard_count):
         self.kernel = CalcAGBNPForceKernel(CalcAGBNPForceKernel.Name(), None, device, shard_rank, shard_count)
