@@ -15,6 +15,9 @@
 namespace agbnp_b200_impl {
 
 constexpr int GB_THREADS = 128;
+#ifndef GB_MIN_BLOCKS
+#define GB_MIN_BLOCKS 3
+#endif
 constexpr int GB_CHUNK = 8;             // column tiles per GB work unit
 constexpr int I4_INTERVALS = 15;        // AGBNP_I4LOOKUP_NA - 1
 constexpr float PIFAC = 0.07957747154594767f;   // 1/(4 pi)
@@ -302,12 +305,14 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
 // k_gb: GB pair energy, direct force and Y accumulators over symmetric 32x32 tiles
 // (ReferenceAGBNPKernels.cpp:476-498), in packed FP32x2 arithmetic (fma.rn.f32x2 -> FFMA2 on sm_100a).
 //
-// The pass is bound by FP32 issue: one pair costs 27 FP32 operations + 2 MUFU (ex2, rsqrt).  Scalar code spends an
+// The pass is bound by the FP32 pipe: one pair costs 29 FP32 operations + 2 MUFU (ex2, rsqrt).  Scalar code spends an
 // issue slot per operation; here every arithmetic instruction handles the pairs (i0,j) and (i1,j) of two row atoms at
 // once, which halves the issue slots of the FP32 part and leaves the FMA pipe itself as the limit.
 //   lane grid 4 (li) x 8 (lj): a lane owns 8 row atoms (4 packed pairs) for a whole work unit and 4 column atoms per
-//   tile; column atoms come from `gbj`, written by the Born kernel in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib}
-//   so that three 16-byte loads land directly in aligned register pairs;
+//   tile.  Column tiles are staged in shared memory, double buffered per warp with cp.async (one 48-byte record per
+//   lane and tile, written by k_born_finish in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib} so that 16-byte shared
+//   loads land directly in aligned register pairs -- no MOVs to build the packed operands), so the next tile's
+//   global-memory latency hides behind the current tile's 16 packed pair evaluations per lane;
 //   column-side sums are reduce-scattered over the 4 lanes that share them (12 shuffles per tile) and leave as ONE
 //   vector atomic (red.global.add.v4.f32) per lane and tile; row-side sums are flushed once per work unit.
 // Charges are pre-scaled by sqrt(-2k), so q_i q_j carries the GB prefactor; ib = sqrt(log2(e)/4)/B, so that
@@ -315,8 +320,8 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
 // ---------------------------------------------------------------------------------------------------------------
 struct GBArgs {
     PairCommon c;
-    const float4* gbj;          // [3*np] broadcast-form GB atom records
-    const int2* units;          // (row block, first column block | number of column blocks << 20), heaviest first: triangular cover in chunks of GB_CHUNK column tiles
+    const float4* gbj;          // [3*np] GB atom records in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib}, q scaled by sqrt(-2k)
+    const int2* units;          // (row block, first column block): triangular cover in chunks of GB_CHUNK column tiles
     int nunits;
     int shard_rank, shard_count;
     float4* gbacc;              // out [np]: fx, fy, fz (GB pair force), Y_i*(-2k)
@@ -328,9 +333,28 @@ struct GBArgs {
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
+
+// staged column tile: atom c of the tile lives at slot (c & 3)*8 + (c >> 2), so that the 8 lanes of a quarter warp (which
+// read atoms lj*4 + n for lj = 0..7) hit 8 consecutive 16-byte slots: no bank conflicts
+struct GBStage { float4 r0[TILE], r1[TILE], r2[TILE]; };
+
+__device__ __forceinline__ void gb_prefetch(const GBArgs& A, int cb, int lane, GBStage& st) {
+    const float4* rec = A.gbj + 3*(size_t) (cb*TILE + lane);
+    const int slot = (lane & 3)*8 + (lane >> 2);
+    cp_async16(&st.r0[slot], rec);
+    cp_async16(&st.r1[slot], rec+1);
+    cp_async16(&st.r2[slot], rec+2);
+    cp_async_commit();
+}
+
 // one 32x32 tile: 4 column atoms x 4 packed row pairs per lane
 template <bool CUTOFF, bool DIAG>
-__device__ __forceinline__ void gb_tile(const GBArgs& A, int cb, int li, int lj,
+__device__ __forceinline__ void gb_tile(const GBArgs& A, const GBStage& st, int cb, int li, int lj,
                                         const float2 (&nx)[4], const float2 (&ny)[4], const float2 (&nz)[4],
                                         const float2 (&qi)[4], const float2 (&bi)[4], const float2 (&nib)[4],
                                         float2 (&fi)[4][4], float2& e2, unsigned& npair) {
@@ -341,8 +365,8 @@ __device__ __forceinline__ void gb_tile(const GBArgs& A, int cb, int li, int lj,
 #pragma unroll
     for (int n = 0; n < 4; n++) {
         const int jl = lj*4 + n;                                  // column atom within the tile
-        const float4* rec = A.gbj + 3*(size_t) (cb*TILE + jl);
-        const float4 r0 = __ldg(rec), r1 = __ldg(rec+1), r2 = __ldg(rec+2);
+        // broadcast-form records {x,x,y,y | z,z,q,q | B,B,ib,ib}: three 16-byte loads land directly in aligned register pairs
+        const float4 r0 = st.r0[n*8 + lj], r1 = st.r1[n*8 + lj], r2 = st.r2[n*8 + lj];
         const float2 xj = make_float2(r0.x, r0.y), yj = make_float2(r0.z, r0.w), zj = make_float2(r1.x, r1.y);
         const float2 qj = make_float2(r1.z, r1.w), bj = make_float2(r2.x, r2.y), ibj = make_float2(r2.z, r2.w);
         float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax, aY = ax;
@@ -414,9 +438,11 @@ __device__ __forceinline__ void gb_tile(const GBArgs& A, int cb, int li, int lj,
 }
 
 template <bool CUTOFF>
-__global__ void __launch_bounds__(GB_THREADS, 3) k_gb(GBArgs A) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
+    __shared__ GBStage s_stage[GB_THREADS/32][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int li = lane >> 3, lj = lane & 7;
+    GBStage* stage = s_stage[warp];
     double e_acc = 0.0;
     unsigned long long npair = 0, ntile = 0;
     for (;;) {
@@ -428,6 +454,18 @@ __global__ void __launch_bounds__(GB_THREADS, 3) k_gb(GBArgs A) {
         const int2 un = A.units[u];
         const int ra = un.x;
         const int cend = min(un.y+GB_CHUNK, A.c.nb);
+        const float4 ca = A.c.bbc[ra], ha = A.c.bbh[ra];
+        // column tiles of this unit that take part (cutoff: bounding boxes within range), as a bit mask
+        unsigned tiles = 0;
+        {
+            bool hit = false;
+            if (lane < cend-un.y) hit = !CUTOFF || box_box_dist2(ca, ha, A.c.bbc[un.y+lane], A.c.bbh[un.y+lane]) < A.c.cut2;
+            tiles = __ballot_sync(FULL, hit);
+        }
+        if (!tiles) continue;
+        __syncwarp();                                             // the previous unit is done with the stages
+        int cur = 0;
+        gb_prefetch(A, un.y + __ffs(tiles)-1, lane, stage[0]);
         // row atoms: 4 packed pairs (even atom in .x, odd atom in .y); positions negated, ib negated
         float2 nx[4], ny[4], nz[4], qi[4], bi[4], nib[4], fi[4][4];
 #pragma unroll
@@ -439,18 +477,24 @@ __global__ void __launch_bounds__(GB_THREADS, 3) k_gb(GBArgs A) {
 #pragma unroll
             for (int c = 0; c < 4; c++) fi[m][c] = make_float2(0.f, 0.f);
         }
-        const float4 ca = A.c.bbc[ra], ha = A.c.bbh[ra];
         float2 e2 = make_float2(0.f, 0.f);
         unsigned np32 = 0;
-        for (int cb = un.y; cb < cend; cb++) {
-            if (CUTOFF && box_box_dist2(ca, ha, A.c.bbc[cb], A.c.bbh[cb]) >= A.c.cut2) continue;
+        while (tiles) {
+            const int cb = un.y + __ffs(tiles)-1;
+            tiles &= tiles-1;
+            if (tiles) { gb_prefetch(A, un.y + __ffs(tiles)-1, lane, stage[cur^1]); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp();
             ntile++;
-            if (cb == ra) gb_tile<CUTOFF, true>(A, cb, li, lj, nx, ny, nz, qi, bi, nib, fi, e2, np32);
-            else {
-                gb_tile<CUTOFF, false>(A, cb, li, lj, nx, ny, nz, qi, bi, nib, fi, e2, np32);
+            if (cb == ra) {
+                gb_tile<CUTOFF, true>(A, stage[cur], cb, li, lj, nx, ny, nz, qi, bi, nib, fi, e2, np32);
+                if (!CUTOFF && lane < 16) np32 += 31;             // 496 = 16*31 pairs in a diagonal tile
+            } else {
+                gb_tile<CUTOFF, false>(A, stage[cur], cb, li, lj, nx, ny, nz, qi, bi, nib, fi, e2, np32);
                 if (!CUTOFF) np32 += 32;
             }
-            if (!CUTOFF && cb == ra && lane < 16) np32 += 31;      // 496 = 16*31 pairs in a diagonal tile
+            __syncwarp();                                         // everyone is done reading stage[cur] before it is refilled
+            cur ^= 1;
         }
         e_acc += (double) e2.x + (double) e2.y;
         npair += np32;

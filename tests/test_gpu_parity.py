@@ -156,7 +156,7 @@ def test_execute_accumulates_forces_like_the_reference():
     ctx.forces[:] = 1.0
     e2 = ctx.kernel.execute(ctx, True, True)
     assert np.allclose(ctx.forces - 1.0, f, rtol=0, atol=1e-6 * np.abs(f).max())
-    assert abs(e2 - e) <= 1e-7 * abs(e)
+    assert abs(e2 - e) <= 1e-6 * abs(e)       # float red.global accumulation order varies run to run
 
 
 def test_update_parameters_in_context():
