@@ -97,9 +97,12 @@ struct agbnp_b200 {
     bool tree_work_global = false;          // work arrays too large for shared memory: per-warp global scratch instead
     DevBuf<unsigned char> d_tree_stage, d_tree_work, d_gamma_scratch;
     TreeStore st{};
-    DevBuf<int> d_root_off, d_st_atom;
-    DevBuf<short> d_root_lvs, d_st_parent, d_st_cstart, d_st_ccount, d_st_rank;
-    DevBuf<float> d_st_f;                   // 7 float arrays
+    DevBuf<int> d_root_off;
+    DevBuf<short> d_root_lvs, d_st_rank;
+    DevBuf<float4> d_st_rec;                // 2 float4 per node
+    DevBuf<float> d_inv_vS;
+    int gamma_warps = 4;
+    bool gamma_work_global = false;
     // pinned host staging
     float4* h_posq = nullptr;
     double* h_force = nullptr;
@@ -142,14 +145,11 @@ struct agbnp_b200 {
 namespace {
 
 void alloc_store(agbnp_b200* h, int cap) {
-    h->d_st_f.alloc((size_t) 7*cap);
-    h->d_st_atom.alloc(cap);
-    h->d_st_parent.alloc(cap); h->d_st_cstart.alloc(cap); h->d_st_ccount.alloc(cap); h->d_st_rank.alloc(cap);
+    h->d_st_rec.alloc((size_t) 2*cap);
+    h->d_st_rank.alloc(cap);
     TreeStore& s = h->st;
     s.cap = cap;
-    s.cs = h->d_st_f.p; s.dvv = s.cs+cap; s.dx = s.dvv+cap; s.dy = s.dx+cap; s.dz = s.dy+cap; s.c2a = s.dz+cap; s.c2b = s.c2a+cap;
-    s.atom = h->d_st_atom.p; s.parent = h->d_st_parent.p; s.cstart = h->d_st_cstart.p; s.ccount = h->d_st_ccount.p;
-    s.rank = h->d_st_rank.p;
+    s.rec = h->d_st_rec.p; s.rank = h->d_st_rank.p;
     s.root_off = h->d_root_off.p; s.root_cnt = h->d_root_cnt; s.root_lvs = h->d_root_lvs.p;
 }
 
@@ -168,7 +168,18 @@ void alloc_tree_scratch(agbnp_b200* h) {
     if (h->tree_work_global) h->d_tree_work.alloc(nwarps*per_warp); else h->d_tree_work.release();
     const size_t smem = h->tree_work_global ? 0 : h->tree_warps*per_warp;
     CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
-    h->d_gamma_scratch.alloc((size_t) h->gamma_grid*TREE_WARPS*5*h->tree_cap*sizeof(float));
+    // k_tree_gamma: per-warp gamma_1..n and children sums, in shared memory while they fit
+    {
+        const size_t pw = gamma_work_bytes(h->tree_cap);
+        h->gamma_warps = 4;
+        size_t gctas = std::min<size_t>(8, smem_sm/(h->gamma_warps*pw + 1024));
+        h->gamma_work_global = gctas < 2;
+        if (h->gamma_work_global) gctas = 4;
+        h->gamma_grid = h->num_sm*(int) gctas;
+        if (h->gamma_work_global) h->d_gamma_scratch.alloc((size_t) h->gamma_grid*h->gamma_warps*pw); else h->d_gamma_scratch.release();
+        CK(cudaFuncSetAttribute(k_tree_gamma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) std::max<size_t>(h->gamma_work_global ? 0 : h->gamma_warps*pw, 1024)));
+    }
 }
 
 // (re)compute the internal atom order from caller-order positions and upload every order-dependent static array
@@ -239,6 +250,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     const int np = h->np;
     std::vector<float> charge(np, 0.f), radius(np, 0.15f), alpha(np, 0.f), gamma(np, 0.f);
     std::vector<double> aL(np, 1.0), vL(np, 0.0), aS(np, 1.0), vS(np, 0.0);
+    std::vector<float> inv_vS(np, 0.f);
     std::vector<unsigned char> rcbin(np, 0), ts(np, 0);
     std::vector<signed char> tj(np, -1);
     for (int k = 0; k < np; k++) {
@@ -247,13 +259,14 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         charge[k] = (float) sp.charge[o]; radius[k] = (float) sp.radius[o]; alpha[k] = (float) sp.alpha[o];
         gamma[k] = (float) sp.gamma[o];
         aL[k] = sp.aL[o]; vL[k] = sp.vL[o]; aS[k] = sp.aS[o]; vS[k] = sp.vS[o];
+        inv_vS[k] = sp.vS[o] > 0 ? (float) (1.0/sp.vS[o]) : 0.f;
         rcbin[k] = (unsigned char) sp.rc_bin[o];
         ts[k] = (unsigned char) sp.i4.type_screened[o];
         tj[k] = (signed char) sp.i4.type_screener[o];
     }
     h->d_orig.upload(h->orig, s);
     h->d_charge.upload(charge, s); h->d_radius.upload(radius, s); h->d_alpha.upload(alpha, s); h->d_gamma.upload(gamma, s);
-    h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s);
+    h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s); h->d_inv_vS.upload(inv_vS, s);
     h->d_rcbin.upload(rcbin, s); h->d_ts.upload(ts, s); h->d_tj.upload(tj, s);
     h->d_rc2.upload(sp.rc2, s); h->d_rc2max.upload(sp.rc2max, s);
     // I4 splines in power form around the left knot (see agbnp_pair.cuh): with zl = y2_k h^2/6, zu = y2_{k+1} h^2/6,
@@ -441,11 +454,12 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     }
     if (v1 && (phase_mask & PH_GAMMA)) {
         GammaArgs gm{};
-        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.dacc = h->d_dacc; gm.vS = h->d_vS.p;
-        gm.gacc = h->d_gacc; gm.scratch = h->d_gamma_scratch.p; gm.scratch_stride = (size_t) 5*h->tree_cap*sizeof(float);
+        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.dacc = h->d_dacc; gm.inv_vS = h->d_inv_vS.p;
+        gm.gacc = h->d_gacc; gm.scratch_stride = gamma_work_bytes(h->tree_cap);
+        gm.scratch = h->gamma_work_global ? h->d_gamma_scratch.p : nullptr;
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
         begin(K_GAMMA);
-        k_tree_gamma<<<h->gamma_grid, TREE_THREADS, 0, s>>>(gm);
+        k_tree_gamma<<<h->gamma_grid, 32*h->gamma_warps, h->gamma_work_global ? 0 : h->gamma_warps*gm.scratch_stride, s>>>(gm);
         end(K_GAMMA);
     }
     if (phase_mask & PH_FINISH) {
@@ -647,7 +661,6 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->have_events = true;
         CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
-        h->gamma_grid = h->num_sm*4;
         h->gb_grid = h->num_sm*4;
         h->pq_grid = h->num_sm*4;
         const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*2*sizeof(DerivSmem));
@@ -866,11 +879,16 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             need(sizeof(int)*4*(size_t) m);
             std::vector<int> off(h->nh), cnt(h->nh), atom(cur);
             std::vector<short> par(cur), rank(cur);
+            std::vector<float4> rec((size_t) 2*cur);
             CK(cudaMemcpy(off.data(), h->st.root_off, sizeof(int)*h->nh, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(cnt.data(), h->st.root_cnt, sizeof(int)*h->nh, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(atom.data(), h->st.atom, sizeof(int)*cur, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(par.data(), h->st.parent, sizeof(short)*cur, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(rec.data(), h->st.rec, sizeof(float4)*2*cur, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(rank.data(), h->st.rank, sizeof(short)*cur, cudaMemcpyDeviceToHost));
+            for (int g = 0; g < cur; g++) {
+                int a, pk;
+                std::memcpy(&a, &rec[2*(size_t) g].w, 4); std::memcpy(&pk, &rec[2*(size_t) g+1].w, 4);
+                atom[g] = a; par[g] = (short) (pk & 0xffff);
+            }
             // roots in increasing caller index
             std::vector<int> roots(h->nh);
             for (int r = 0; r < h->nh; r++) roots[r] = r;

@@ -25,23 +25,22 @@
 
 namespace agbnp_b200_impl {
 
-constexpr int TREE_THREADS = 256;   // k_tree_gamma
-constexpr int TREE_WARPS = TREE_THREADS/32;
 constexpr int MAX_LEVELS = 10;      // level index 1..8 used (MAX_ORDER 8)
 #ifndef SCREEN_UNROLL
 #define SCREEN_UNROLL 1             // candidates per lane and trip of the FP32 screen (measured: 1 is fastest on B200)
 #endif
 
-// persisted per-node records (SoA) for the gamma sweep and for the topology dump
+// persisted per-node records for the gamma sweep and for the topology dump: two float4 per node,
+//   rec[2*o]   = (coefp*sfp, dvv1, a_i/a_1i, bits of the sorted index of the node's last atom)        (vdW radii)
+//   rec[2*o+1] = (dv1 x, y, z, bits of: parent slot (low 16 bits, 0xffff for the root) | has-children flag << 16)
 struct TreeStore {
     int cap;                 // node capacity
     int* cursor;             // bump allocator
     int* root_off;           // [nh] first node of the root's subtree (slot 0 = the root atom itself)
     int* root_cnt;           // [nh] nodes in the subtree including slot 0; 0 if not built
     short* root_lvs;         // [nh*MAX_LEVELS] first slot of each level, root_lvs[r*MAX_LEVELS+l], l = 1..nlev+1
-    float *cs, *dvv, *dx, *dy, *dz, *c2a, *c2b;   // coefp*sfp, dvv1, dv1[3], a_i/a_1i, a_1/a_1i   (vdW radii)
-    int* atom;               // sorted index of the node's last atom
-    short *parent, *cstart, *ccount, *rank;       // slots relative to the subtree start; rank among siblings
+    float4* rec;             // [2*cap]
+    short* rank;             // [cap] rank among siblings (topology dump only)
 };
 
 // a node's two Gaussians (enlarged / vdW radii) in the root's frame: positions are relative to the root atom
@@ -537,12 +536,10 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
                     const float4 q0 = swS[2*sl], q1 = swS[2*sl+1];
                     const int ia = W.nbr[sl];
                     const int o = off+sl;
-                    A.st.cs[o] = cp*q0.y;
-                    A.st.dvv[o] = q0.z;
-                    A.st.dx[o] = q1.x; A.st.dy[o] = q1.y; A.st.dz[o] = q1.z;
-                    A.st.c2a[o] = q0.w; A.st.c2b[o] = 1.f-q0.w;
-                    A.st.atom[o] = ia == 0 ? r : W.nbi[ia-1];
-                    A.st.parent[o] = W.parent[sl]; A.st.cstart[o] = W.cstart[sl]; A.st.ccount[o] = W.ccount[sl];
+                    const int ja = ia == 0 ? r : W.nbi[ia-1];
+                    const int pk = ((int) W.parent[sl] & 0xffff) | (W.ccount[sl] > 0 ? 0x10000 : 0);
+                    A.st.rec[2*o] = make_float4(cp*q0.y, q0.z, q0.w, __int_as_float(ja));
+                    A.st.rec[2*o+1] = make_float4(q1.x, q1.y, q1.z, __int_as_float(pk));
                     A.st.rank[o] = rk[sl];
                 }
             }
@@ -576,21 +573,23 @@ struct GammaArgs {
     int nh, np;
     TreeStore st;
     const float4* dacc;         // [np] .w = W_i + U_i
-    const double* vS;           // atomic volumes, vdW radii
+    const float* inv_vS;        // [np] 1/V_i (vdW radii), 0 for hydrogens / padding
     float4* gacc;               // [np] out: force x,y,z (w unused)
-    unsigned char* scratch;     // per-warp float[5*cap]: gam, f', p'x, p'y, p'z
+    unsigned char* scratch;     // per-warp work arrays in global memory (oversize capacity), or nullptr = shared memory
     size_t scratch_stride;
     int cap;
     int* work_counter;
 };
 
-__global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_gamma(GammaArgs A) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* gam = (float*) (A.scratch + (size_t) (blockIdx.x*TREE_WARPS+warp)*A.scratch_stride);
-    float* af = gam+A.cap;
-    float* apx = af+A.cap;
-    float* apy = apx+A.cap;
-    float* apz = apy+A.cap;
+__host__ __device__ inline size_t gamma_work_bytes(int cap) { return (size_t) cap*(sizeof(float) + sizeof(float4)); }
+
+__global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    unsigned char* wk = A.scratch ? A.scratch + (size_t) (blockIdx.x*nwarp+warp)*A.scratch_stride
+                                  : smem_raw + (size_t) warp*gamma_work_bytes(A.cap);
+    float4* hu = (float4*) wk;                      // [cap] children sums (F', P'x, P'y, P'z) per parent slot
+    float* gam = (float*) (hu + A.cap);             // [cap] gamma_1..n per slot
     for (;;) {
         int r = 0;
         if (lane == 0) r = atomicAdd(A.work_counter, 1);
@@ -598,7 +597,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_gamma(GammaArgs A) {
         if (r >= A.nh) break;
         const int cnt = A.st.root_cnt[r];
         if (cnt <= 1) continue;             // an atom without overlaps: dv1 = 0, no force (gaussvol.cpp:472)
-        const int off = A.st.root_off[r];
+        const float4* rec = A.st.rec + 2*(size_t) A.st.root_off[r];
         const short* lvs = A.st.root_lvs + r*MAX_LEVELS;
         int nlev = 1;
         while (nlev+1 < MAX_LEVELS && lvs[nlev+1] < cnt) nlev++;
@@ -606,29 +605,57 @@ __global__ void __launch_bounds__(TREE_THREADS, 4) k_tree_gamma(GammaArgs A) {
         for (int lev = 1; lev <= nlev; lev++) {
             const int b = lvs[lev], e = lev == nlev ? cnt : lvs[lev+1];
             for (int sl = b+lane; sl < e; sl += 32) {
-                const int ja = A.st.atom[off+sl];
-                const float nu = (float) ((double) A.dacc[ja].w/A.vS[ja]);
-                const int p = A.st.parent[off+sl];
-                gam[sl] = (p >= 0 ? gam[p] : 0.f) + nu;
+                const int ja = __float_as_int(rec[2*sl].w);
+                const int p = __float_as_int(rec[2*sl+1].w) & 0xffff;
+                const float nu = A.dacc[ja].w*A.inv_vS[ja];
+                gam[sl] = (p != 0xffff ? gam[p] : 0.f) + nu;
             }
             __syncwarp();
         }
-        // bottom-up energy-gradient sweep
+        // bottom-up energy-gradient sweep; children sums by segmented warp scans (see tree_sweep)
         for (int lev = nlev; lev >= 1; lev--) {
             const int b = lvs[lev], e = lev == nlev ? cnt : lvs[lev+1];
-            for (int sl = b+lane; sl < e; sl += 32) {
-                const int o = off+sl;
-                float f = A.st.cs[o]*gam[sl], px = 0.f, py = 0.f, pz = 0.f;
-                const int cs = A.st.cstart[o], ce = cs + A.st.ccount[o];
-                for (int c = cs; c < ce; c++) { f += af[c]; px += apx[c]; py += apy[c]; pz += apz[c]; }
-                const float dx = A.st.dx[o], dy = A.st.dy[o], dz = A.st.dz[o];
-                const float c2a = A.st.c2a[o], c2b = A.st.c2b[o];
-                const float gx = -dx*f + px*c2a, gy = -dy*f + py*c2a, gz = -dz*f + pz*c2a;
-                const int ja = A.st.atom[o];
-                if (gx != 0.f || gy != 0.f || gz != 0.f) atomicAdd(&A.gacc[ja], make_float4(-gx, -gy, -gz, 0.f));
-                apx[sl] = dx*f + px*c2b; apy[sl] = dy*f + py*c2b; apz[sl] = dz*f + pz*c2b;
-                af[sl] = A.st.dvv[o]*f;
+            int carry_key = -2;
+            float cF = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+            for (int s0 = b; s0 < e; s0 += 32) {
+                const int sl = s0+lane;
+                const bool valid = sl < e;
+                int key = -3-lane;
+                float vF = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+                if (valid) {
+                    const float4 q0 = rec[2*sl], q1 = rec[2*sl+1];
+                    const int pk = __float_as_int(q1.w);
+                    float f = q0.x*gam[sl], px = 0.f, py = 0.f, pz = 0.f;
+                    if (pk & 0x10000) { const float4 h = hu[sl]; f += h.x; px = h.y; py = h.z; pz = h.w; }
+                    const float c2a = q0.z, c2b = 1.f-q0.z;
+                    const float gx = fmaf(px, c2a, -q1.x*f), gy = fmaf(py, c2a, -q1.y*f), gz = fmaf(pz, c2a, -q1.z*f);
+                    if (gx != 0.f || gy != 0.f || gz != 0.f) atomicAdd(&A.gacc[__float_as_int(q0.w)], make_float4(-gx, -gy, -gz, 0.f));
+                    key = pk & 0xffff;
+                    vF = q0.y*f; vx = fmaf(px, c2b, q1.x*f); vy = fmaf(py, c2b, q1.y*f); vz = fmaf(pz, c2b, q1.z*f);
+                }
+                if (lev == 1) break;
+                const int key0 = __shfl_sync(FULL, key, 0);
+                if (carry_key >= 0) {
+                    if (key0 == carry_key) { if (lane == 0) { vF += cF; vx += cx; vy += cy; vz += cz; } }
+                    else if (lane == 0) hu[carry_key] = make_float4(cF, cx, cy, cz);
+                }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int ku = __shfl_up_sync(FULL, key, d);
+                    const bool take = lane >= d && ku == key;
+                    const float tF = __shfl_up_sync(FULL, vF, d), tx = __shfl_up_sync(FULL, vx, d);
+                    const float ty = __shfl_up_sync(FULL, vy, d), tz = __shfl_up_sync(FULL, vz, d);
+                    if (take) { vF += tF; vx += tx; vy += ty; vz += tz; }
+                }
+                const int kn = __shfl_down_sync(FULL, key, 1);
+                const bool tail = valid && (lane == 31 || kn != key);
+                const int last = min(31, e-1-s0);
+                if (tail && lane != last) hu[key] = make_float4(vF, vx, vy, vz);
+                carry_key = __shfl_sync(FULL, key, last);
+                cF = __shfl_sync(FULL, vF, last); cx = __shfl_sync(FULL, vx, last);
+                cy = __shfl_sync(FULL, vy, last); cz = __shfl_sync(FULL, vz, last);
             }
+            if (lev > 1 && carry_key >= 0 && lane == 0) hu[carry_key] = make_float4(cF, cx, cy, cz);
             __syncwarp();
         }
     }
