@@ -419,7 +419,6 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         bf.np = h->np; bf.posq = h->d_posq.p; bf.orig = h->d_orig.p; bf.bsum = h->d_bsum; bf.accS = h->d_accS; bf.vS = h->d_vS.p;
         bf.radius = h->d_radius.p; bf.alpha = h->d_alpha.p;
         bf.vsf = h->d_vsf.p; bf.born = h->d_born.p; bf.bfp = h->d_bfp.p; bf.brw = h->d_brw.p; bf.gbj = h->d_gbj.p;
-        bf.qscale = (float) std::sqrt(-2.0*h->k.dielectric_factor);
         bf.kdiel = (float) h->k.dielectric_factor; bf.hb_radius = (float) h->k.hb_radius;
         bf.scalars = h->d_scalars; bf.own_begin = pc.row_begin*TILE; bf.own_end = pc.row_end*TILE;
         begin(K_BORNFIN);
@@ -430,7 +429,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         GBArgs ga{};
         ga.c = pc; ga.gbj = h->d_gbj.p; ga.units = h->d_units.p; ga.nunits = h->nunits;
         ga.shard_rank = h->cfg.shard_rank; ga.shard_count = h->cfg.shard_count;
-        ga.gbacc = h->d_gbacc; ga.scalars = h->d_scalars; ga.counters = h->d_counters;
+        ga.gbacc = h->d_gbacc; ga.scalars = h->d_scalars; ga.counters = h->d_counters; ga.kdiel = h->k.dielectric_factor;
         ga.work_counter = h->d_ctrl+CW_WORK_GB;
         begin(K_GB);
         if (cutoff) k_gb<true><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
@@ -467,7 +466,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.accL = h->d_accL; fa.accS = h->d_accS; fa.scalars = h->d_scalars;
         fa.inv_roffset = (float) (1.0/h->k.roffset);
         fa.status = h->d_ctrl+CW_STATUS;
-        if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; }
+        if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; fa.gb_scale = -2.0*h->k.dielectric_factor; }
         fa.padded_n = sink ? sink->padded_n : 0;
         if (sink && sink->ptr) {
             if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;
@@ -837,7 +836,7 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             need(sizeof(double)*n);
             std::vector<float4> t(np);
             CK(cudaMemcpy(t.data(), h->d_gbacc, sizeof(float4)*np, cudaMemcpyDeviceToHost));
-            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) od[h->orig[k]] = t[k].w/(-2.0*h->k.dielectric_factor);
+            for (int k = 0; k < np; k++) if (h->orig[k] >= 0) od[h->orig[k]] = t[k].w;
             break;
         }
         case AGBNP_B200_GET_DERIV_WU: {

@@ -259,7 +259,6 @@ struct BornFinishArgs {
     const float *radius, *alpha;
     float *vsf, *born, *bfp, *brw;
     float4* gbj;                // out [3*np]: GB atom records in broadcast form (see k_gb)
-    float qscale;               // sqrt(-2k)
     float kdiel, hb_radius;
     double* scalars;
     int own_begin, own_end;     // sorted-index range whose per-atom energies this shard reports
@@ -291,7 +290,7 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
         } else {
             A.born[a] = 1.f; A.bfp[a] = 0.f; A.vsf[a] = 0.f; A.brw[a] = 0.f;
         }
-        const float qs = pa.w*A.qscale, ib = 0.60056120439322491f/br;   // sqrt(log2(e)/4)/B
+        const float qs = pa.w, ib = 0.60056120439322491f/br;   // sqrt(log2(e)/4)/B
         float4* rec = A.gbj + 3*(size_t) a;
         rec[0] = make_float4(pa.x, pa.x, pa.y, pa.y);
         rec[1] = make_float4(pa.z, pa.z, qs, qs);
@@ -315,16 +314,20 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
 //   global-memory latency hides behind the current tile's 16 packed pair evaluations per lane;
 //   column-side sums are reduce-scattered over the 4 lanes that share them (12 shuffles per tile) and leave as ONE
 //   vector atomic (red.global.add.v4.f32) per lane and tile; row-side sums are flushed once per work unit.
-// Charges are pre-scaled by sqrt(-2k), so q_i q_j carries the GB prefactor; ib = sqrt(log2(e)/4)/B, so that
-// exp(-d2/(4 B_i B_j)) = ex2(-d2 ib_i ib_j).
+// Charges enter UNSCALED: force fields use a few dozen distinct charge values, so the float rounding of a scaled charge
+// q*sqrt(-2k) and of the products is the same for every pair of the same two atom types and does not average out
+// (measured: +6.5e-7 .. +1.1e-6 relative bias of the pair energy on 2clr / RNase H; 5-8 times less unscaled).  The GB
+// prefactor -2k is applied once per atom / per sum downstream (k_gb's energy reduction, k_bw, k_finish).
+// ib = sqrt(log2(e)/4)/B, so that exp(-d2/(4 B_i B_j)) = ex2(-d2 ib_i ib_j).
 // ---------------------------------------------------------------------------------------------------------------
 struct GBArgs {
     PairCommon c;
-    const float4* gbj;          // [3*np] GB atom records in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib}, q scaled by sqrt(-2k)
+    const float4* gbj;          // [3*np] GB atom records in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib}
     const int2* units;          // (row block, first column block): triangular cover in chunks of GB_CHUNK column tiles
     int nunits;
     int shard_rank, shard_count;
-    float4* gbacc;              // out [np]: fx, fy, fz (GB pair force), Y_i*(-2k)
+    float4* gbacc;              // out [np]: (fx, fy, fz)/(-2k) (GB pair force), Y_i
+    double kdiel;               // k = 4.184*332/10*(-1/2)(1 - 1/80)  (ReferenceAGBNPKernels.cpp:465-468)
     double* scalars;
     unsigned long long* counters;
     int* work_counter;
@@ -402,7 +405,7 @@ __device__ __forceinline__ void gb_tile(const GBArgs& A, const GBStage& st, int 
             e2 = __ffma2_rn(qf, corr, e2);
             const float2 g = __fmul2_rn(qf, ff);
             const float2 hh = __fmul2_rn(g, et);
-            const float2 mw = __ffma2_rn(m025, hh, g);            // -2 k q_i q_j (1 - e/4) f^3
+            const float2 mw = __ffma2_rn(m025, hh, g);            // q_i q_j (1 - e/4) f^3
             const float2 yt = __fmul2_rn(hh, __ffma2_rn(p025, d2, bb));
             fi[m][0] = __ffma2_rn(dx, mw, fi[m][0]); fi[m][1] = __ffma2_rn(dy, mw, fi[m][1]); fi[m][2] = __ffma2_rn(dz, mw, fi[m][2]);
             fi[m][3] = __fadd2_rn(fi[m][3], yt);
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
     e_acc = warp_sum(e_acc);
     npair = (unsigned long long) warp_sum((double) npair);
     if (lane == 0) {
-        atomicAdd(&A.scalars[SC_EGB], -e_acc);
+        atomicAdd(&A.scalars[SC_EGB], 2.0*A.kdiel*e_acc);       // E_pair = 2k sum_{i<j} q_i q_j f   (ReferenceAGBNPKernels.cpp:484)
         atomicAdd(&A.counters[CT_PGB], npair);
         atomicAdd(&A.counters[CT_TILES_GB], ntile);
     }
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(256) k_bw(BwArgs A) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= A.np) return;
     const float q = A.posq[i].w;
-    const float y = A.gbacc[i].w/(-2.f*A.kdiel);
+    const float y = A.gbacc[i].w;
     A.bw[i] = A.brw[i] - PIFAC*A.kdiel*(q*q + y*A.born[i])*A.bfp[i];
 }
 
@@ -699,7 +702,8 @@ struct FinishArgs {
     int np, n;
     const int* orig;
     const float4 *accL, *accS;          // surface-tension gradients of sum coef*gamma*vol (enlarged / vdW radii), from k_tree
-    const float4* gbacc;                // GB pair force (xyz)                              -- null for version 0
+    const float4* gbacc;                // GB pair force (xyz) / gb_scale                   -- null for version 0
+    double gb_scale;                    // -2k
     const float4* dacc;                 // Born-radius derivative pair force (xyz)          -- null for version 0
     const float4* gacc;                 // force of the W+U tree sweep (xyz)                -- null for version 0
     float inv_roffset;                  // nu = +gamma/roffset (enlarged radii), -gamma/roffset (vdW radii)
@@ -732,8 +736,8 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
            fz = ((double) s.z - (double) l.z)*(double) A.inv_roffset;
     if (A.gbacc) {
         const float4 g = A.gbacc[k], d = A.dacc[k], t = A.gacc[k];
-        fx += (double) g.x + (double) d.x + (double) t.x; fy += (double) g.y + (double) d.y + (double) t.y;
-        fz += (double) g.z + (double) d.z + (double) t.z;
+        fx += A.gb_scale*(double) g.x + (double) d.x + (double) t.x; fy += A.gb_scale*(double) g.y + (double) d.y + (double) t.y;
+        fz += A.gb_scale*(double) g.z + (double) d.z + (double) t.z;
     }
     if (A.out_f64) { A.out_f64[3*o+0] = fx; A.out_f64[3*o+1] = fy; A.out_f64[3*o+2] = fz; }
     if (A.out_f32) { A.out_f32[3*o+0] += (float) fx; A.out_f32[3*o+1] += (float) fy; A.out_f32[3*o+2] += (float) fz; }

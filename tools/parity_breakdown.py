@@ -35,3 +35,27 @@ for nm in sys.argv[1:] or ["2clr"]:
     print("   self volume: max rel %.2e  mean rel (signed) %+.2e" % (np.abs(sv[hv] / sv_ref[hv] - 1).max(), (sv[hv] / sv_ref[hv] - 1).mean()))
     y, y_ref = ctx.kernel.get("DERIV_Y"), o.get("Y")
     print("   Y: relrms %.2e" % np.sqrt(((y - y_ref) ** 2).sum() / (y_ref ** 2).sum()))
+    # where does the GB difference sit?  self term from the GPU's own Born radii, evaluated in double on the host
+    kd = 4.184 * 332.0 / 10.0 * (-0.5) * (1.0 - 1.0 / 80.0)
+    q = s["charge"]
+    self_gpu_B = kd * float((q * q / b).sum())
+    self_ref_B = kd * float((q * q / b_ref).sum())
+    print("   gb_self from GPU Born radii (double) = %.6f, from oracle radii = %.6f, diff %+.3e" % (self_gpu_B, self_ref_B, self_gpu_B - self_ref_B))
+    print("   => gb_pair gpu (total - self(gpuB)) = %.6f vs ref %.6f diff %+.3e" % (got["gb"] - self_gpu_B, o.scalar("gb_pair"), got["gb"] - self_gpu_B - o.scalar("gb_pair")))
+    # pair energy recomputed in double on the host from the GPU's Born radii (sample of rows to bound the cost)
+    pos64 = pos.astype(np.float64)
+    n = len(q)
+    rows = np.arange(0, n, max(1, n // 400))
+    ep_gpuB = ep_refB = 0.0
+    for i in rows:
+        d2 = ((pos64 - pos64[i]) ** 2).sum(axis=1)
+        m = np.ones(n, dtype=bool); m[i] = False
+        for bb, tag in ((b, "g"), (b_ref, "r")):
+            t = d2[m] + bb[i] * bb[m] * np.exp(-d2[m] / (4.0 * bb[i] * bb[m]))
+            v = kd * float((q[i] * q[m] / np.sqrt(t)).sum())
+            if tag == "g":
+                ep_gpuB += v
+            else:
+                ep_refB += v
+    print("   sampled pair rows (%d): with GPU radii %.6f, with oracle radii %.6f, diff %+.3e (scaled to all rows: %+.3e)" %
+          (len(rows), ep_gpuB, ep_refB, ep_gpuB - ep_refB, (ep_gpuB - ep_refB) * n / len(rows)))
