@@ -271,7 +271,9 @@ def b200_arm(args):
 
     # ---- timed region: K steps, one CUDA-event bracket per step on the launching stream ----
     K = args.steps
-    GB_BIT = 4                                       # index of k_gb in the library's kernel list
+    sums = (C.c_double * 16)(); cnts = (C.c_int * 16)(); names_p = C.c_char_p()
+    L.agbnp_b200_profile_read(handle, sums, cnts, 16, C.byref(names_p))
+    GB_BIT = names_p.value.decode().split("\n").index("k_gb")     # index of k_gb in the library's kernel list
     L.agbnp_b200_profile(handle, 1 << GB_BIT)
     launches0 = L.agbnp_b200_launch_count(handle)
     d_force.zero_(); d_energy.zero_()
@@ -293,7 +295,6 @@ def b200_arm(args):
     coll_per_step = ((ev.collectives - coll0) / K) if sharded else 0
     launches = L.agbnp_b200_launch_count(handle) - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-    sums = (C.c_double * 16)(); cnts = (C.c_int * 16)(); names_p = C.c_char_p()
     L.agbnp_b200_profile_read(handle, sums, cnts, 16, C.byref(names_p))
     L.agbnp_b200_profile(handle, 0)
     gb_ms = sums[GB_BIT] / max(1, cnts[GB_BIT])

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -44,8 +45,8 @@ template <class T> struct DevBuf {
     ~DevBuf() { release(); }
 };
 
-enum KernelId { K_ZERO = 0, K_PREP, K_TREE, K_BORN, K_GB, K_BW, K_DERIV, K_GAMMA, K_FINISH, K_BORNFIN, K_COUNT };
-const char* const kKernelNames = "memset_accum\nk_prep\nk_tree\nk_born\nk_gb\nk_bw\nk_deriv\nk_tree_gamma\nk_finish\nk_born_finish";
+enum KernelId { K_PREP = 0, K_TREE, K_BORN, K_BORNFIN, K_GB, K_DERIV, K_GAMMA, K_FINISH, K_COUNT };
+const char* const kKernelNames = "k_prep\nk_tree\nk_born\nk_born_finish\nk_gb\nk_deriv\nk_tree_gamma\nk_finish";
 
 // control words inside the zeroed slab
 enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_MAX_NBR, CW_MAX_NODES, CW_WORK_BORN, CW_WORK_DERIV, CW_MAX_WIDTH, CW_COUNT = 12 };
@@ -129,6 +130,12 @@ struct agbnp_b200 {
     bool async_fault = false;
     int ahead[16] = {};                     // capacities to grow before the next evaluation (grow_ahead)
     bool ahead_pending = false;
+    // CUDA graphs of the whole kernel sequence, keyed by everything the launches bake in: `launch_gen` (bumped whenever
+    // a buffer, capacity or launch shape changes) and the caller's pointers
+    struct GraphEntry { long long gen; const void* posq; void* sink; int layout, padded_n; double* d_energy; cudaGraphExec_t exec; int kernels; long long last_use; };
+    std::vector<GraphEntry> graphs;
+    long long launch_gen = 0, graph_clock = 0;
+    bool use_graph = true;
 
     ~agbnp_b200() {
         if (h_posq) cudaFreeHost(h_posq);
@@ -137,6 +144,7 @@ struct agbnp_b200 {
         if (h_ctrl) cudaFreeHost(h_ctrl);
         if (have_events) { for (auto& e : ev) cudaEventDestroy(e); for (auto& e : async_ev) cudaEventDestroy(e); }
         for (auto& e : prof_pool) cudaEventDestroy(e);
+        for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
         if (h_async) cudaFreeHost(h_async);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -145,6 +153,7 @@ struct agbnp_b200 {
 namespace {
 
 void alloc_store(agbnp_b200* h, int cap) {
+    h->launch_gen++;
     h->d_st_rec.alloc((size_t) 2*cap);
     h->d_st_rank.alloc(cap);
     TreeStore& s = h->st;
@@ -155,6 +164,7 @@ void alloc_store(agbnp_b200* h, int cap) {
 
 // choose the launch shape of k_tree for the current capacities and (re)allocate its per-warp buffers
 void alloc_tree_scratch(agbnp_b200* h) {
+    h->launch_gen++;
     const size_t per_warp = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
     const size_t smem_sm = 200*1024;                       // of 227 KB; leaves room for L1
     // CTAs of 2 warps (warps never cooperate); 128 registers/thread bound the residency at 16 warps per SM
@@ -246,6 +256,7 @@ void build_pq_units(agbnp_b200* h, std::vector<int2>& out) {
 }
 
 void upload_static(agbnp_b200* h, cudaStream_t s) {
+    h->launch_gen++;
     const SystemParams& sp = h->sp;
     const int np = h->np;
     std::vector<float> charge(np, 0.f), radius(np, 0.15f), alpha(np, 0.f), gamma(np, 0.f);
@@ -371,10 +382,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     };
     PairCommon pc = pair_common(h);
     if (phase_mask & PH_TREE) {
-        begin(K_ZERO);
-        CK(cudaMemsetAsync(h->d_slab.p, 0, h->slab_bytes, s));
-        end(K_ZERO, false);
-        PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p};
+        PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p,
+                    (float4*) h->d_slab.p, (int) (h->slab_bytes/sizeof(float4))};
         begin(K_PREP);
         k_prep<<<(h->nb+7)/8, 256, 0, s>>>(pa);
         end(K_PREP);
@@ -437,14 +446,11 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         end(K_GB);
     }
     if (v1 && (phase_mask & PH_DERIV)) {
-        BwArgs wa{h->np, h->d_posq.p, h->d_gbacc, h->d_born.p, h->d_bfp.p, h->d_brw.p, (float) h->k.dielectric_factor, h->d_bw.p};
-        begin(K_BW);
-        k_bw<<<(h->np+255)/256, 256, 0, s>>>(wa);
-        end(K_BW);
         DerivArgs da{};
         da.c = pc;
         da.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count};
-        da.vsf = h->d_vsf.p; da.bw = h->d_bw.p; da.dacc = h->d_dacc;
+        da.vsf = h->d_vsf.p; da.gbacc = h->d_gbacc; da.born = h->d_born.p; da.bfp = h->d_bfp.p; da.brw = h->d_brw.p;
+        da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
         const size_t sm = 2*tab_bytes + PQ_WARPS*2*sizeof(DerivSmem);
         begin(K_DERIV);
         if (cutoff) k_deriv<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da);
@@ -482,6 +488,46 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
 }
 
 constexpr int PH_ALL = PH_TREE|PH_BORN|PH_GB|PH_DERIV|PH_GAMMA|PH_FINISH;
+
+// one whole evaluation on stream s: a cached CUDA graph of the kernel sequence (one launch instead of eight; the capture
+// happens on the handle's own stream because the caller's may be the legacy default stream, which cannot be captured)
+void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
+    if (!h->use_graph || h->prof_mask) { enqueue(h, d_posq_in, s, PH_ALL, sink); return; }
+    agbnp_b200::GraphEntry* hit = nullptr;
+    for (auto& g : h->graphs)
+        if (g.gen == h->launch_gen && g.posq == d_posq_in && g.sink == sink->ptr && g.layout == sink->layout &&
+            g.padded_n == sink->padded_n && g.d_energy == sink->d_energy) { hit = &g; break; }
+    if (!hit) {
+        // drop graphs of an older configuration, and the least recently used one beyond 16
+        for (size_t i = 0; i < h->graphs.size(); ) {
+            if (h->graphs[i].gen != h->launch_gen) { cudaGraphExecDestroy(h->graphs[i].exec); h->graphs.erase(h->graphs.begin()+i); }
+            else i++;
+        }
+        if (h->graphs.size() >= 16) {
+            size_t lru = 0;
+            for (size_t i = 1; i < h->graphs.size(); i++) if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+            cudaGraphExecDestroy(h->graphs[lru].exec);
+            h->graphs.erase(h->graphs.begin()+lru);
+        }
+        const long long before = h->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+        try { enqueue(h, d_posq_in, h->own_stream, PH_ALL, sink); }
+        catch (...) { cudaStreamEndCapture(h->own_stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        CK(cudaStreamEndCapture(h->own_stream, &graph));
+        agbnp_b200::GraphEntry e{h->launch_gen, d_posq_in, sink->ptr, sink->layout, sink->padded_n, sink->d_energy, nullptr,
+                                 (int) (h->launches-before), 0};
+        h->launches = before;
+        const cudaError_t ce = cudaGraphInstantiate(&e.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) throw CudaFail{std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)};
+        h->graphs.push_back(e);
+        hit = &h->graphs.back();
+    }
+    hit->last_use = ++h->graph_clock;
+    CK(cudaGraphLaunch(hit->exec, s));
+    h->launches += hit->kernels;
+}
 
 // read back status + scalars (synchronises the stream); returns the status bits
 int fetch_status(agbnp_b200* h, cudaStream_t s) {
@@ -547,7 +593,7 @@ void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_pos
 // caller's sink only ever receives forces of a complete evaluation.
 int run_checked(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
     for (int attempt = 0; attempt < 8; attempt++) {
-        enqueue(h, d_posq_in, s, PH_ALL, sink);
+        launch_all(h, d_posq_in, s, sink);
         const int status = fetch_status(h, s);
         if (status == 0) {
             h->evals_since_sort++; h->total_evals++;
@@ -586,7 +632,7 @@ int run_async(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Forc
         const int rc = async_retire(h, k-(agbnp_b200::ASYNC_DEPTH-1));
         if (rc != AGBNP_B200_OK) return rc;
     }
-    enqueue(h, d_posq_in, s, PH_ALL, sink);
+    launch_all(h, d_posq_in, s, sink);
     const int slot = (int) (k % agbnp_b200::ASYNC_DEPTH);
     CK(cudaMemcpyAsync(h->h_async + slot*CW_COUNT, h->d_ctrl, sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(h->async_ev[slot], s));
@@ -656,6 +702,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         h->num_sm = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        { const char* ng = std::getenv("AGBNP_B200_NO_GRAPH"); h->use_graph = !(ng && ng[0] == '1'); }
         for (auto& e2 : h->ev) CK(cudaEventCreate(&e2));
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->have_events = true;
@@ -711,7 +758,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         prepare(h, (const float*) h->h_posq, 4, nullptr, s);
         ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
         for (int attempt = 0; ; attempt++) {
-            enqueue(h, h->d_posq_in.p, s, PH_ALL, &sink);
+            launch_all(h, h->d_posq_in.p, s, &sink);
             if (include_forces && forces)
                 CK(cudaMemcpyAsync(h->h_force, h->d_force_out.p, sizeof(double)*3*h->n, cudaMemcpyDeviceToHost, s));
             const int status = fetch_status(h, s);          // the one synchronisation of the call

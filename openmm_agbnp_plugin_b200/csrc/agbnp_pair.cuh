@@ -32,11 +32,15 @@ struct PrepArgs {
     const float* charge;        // sorted
     float4* posq;               // sorted out
     float4 *bbc, *bbh;
+    float4* slab;               // the per-evaluation accumulators and control words, zeroed here (slab_vec float4)
+    int slab_vec;
 };
 
 __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
     const int lane = threadIdx.x & 31;
-    const int blk = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int gid = blockIdx.x*blockDim.x + threadIdx.x;
+    for (int i = gid; i < A.slab_vec; i += gridDim.x*blockDim.x) A.slab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int blk = gid >> 5;
     if (blk*TILE >= A.np) return;
     const int k = blk*TILE+lane;
     const int o = A.orig[k];
@@ -550,26 +554,6 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_bw: bw_i = brw_i + bru_i, bru_i = -(k/4pi)(q_i^2 + Y_i B_i) fp_i   (ReferenceAGBNPKernels.cpp:537-542)
-// ---------------------------------------------------------------------------------------------------------------
-struct BwArgs {
-    int np;
-    const float4* posq;
-    const float4* gbacc;
-    const float *born, *bfp, *brw;
-    float kdiel;
-    float* bw;
-};
-
-__global__ void __launch_bounds__(256) k_bw(BwArgs A) {
-    const int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= A.np) return;
-    const float q = A.posq[i].w;
-    const float y = A.gbacc[i].w;
-    A.bw[i] = A.brw[i] - PIFAC*A.kdiel*(q*q + y*A.born[i])*A.bfp[i];
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // k_deriv: Born-radius derivative pass (ReferenceAGBNPKernels.cpp:555-586), regrouped by the atom that RECEIVES each
 // contribution.  For atom "me" and partner "o" (d < 2.0, o != me), with D = r_o - r_me:
 //   F_me  += D/d [ heavy(o) bw_me s_o Q'(d; ts_me, tj_o)  +  heavy(me) bw_o s_me Q'(d; ts_o, tj_me) ]
@@ -580,7 +564,11 @@ struct DerivArgs {
     PairCommon c;
     PairUnits u;
     const float* vsf;
-    const float* bw;
+    // bw_i = brw_i + bru_i, bru_i = -(k/4pi)(q_i^2 + Y_i B_i) fp_i   (ReferenceAGBNPKernels.cpp:537-542), formed when an
+    // atom is staged: Y_i is complete once k_gb has finished
+    const float4* gbacc;        // .w = Y_i
+    const float *born, *bfp, *brw;
+    float kdiel;
     float4* dacc;               // out [np]: fx, fy, fz, W+U (zeroed slab; float red.global)
 };
 
@@ -635,7 +623,7 @@ __device__ __forceinline__ void deriv_load(const DerivArgs& A, int blk, int lane
     const float4 p = A.c.posq[j];
     s.x[lane] = p.x; s.y[lane] = p.y; s.z[lane] = p.z;
     s.s[lane] = A.vsf[j];
-    s.bw[lane] = A.bw[j];
+    s.bw[lane] = A.brw[j] - PIFAC*A.kdiel*(p.w*p.w + A.gbacc[j].w*A.born[j])*A.bfp[j];
     s.pk[lane] = (int) A.c.ts[j] | (((int) A.c.tj[j] & 0xff) << 8);
 }
 
