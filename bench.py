@@ -25,6 +25,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 METRIC = "AGBNP1 energy+force evals/s on HIV RT"
 UNIT = "evals/s"
 NS_PER_DAY_PER_EVAL_PER_S = 0.0864          # dt = 1 fs, one evaluation per step (example/hivrt_benchmark.py:20)
@@ -169,7 +170,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ns_per_day": value * NS_PER_DAY_PER_EVAL_PER_S, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def config_dict(s, args, parallelism):
@@ -410,13 +411,17 @@ def b200_arm(args):
         line["cpu_baseline"] = base
         line["parity"] = parity
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print banners there (NCCL's version line) go to stderr instead
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

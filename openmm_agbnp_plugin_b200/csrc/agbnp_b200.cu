@@ -45,8 +45,8 @@ template <class T> struct DevBuf {
     ~DevBuf() { release(); }
 };
 
-enum KernelId { K_PREP = 0, K_TREE, K_BORN, K_BORNFIN, K_GB, K_DERIV, K_GAMMA, K_FINISH, K_COUNT };
-const char* const kKernelNames = "k_prep\nk_tree\nk_born\nk_born_finish\nk_gb\nk_deriv\nk_tree_gamma\nk_finish";
+enum KernelId { K_PREP = 0, K_TREE, K_BORN, K_BORNFIN, K_GB, K_DERIV, K_GAMMA, K_FINISH, K_BLIST, K_COUNT };
+const char* const kKernelNames = "k_prep\nk_tree\nk_born\nk_born_finish\nk_gb\nk_deriv\nk_tree_gamma\nk_finish\nk_blocklist";
 
 // control words inside the zeroed slab
 enum Ctrl { CW_WORK_TREE = 0, CW_WORK_GB, CW_WORK_GAMMA, CW_STATUS, CW_TREE_CURSOR, CW_MAX_NBR, CW_MAX_NODES, CW_WORK_BORN, CW_WORK_DERIV, CW_MAX_WIDTH, CW_COUNT = 12 };
@@ -98,7 +98,10 @@ struct agbnp_b200 {
     bool tree_work_global = false;          // work arrays too large for shared memory: per-warp global scratch instead
     DevBuf<unsigned char> d_tree_stage, d_tree_work, d_gamma_scratch;
     TreeStore st{};
-    DevBuf<int> d_root_off;
+    DevBuf<int> d_root_off, d_root_order, d_bcount;
+    DevBuf<unsigned short> d_blist;
+    std::vector<int> root_order;            // heavy roots, most level-2 neighbors first (host, rebuilt with the atom order)
+    float rc2_global = 0.f;
     DevBuf<short> d_root_lvs, d_st_rank;
     DevBuf<float4> d_st_rec;                // 2 float4 per node
     DevBuf<float> d_inv_vS;
@@ -209,6 +212,38 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
     h->params_dirty = true;
     h->evals_since_sort = 0;
     (void) s;
+    // roots ordered by the number of heavy atoms within 0.5 nm (a proxy for the subtree size, which grows like its 2nd-3rd
+    // power): the work-stealing loop of k_tree then starts the expensive subtrees first (longest-processing-time order)
+    {
+        const int nh = h->nh;
+        const float cell = 0.5f;
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+        for (int k = 0; k < nh; k++) for (int c = 0; c < 3; c++) { const float v = xyz[(size_t) h->orig[k]*stride+c]; lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v); }
+        int dim[3];
+        for (int c = 0; c < 3; c++) dim[c] = nh ? std::min(256, std::max(1, (int) ((hi[c]-lo[c])/cell)+1)) : 1;
+        auto cell_of = [&](int k, int* ic) {
+            for (int c = 0; c < 3; c++) ic[c] = std::min(dim[c]-1, std::max(0, (int) ((xyz[(size_t) h->orig[k]*stride+c]-lo[c])/cell)));
+        };
+        std::vector<std::vector<int>> cells((size_t) dim[0]*dim[1]*dim[2]);
+        for (int k = 0; k < nh; k++) { int ic[3]; cell_of(k, ic); cells[((size_t) ic[0]*dim[1]+ic[1])*dim[2]+ic[2]].push_back(k); }
+        std::vector<int> count(nh, 0);
+        for (int k = 0; k < nh; k++) {
+            int ic[3]; cell_of(k, ic);
+            const float* pk = xyz + (size_t) h->orig[k]*stride;
+            for (int a = std::max(0, ic[0]-1); a <= std::min(dim[0]-1, ic[0]+1); a++)
+            for (int b = std::max(0, ic[1]-1); b <= std::min(dim[1]-1, ic[1]+1); b++)
+            for (int c = std::max(0, ic[2]-1); c <= std::min(dim[2]-1, ic[2]+1); c++)
+                for (int j : cells[((size_t) a*dim[1]+b)*dim[2]+c]) {
+                    if (h->orig[j] <= h->orig[k]) continue;           // level-2 children are later atoms only
+                    const float* pj = xyz + (size_t) h->orig[j]*stride;
+                    const float dx = pj[0]-pk[0], dy = pj[1]-pk[1], dz = pj[2]-pk[2];
+                    if (dx*dx + dy*dy + dz*dz < cell*cell) count[k]++;
+                }
+        }
+        h->root_order.resize(nh);
+        for (int k = 0; k < nh; k++) h->root_order[k] = k;
+        std::stable_sort(h->root_order.begin(), h->root_order.end(), [&](int a, int b) { return count[a] > count[b]; });
+    }
     // block bounding boxes at sort time: used only to ORDER and PACK the work units of the range-limited pair passes
     // (heaviest first, far-apart block pairs packed several per unit); membership is decided on the device every evaluation
     h->box_lo.assign((size_t) 3*h->nb, 3.0e38f); h->box_hi.assign((size_t) 3*h->nb, -3.0e38f);
@@ -280,6 +315,10 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s); h->d_inv_vS.upload(inv_vS, s);
     h->d_rcbin.upload(rcbin, s); h->d_ts.upload(ts, s); h->d_tj.upload(tj, s);
     h->d_rc2.upload(sp.rc2, s); h->d_rc2max.upload(sp.rc2max, s);
+    h->rc2_global = 0.f;
+    for (float v : sp.rc2max) h->rc2_global = std::max(h->rc2_global, v);
+    h->d_root_order.upload(h->root_order, s);
+    h->d_bcount.alloc(std::max(1, h->nhb)); h->d_blist.alloc((size_t) std::max(1, h->nhb)*BLIST_MAX);
     // I4 splines in power form around the left knot (see agbnp_pair.cuh): with zl = y2_k h^2/6, zu = y2_{k+1} h^2/6,
     //   y(fr) = yl + fr [(yu-yl) - 2 zl - zu] + fr^2 [3 zl] + fr^3 [zu - zl]
     {
@@ -387,8 +426,13 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         begin(K_PREP);
         k_prep<<<(h->nb+7)/8, 256, 0, s>>>(pa);
         end(K_PREP);
+        BlockListArgs bl{h->nhb, h->d_bbc.p, h->d_bbh.p, h->rc2_global, h->d_bcount.p, h->d_blist.p};
+        begin(K_BLIST);
+        k_blocklist<<<(h->nhb+7)/8, 256, 0, s>>>(bl);
+        end(K_BLIST);
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
+        ta.root_order = h->d_root_order.p; ta.bcount = h->d_bcount.p; ta.blist = h->d_blist.p;
         ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.rcbin = h->d_rcbin.p;
         ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;
         ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
@@ -459,7 +503,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     }
     if (v1 && (phase_mask & PH_GAMMA)) {
         GammaArgs gm{};
-        gm.nh = h->nh; gm.np = h->np; gm.st = h->st; gm.dacc = h->d_dacc; gm.inv_vS = h->d_inv_vS.p;
+        gm.nh = h->nh; gm.np = h->np; gm.root_order = h->d_root_order.p; gm.st = h->st; gm.dacc = h->d_dacc; gm.inv_vS = h->d_inv_vS.p;
         gm.gacc = h->d_gacc; gm.scratch_stride = gamma_work_bytes(h->tree_cap);
         gm.scratch = h->gamma_work_global ? h->d_gamma_scratch.p : nullptr;
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;

@@ -52,8 +52,44 @@ struct __align__(16) NodeGauss {
 };
 static_assert(sizeof(NodeGauss) == 112, "NodeGauss layout");
 
+constexpr int BLIST_MAX = 64;       // neighbor blocks listed per heavy block (more: the root scans all blocks)
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_blocklist: for every heavy block, the heavy blocks whose bounding box comes within the largest level-2 pair radius
+// of its own box, in ascending order -- the roots of the block then test ~10 boxes instead of all of them
+// ---------------------------------------------------------------------------------------------------------------
+struct BlockListArgs {
+    int nhb;
+    const float4 *bbc, *bbh;
+    float rc2;                  // largest conservative pair radius, squared
+    int* bcount;                // [nhb] number of listed blocks, -1 = more than BLIST_MAX
+    unsigned short* blist;      // [nhb*BLIST_MAX]
+};
+
+__global__ void __launch_bounds__(256) k_blocklist(BlockListArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int rb = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    if (rb >= A.nhb) return;
+    const float4 ca = A.bbc[rb], ha = A.bbh[rb];
+    int n = 0;
+    for (int b0 = 0; b0 < A.nhb; b0 += 32) {
+        const int b = b0+lane;
+        const bool hit = b < A.nhb && box_box_dist2(ca, ha, A.bbc[b], A.bbh[b]) < A.rc2;
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (hit) {
+            const int p = n + __popc(m & lanemask_lt());
+            if (p < BLIST_MAX) A.blist[rb*BLIST_MAX + p] = (unsigned short) b;
+        }
+        n += __popc(m);
+    }
+    if (lane == 0) A.bcount[rb] = n <= BLIST_MAX ? n : -1;
+}
+
 struct TreeArgs {
     int nh, nhb, np;
+    const int* root_order;            // [nh] work index -> root (most expensive first), or nullptr = identity
+    const int* bcount;                // k_blocklist output
+    const unsigned short* blist;
     const float4* posq;
     const int* orig;
     const unsigned char* rcbin;
@@ -262,6 +298,7 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
             if (r >= A.nhb*TILE) break;
             if (r >= A.nh) continue;
         } else if (r >= A.nh) break;
+        if (A.root_order) r = A.root_order[r];
 
         const float4 pr = A.posq[r];
         const int orig_r = A.orig[r];
@@ -270,13 +307,18 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
 
         // ---- level-2 candidate list: heavy atoms later in the caller's order within the conservative pair radius ----
         int nn = 0;
-        for (int b0 = 0; b0 < A.nhb; b0 += 32) {
-            const int b = b0+lane;
+        const int nlist = A.bcount[r >> 5];
+        const int nscan = nlist >= 0 ? nlist : A.nhb;
+        for (int b0 = 0; b0 < nscan; b0 += 32) {
+            int b = b0+lane;
             bool hit = false;
-            if (b < A.nhb) hit = point_box_dist2(pr.x, pr.y, pr.z, A.bbc[b], A.bbh[b]) < rcmax;
+            if (b < nscan) {
+                if (nlist >= 0) b = A.blist[(r >> 5)*BLIST_MAX + b];
+                hit = point_box_dist2(pr.x, pr.y, pr.z, A.bbc[b], A.bbh[b]) < rcmax;
+            }
             unsigned m = __ballot_sync(FULL, hit);
             while (m) {
-                const int bb = b0+__ffs(m)-1;
+                const int bb = __shfl_sync(FULL, b, __ffs(m)-1);
                 m &= m-1;
                 const int j = bb*TILE+lane;
                 const float4 pj = A.posq[j];
@@ -571,6 +613,7 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
 // ---------------------------------------------------------------------------------------------------------------
 struct GammaArgs {
     int nh, np;
+    const int* root_order;      // as in TreeArgs
     TreeStore st;
     const float4* dacc;         // [np] .w = W_i + U_i
     const float* inv_vS;        // [np] 1/V_i (vdW radii), 0 for hydrogens / padding
@@ -595,6 +638,7 @@ __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
         if (lane == 0) r = atomicAdd(A.work_counter, 1);
         r = __shfl_sync(FULL, r, 0);
         if (r >= A.nh) break;
+        if (A.root_order) r = A.root_order[r];
         const int cnt = A.st.root_cnt[r];
         if (cnt <= 1) continue;             // an atom without overlaps: dv1 = 0, no force (gaussvol.cpp:472)
         const float4* rec = A.st.rec + 2*(size_t) A.st.root_off[r];
