@@ -78,7 +78,7 @@ struct agbnp_b200 {
     int nunits = 0, npq_units = 0;
     // per-evaluation arrays
     DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in, d_gbj;
-    DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bw;
+    DevBuf<float> d_vsf, d_born, d_bfp, d_brw, d_bmax;
     DevBuf<unsigned char> d_slab;           // zeroed every evaluation
     double* d_scalars = nullptr;
     unsigned long long* d_counters = nullptr;
@@ -349,7 +349,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     // per-evaluation arrays
     if (h->d_posq.n < (size_t) np) {
         h->d_posq.alloc(np); h->d_bbc.alloc(h->nb); h->d_bbh.alloc(h->nb); h->d_gbj.alloc((size_t) 3*np);
-        h->d_vsf.alloc(np); h->d_born.alloc(np); h->d_bfp.alloc(np); h->d_brw.alloc(np); h->d_bw.alloc(np);
+        h->d_vsf.alloc(np); h->d_born.alloc(np); h->d_bfp.alloc(np); h->d_brw.alloc(np); h->d_bmax.alloc(h->nb);
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o += (bytes+255)/256*256; return r; };
         const size_t o_accL = take(sizeof(float4)*np*2), o_gacc = take(sizeof(float4)*np);
@@ -471,7 +471,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         BornFinishArgs bf{};
         bf.np = h->np; bf.posq = h->d_posq.p; bf.orig = h->d_orig.p; bf.bsum = h->d_bsum; bf.accS = h->d_accS; bf.vS = h->d_vS.p;
         bf.radius = h->d_radius.p; bf.alpha = h->d_alpha.p;
-        bf.vsf = h->d_vsf.p; bf.born = h->d_born.p; bf.bfp = h->d_bfp.p; bf.brw = h->d_brw.p; bf.gbj = h->d_gbj.p;
+        bf.vsf = h->d_vsf.p; bf.born = h->d_born.p; bf.bfp = h->d_bfp.p; bf.brw = h->d_brw.p; bf.gbj = h->d_gbj.p; bf.bmax = h->d_bmax.p;
         bf.kdiel = (float) h->k.dielectric_factor; bf.hb_radius = (float) h->k.hb_radius;
         bf.scalars = h->d_scalars; bf.own_begin = pc.row_begin*TILE; bf.own_end = pc.row_end*TILE;
         begin(K_BORNFIN);
@@ -482,7 +482,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         GBArgs ga{};
         ga.c = pc; ga.gbj = h->d_gbj.p; ga.units = h->d_units.p; ga.nunits = h->nunits;
         ga.shard_rank = h->cfg.shard_rank; ga.shard_count = h->cfg.shard_count;
-        ga.gbacc = h->d_gbacc; ga.scalars = h->d_scalars; ga.counters = h->d_counters; ga.kdiel = h->k.dielectric_factor;
+        ga.gbacc = h->d_gbacc; ga.scalars = h->d_scalars; ga.counters = h->d_counters; ga.kdiel = h->k.dielectric_factor; ga.bmax = h->d_bmax.p;
         ga.work_counter = h->d_ctrl+CW_WORK_GB;
         begin(K_GB);
         if (cutoff) k_gb<true><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
