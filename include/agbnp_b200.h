@@ -143,12 +143,12 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);
 /* ---- multi-GPU plumbing: one process per GPU; the caller runs the phases and does the collectives between
  * them on the exported device buffers (NCCL through torch.distributed in this repo's host layer, sharding.py).
  * Work split: overlap-tree roots are dealt block-cyclically (each shard builds, sweeps and stores only its subtrees);
- * the Born-radius pass is replicated (cheaper than an exchange); GB tile units and derivative-pass units are dealt
- * round-robin.
+ * the work units of the Born-radius, GB and derivative pair passes are dealt round-robin.
  *   phase 0: gather/sort, tree build + rescan + sweeps for the owned roots   -> all-reduce SELFVOL (8*np floats)
- *   phase 1: Born radii (all rows), GB pair pass for the owned tile units     -> all-reduce YQ      (4*np floats)
- *   phase 2: bru/brw (all atoms), derivative pass for the owned units         -> all-reduce WU      (4*np floats)
- *   phase 3: tree gamma sweep over the owned subtrees                         -> all-reduce FORCE (4*np floats)
+ *   phase 1: Born-radius pair sums for the owned units                        -> all-reduce BSUM    (np floats)
+ *   phase 2: Born radii (all atoms), GB pair pass for the owned tile units    -> all-reduce YQ      (4*np floats)
+ *   phase 3: derivative pass for the owned units                              -> all-reduce WU      (4*np floats)
+ *   phase 4: tree gamma sweep over the owned subtrees                         -> all-reduce FORCE   (4*np floats)
  *                                                                                 and ENERGY (8 doubles)
  *   finish : scatter forces to the caller's sink, total energy
  * With shard_count == 1 execute_* run all phases back to back. */
@@ -158,7 +158,8 @@ typedef enum {
     AGBNP_B200_BUF_YQ = 1,       /* float[4*np]   partial GB pair force (xyz) and GB derivative accumulator Y (w) */
     AGBNP_B200_BUF_FORCE = 2,    /* float[4*np]   partial forces of the W+U tree sweep (xyz, -) */
     AGBNP_B200_BUF_ENERGY = 3,   /* double[8]     partial energy scalars */
-    AGBNP_B200_BUF_WU = 4        /* float[4*np]   partial derivative-pass force (xyz) and W+U (w) */
+    AGBNP_B200_BUF_WU = 4,       /* float[4*np]   partial derivative-pass force (xyz) and W+U (w) */
+    AGBNP_B200_BUF_BSUM = 5      /* float[np]     partial Born-radius pair sums */
 } agbnp_b200_buffer;
 int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes);
 /* h_energy == NULL: asynchronous.  Otherwise synchronises and returns ERR_CAPACITY if THIS shard overflowed (the caller

@@ -389,7 +389,7 @@ PairCommon pair_common(agbnp_b200* h) {
     return c;
 }
 
-enum Phase { PH_TREE = 1, PH_GB = 2, PH_DERIV = 4, PH_FINISH = 8, PH_GAMMA = 16, PH_BORN = 32 };
+enum Phase { PH_TREE = 1, PH_GB = 2, PH_DERIV = 4, PH_FINISH = 8, PH_GAMMA = 16, PH_BORN = 32, PH_BORNFIN = 64 };
 
 struct ForceSink { void* ptr; int layout; int padded_n; double* d_energy; };
 
@@ -458,16 +458,17 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     }
     const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
     if (v1 && (phase_mask & PH_BORN)) {
-        // the Born pass is replicated on every shard (cheap; saves an exchange)
         BornArgs ba{};
         ba.c = pc;
-        ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, 1};
+        ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, h->cfg.shard_count};
         ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
         const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
         begin(K_BORN);
         if (cutoff) k_born<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
         else k_born<false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
         end(K_BORN);
+    }
+    if (v1 && (phase_mask & PH_BORNFIN)) {
         BornFinishArgs bf{};
         bf.np = h->np; bf.posq = h->d_posq.p; bf.orig = h->d_orig.p; bf.bsum = h->d_bsum; bf.accS = h->d_accS; bf.vS = h->d_vS.p;
         bf.radius = h->d_radius.p; bf.alpha = h->d_alpha.p;
@@ -531,7 +532,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     CK(cudaGetLastError());
 }
 
-constexpr int PH_ALL = PH_TREE|PH_BORN|PH_GB|PH_DERIV|PH_GAMMA|PH_FINISH;
+constexpr int PH_ALL = PH_TREE|PH_BORN|PH_BORNFIN|PH_GB|PH_DERIV|PH_GAMMA|PH_FINISH;
 
 // one whole evaluation on stream s: a cached CUDA graph of the kernel sequence (one launch instead of eight; the capture
 // happens on the handle's own stream because the caller's may be the legacy default stream, which cannot be captured)
@@ -1025,8 +1026,8 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
 }
 
 int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* stream) {
-    if (!h || phase < 0 || phase > 3) return AGBNP_B200_ERR_ARG;
-    static const int masks[4] = {PH_TREE, PH_BORN|PH_GB, PH_DERIV, PH_GAMMA};
+    if (!h || phase < 0 || phase > 4) return AGBNP_B200_ERR_ARG;
+    static const int masks[5] = {PH_TREE, PH_BORN, PH_BORNFIN|PH_GB, PH_DERIV, PH_GAMMA};
     try {
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = (cudaStream_t) stream;
@@ -1046,6 +1047,7 @@ int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* byte
     case AGBNP_B200_BUF_SELFVOL: *d_ptr = h->d_accL; *bytes = sizeof(float4)*2*h->np; break;
     case AGBNP_B200_BUF_YQ: *d_ptr = h->d_gbacc; *bytes = sizeof(float4)*h->np; break;
     case AGBNP_B200_BUF_WU: *d_ptr = h->d_dacc; *bytes = sizeof(float4)*h->np; break;
+    case AGBNP_B200_BUF_BSUM: *d_ptr = h->d_bsum; *bytes = sizeof(float)*h->np; break;
     case AGBNP_B200_BUF_FORCE: *d_ptr = h->d_gacc; *bytes = sizeof(float4)*h->np; break;
     case AGBNP_B200_BUF_ENERGY: *d_ptr = h->d_scalars; *bytes = sizeof(double)*SC_COUNT; break;
     default: return AGBNP_B200_ERR_ARG;

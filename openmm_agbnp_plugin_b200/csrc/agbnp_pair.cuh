@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
         if (lane == 0) u = atomicAdd(A.u.work_counter, 1);
         u = __shfl_sync(FULL, u, 0);
         if (u >= A.u.nunits) break;
+        if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
         const int2 un = A.u.units[u];
         const int ra = un.x;
         const int cb0 = un.y & 0xfffff, nc = un.y >> 20;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
         if (rsum != 0.f) atomicAdd(&A.bsum[ra*TILE+lane], rsum);
     }
     unsigned long long np64 = (unsigned long long) warp_sum((double) npair);
-    if (lane == 0 && np64 && A.u.shard_rank == 0) atomicAdd(&A.counters[CT_PQ], np64);
+    if (lane == 0 && np64) atomicAdd(&A.counters[CT_PQ], np64);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

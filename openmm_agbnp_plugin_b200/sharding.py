@@ -4,9 +4,10 @@ SURVEY.md section 8e).  Nothing here computes energies or forces.
 
     positions  --broadcast from the rank that owns them-->  every rank
     phase 0    overlap trees of the owned roots           -> all-reduce  partial surface-tension gradients + self-volumes (2 x np float4)
-    phase 1    Born radii (replicated) + owned GB tiles   -> all-reduce  partial GB force + Y   (np float4)
-    phase 2    bru/brw + derivative pass, owned units     -> all-reduce  partial force + W+U    (np float4)
-    phase 3    tree gamma sweep, owned subtrees           -> all-reduce  partial forces (np float4) + energies (8 doubles)
+    phase 1    Born-radius pair sums, owned units         -> all-reduce  partial sums           (np floats)
+    phase 2    Born radii (all atoms) + owned GB tiles    -> all-reduce  partial GB force + Y   (np float4)
+    phase 3    bru/brw + derivative pass, owned units     -> all-reduce  partial force + W+U    (np float4)
+    phase 4    tree gamma sweep, owned subtrees           -> all-reduce  partial forces (np float4) + energies (8 doubles)
     finish     scatter forces into the caller's sink, total energy
 
 The evaluator below is written against a small "shard kernel" protocol (phase / buffer / finish) so that the exchange
@@ -22,7 +23,7 @@ from . import _lib
 from .AGBNPplugin import CalcAGBNPForceKernel, OpenMMException
 
 # exchange after each phase: (buffer name, reduce op)
-EXCHANGES = (("SELFVOL",), ("YQ",), ("WU",), ("FORCE", "ENERGY"))
+EXCHANGES = (("SELFVOL",), ("BSUM",), ("YQ",), ("WU",), ("FORCE", "ENERGY"))
 N_PHASES = len(EXCHANGES)
 
 
@@ -37,7 +38,7 @@ class CudaShardKernel:
     """The C-ABI shard entry points of one handle, with the exchange buffers exposed as torch tensors."""
 
     _TYPES = dict(SELFVOL=("<f4", 4, torch.float32), YQ=("<f4", 4, torch.float32), WU=("<f4", 4, torch.float32),
-                  FORCE=("<f4", 4, torch.float32), ENERGY=("<f8", 8, torch.float64))
+                  FORCE=("<f4", 4, torch.float32), ENERGY=("<f8", 8, torch.float64), BSUM=("<f4", 4, torch.float32))
 
     def __init__(self, force, device, shard_rank, shard_count):
         self.kernel = CalcAGBNPForceKernel(CalcAGBNPForceKernel.Name(), None, device, shard_rank, shard_count)

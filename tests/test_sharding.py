@@ -29,7 +29,7 @@ class MockShardKernel:
     """Same protocol as sharding.CudaShardKernel on CPU tensors: phase p deposits (rank+1)*(p+1) into its exchange
     buffers; finish reports a capacity overflow on `fail_rank` for the first `fail_times` attempts."""
 
-    SIZES = dict(SELFVOL=16, YQ=8, WU=8, FORCE=8, ENERGY=8)
+    SIZES = dict(SELFVOL=16, BSUM=4, YQ=8, WU=8, FORCE=8, ENERGY=8)
 
     def __init__(self, rank, fail_rank=-1, fail_times=0):
         self.rank, self.fail_rank, self.fail_left = rank, fail_rank, fail_times
