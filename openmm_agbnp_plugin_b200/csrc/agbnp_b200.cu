@@ -98,9 +98,11 @@ struct agbnp_b200 {
     bool tree_work_global = false;          // work arrays too large for shared memory: per-warp global scratch instead
     DevBuf<unsigned char> d_tree_stage, d_tree_work, d_gamma_scratch;
     TreeStore st{};
-    DevBuf<int> d_root_off, d_root_order, d_bcount;
+    DevBuf<int> d_root_off, d_bcount;
+    DevBuf<int2> d_items;
+    std::vector<int2> items;                // tree work items (root, part | parts << 8), most expensive first (host)
+    int max_items = 0;
     DevBuf<unsigned short> d_blist;
-    std::vector<int> root_order;            // heavy roots, most level-2 neighbors first (host, rebuilt with the atom order)
     float rc2_global = 0.f;
     DevBuf<short> d_root_lvs, d_st_rank;
     DevBuf<float4> d_st_rec;                // 2 float4 per node
@@ -172,7 +174,7 @@ void alloc_tree_scratch(agbnp_b200* h) {
     const size_t smem_sm = 200*1024;                       // of 227 KB; leaves room for L1
     // CTAs of 2 warps (warps never cooperate); 128 registers/thread bound the residency at 16 warps per SM
     h->tree_warps = 2;
-    size_t ctas = std::min<size_t>(8, smem_sm/(h->tree_warps*per_warp + 1024));
+    size_t ctas = std::min<size_t>(TREE_SMEM_CTAS, smem_sm/(h->tree_warps*per_warp + 1024));
     h->tree_work_global = ctas < 2;                        // fewer than 4 warps per SM: shared memory no longer pays
     if (h->tree_work_global) { h->tree_warps = 8; ctas = 2; }
     h->tree_grid = h->num_sm*(int) ctas;
@@ -180,7 +182,7 @@ void alloc_tree_scratch(agbnp_b200* h) {
     h->d_tree_stage.alloc(nwarps*tree_stage_bytes(h->tree_cap));
     if (h->tree_work_global) h->d_tree_work.alloc(nwarps*per_warp); else h->d_tree_work.release();
     const size_t smem = h->tree_work_global ? 0 : h->tree_warps*per_warp;
-    CK(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
+    CK(cudaFuncSetAttribute(k_tree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
     // k_tree_gamma: per-warp gamma_1..n and children sums, in shared memory while they fit
     {
         const size_t pw = gamma_work_bytes(h->tree_cap);
@@ -240,9 +242,29 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
                     if (dx*dx + dy*dy + dz*dz < cell*cell) count[k]++;
                 }
         }
-        h->root_order.resize(nh);
-        for (int k = 0; k < nh; k++) h->root_order[k] = k;
-        std::stable_sort(h->root_order.begin(), h->root_order.end(), [&](int a, int b) { return count[a] > count[b]; });
+        // work items: a root whose neighbor count predicts a large subtree is split into parts (agbnp_tree.cuh), so that no
+        // single warp carries a subtree that bounds the kernel's duration
+        h->max_items = 2*h->nhp + 64;
+        struct It { int root, part, parts; float cost; };
+        std::vector<It> its;
+        int budget = h->max_items - nh;
+        // cost model: a subtree grows like the cube of its level-2 list.  A root is split when it alone would exceed twice
+        // the balanced load of one resident warp (16 per SM, all shards together): large systems split only their extreme
+        // tail (splitting repeats the level-2 work), small ones split everything that shortens the critical path
+        double total = 0;
+        for (int k = 0; k < nh; k++) total += 1.0 + (double) count[k]*count[k]*count[k];
+        const double per_warp = total/((double) h->num_sm*16*h->cfg.shard_count);
+        for (int k = 0; k < nh; k++) {
+            const double c = 1.0 + (double) count[k]*count[k]*count[k];
+            int parts = (int) std::min(8.0, std::ceil(c/std::max(2.0*per_warp, 64.0)));
+            parts = std::max(1, std::min(parts, count[k]/4));
+            parts = std::min(parts, 1+std::max(0, budget));
+            budget -= parts-1;
+            for (int q = 0; q < parts; q++) its.push_back({k, q, parts, (float) (c/parts)});
+        }
+        std::stable_sort(its.begin(), its.end(), [](const It& a, const It& b) { return a.cost > b.cost; });
+        h->items.clear();
+        for (const It& t : its) h->items.push_back(make_int2(t.root, t.part | (t.parts << 8)));
     }
     // block bounding boxes at sort time: used only to ORDER and PACK the work units of the range-limited pair passes
     // (heaviest first, far-apart block pairs packed several per unit); membership is decided on the device every evaluation
@@ -317,7 +339,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     h->d_rc2.upload(sp.rc2, s); h->d_rc2max.upload(sp.rc2max, s);
     h->rc2_global = 0.f;
     for (float v : sp.rc2max) h->rc2_global = std::max(h->rc2_global, v);
-    h->d_root_order.upload(h->root_order, s);
+    h->d_items.upload(h->items, s);
     h->d_bcount.alloc(std::max(1, h->nhb)); h->d_blist.alloc((size_t) std::max(1, h->nhb)*BLIST_MAX);
     // I4 splines in power form around the left knot (see agbnp_pair.cuh): with zl = y2_k h^2/6, zu = y2_{k+1} h^2/6,
     //   y(fr) = yl + fr [(yu-yl) - 2 zl - zu] + fr^2 [3 zl] + fr^3 [zu - zl]
@@ -355,7 +377,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         const size_t o_accL = take(sizeof(float4)*np*2), o_gacc = take(sizeof(float4)*np);
         const size_t o_yq = take(sizeof(float4)*np), o_scal = take(sizeof(double)*SC_COUNT), o_cnt = take(sizeof(unsigned long long)*CT_COUNT);
         const size_t o_ctrl = take(sizeof(int)*CW_COUNT);
-        const size_t o_dacc = take(sizeof(float4)*np), o_bsum = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->nhp);
+        const size_t o_dacc = take(sizeof(float4)*np), o_bsum = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->max_items);
         h->slab_bytes = o;
         h->d_slab.alloc(o);
         unsigned char* b = h->d_slab.p;
@@ -363,7 +385,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         h->d_gbacc = (float4*) (b+o_yq); h->d_scalars = (double*) (b+o_scal); h->d_counters = (unsigned long long*) (b+o_cnt);
         h->d_ctrl = (int*) (b+o_ctrl);
         h->d_dacc = (float4*) (b+o_dacc); h->d_bsum = (float*) (b+o_bsum); h->d_root_cnt = (int*) (b+o_rcnt);
-        h->d_root_off.alloc(h->nhp); h->d_root_lvs.alloc((size_t) h->nhp*MAX_LEVELS);
+        h->d_root_off.alloc(h->max_items); h->d_root_lvs.alloc((size_t) h->max_items*MAX_LEVELS);
         if (h->st.cap == 0) alloc_store(h, std::max(4096, 160*h->nh + 4096));
         else alloc_store(h, h->st.cap);
     }
@@ -432,7 +454,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         end(K_BLIST);
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
-        ta.root_order = h->d_root_order.p; ta.bcount = h->d_bcount.p; ta.blist = h->d_blist.p;
+        ta.items = h->d_items.p; ta.nitems = (int) h->items.size(); ta.bcount = h->d_bcount.p; ta.blist = h->d_blist.p;
         ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.rcbin = h->d_rcbin.p;
         ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;
         ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
@@ -453,7 +475,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ta.hw_nbr = h->d_ctrl+CW_MAX_NBR; ta.hw_nodes = h->d_ctrl+CW_MAX_NODES; ta.hw_width = h->d_ctrl+CW_MAX_WIDTH;
         const size_t smem = h->tree_work_global ? 0 : h->tree_warps*ta.wk_stride;
         begin(K_TREE);
-        k_tree<<<h->tree_grid, 32*h->tree_warps, smem, s>>>(ta);
+        if (h->tree_work_global) k_tree<false><<<h->tree_grid, 32*h->tree_warps, 0, s>>>(ta);
+        else k_tree<true><<<h->tree_grid, 32*h->tree_warps, smem, s>>>(ta);
         end(K_TREE);
     }
     const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
@@ -504,7 +527,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     }
     if (v1 && (phase_mask & PH_GAMMA)) {
         GammaArgs gm{};
-        gm.nh = h->nh; gm.np = h->np; gm.root_order = h->d_root_order.p; gm.st = h->st; gm.dacc = h->d_dacc; gm.inv_vS = h->d_inv_vS.p;
+        gm.nitems = (int) h->items.size(); gm.np = h->np; gm.st = h->st; gm.dacc = h->d_dacc; gm.inv_vS = h->d_inv_vS.p;
         gm.gacc = h->d_gacc; gm.scratch_stride = gamma_work_bytes(h->tree_cap);
         gm.scratch = h->gamma_work_global ? h->d_gamma_scratch.p : nullptr;
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
@@ -942,11 +965,11 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             need(sizeof(double)*8);
             double sc[SC_COUNT];
             CK(cudaMemcpy(sc, h->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost));
-            int cur = 0;
-            CK(cudaMemcpy(&cur, h->d_ctrl+CW_TREE_CURSOR, sizeof(int), cudaMemcpyDeviceToHost));
+            unsigned long long cm = 0;
+            CK(cudaMemcpy(&cm, h->d_counters+CT_M, sizeof(cm), cudaMemcpyDeviceToHost));
             const double ir = (double) (float) (1.0/h->k.roffset);          // the factor k_finish applies
             od[0] = sc[SC_EVOL_L]*ir; od[1] = -sc[SC_EVOL_S]*ir; od[2] = sc[SC_EGB]; od[3] = sc[SC_EVDW];
-            od[4] = sc[SC_VOL_L]; od[5] = sc[SC_VOL_S]; od[6] = sc[SC_SPARE0]; od[7] = (double) (cur - h->nh);
+            od[4] = sc[SC_VOL_L]; od[5] = sc[SC_VOL_S]; od[6] = sc[SC_SPARE0]; od[7] = (double) cm;
             break;
         }
         case AGBNP_B200_GET_WORK_COUNTERS: {
@@ -958,41 +981,53 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
         }
         case AGBNP_B200_GET_TREE_SIZE: {
             need(sizeof(long long));
-            int cur = 0;
-            CK(cudaMemcpy(&cur, h->d_ctrl+CW_TREE_CURSOR, sizeof(int), cudaMemcpyDeviceToHost));
-            *(long long*) host_out = (long long) cur - h->nh;
+            unsigned long long cm = 0;                  // nodes below the atom level, each counted by the part that owns it
+            CK(cudaMemcpy(&cm, h->d_counters+CT_M, sizeof(cm), cudaMemcpyDeviceToHost));
+            *(long long*) host_out = (long long) cm;
             break;
         }
         case AGBNP_B200_GET_TREE_TOPOLOGY: {
             int cur = 0;
+            unsigned long long cm = 0;
             CK(cudaMemcpy(&cur, h->d_ctrl+CW_TREE_CURSOR, sizeof(int), cudaMemcpyDeviceToHost));
-            const long long m = (long long) cur - h->nh;
-            need(sizeof(int)*4*(size_t) m);
-            std::vector<int> off(h->nh), cnt(h->nh), atom(cur);
-            std::vector<short> par(cur), rank(cur);
+            CK(cudaMemcpy(&cm, h->d_counters+CT_M, sizeof(cm), cudaMemcpyDeviceToHost));
+            need(sizeof(int)*4*(size_t) cm);
+            const int ni = (int) h->items.size();
+            std::vector<int> off(ni), cnt(ni);
+            std::vector<short> lvs((size_t) ni*MAX_LEVELS), rank(cur);
             std::vector<float4> rec((size_t) 2*cur);
-            CK(cudaMemcpy(off.data(), h->st.root_off, sizeof(int)*h->nh, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(cnt.data(), h->st.root_cnt, sizeof(int)*h->nh, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(off.data(), h->st.root_off, sizeof(int)*ni, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(cnt.data(), h->st.root_cnt, sizeof(int)*ni, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(lvs.data(), h->st.root_lvs, sizeof(short)*ni*MAX_LEVELS, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(rec.data(), h->st.rec, sizeof(float4)*2*cur, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(rank.data(), h->st.rank, sizeof(short)*cur, cudaMemcpyDeviceToHost));
-            for (int g = 0; g < cur; g++) {
-                int a, pk;
-                std::memcpy(&a, &rec[2*(size_t) g].w, 4); std::memcpy(&pk, &rec[2*(size_t) g+1].w, 4);
-                atom[g] = a; par[g] = (short) (pk & 0xffff);
-            }
-            // roots in increasing caller index
-            std::vector<int> roots(h->nh);
-            for (int r = 0; r < h->nh; r++) roots[r] = r;
-            std::sort(roots.begin(), roots.end(), [&](int a, int b) { return h->orig[a] < h->orig[b]; });
+            // items grouped by root, roots in increasing caller index; a node is reported by the part that owns it
+            std::vector<int> order(ni);
+            for (int i = 0; i < ni; i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](int a, int b) {
+                const int ra = h->orig[h->items[a].x], rb = h->orig[h->items[b].x];
+                return ra != rb ? ra < rb : (h->items[a].y & 0xff) < (h->items[b].y & 0xff);
+            });
             int* o = (int*) host_out;
             long long w = 0;
-            for (int r : roots) {
-                const long long base = w;
-                for (int sl = 1; sl < cnt[r]; sl++) {
-                    const int g = off[r]+sl;
+            std::vector<long long> dump_of;
+            for (int i : order) {
+                const int r = h->items[i].x, part = h->items[i].y & 0xff, parts = h->items[i].y >> 8;
+                const int n = cnt[i];
+                if (n <= 1) continue;
+                const int l3 = lvs[(size_t) i*MAX_LEVELS+3];         // end of level 2 (level 2 exists: n > 1)
+                dump_of.assign(n, -1);
+                for (int sl = 1; sl < n; sl++) {
+                    const size_t g = (size_t) off[i]+sl;
+                    int a, pk;
+                    std::memcpy(&a, &rec[2*g].w, 4); std::memcpy(&pk, &rec[2*g+1].w, 4);
+                    const int par = pk & 0xffff;
+                    if (sl < l3 && rank[g] % parts != part) continue;   // a level-2 node of another part
+                    if ((unsigned long long) w >= cm) throw CudaFail{"agbnp_b200_get: inconsistent tree store"};
+                    dump_of[sl] = w;
                     o[4*w+0] = h->orig[r];
-                    o[4*w+1] = par[g] == 0 ? -1 : (int) (base + par[g]-1);
-                    o[4*w+2] = h->orig[atom[g]];
+                    o[4*w+1] = par == 0 ? -1 : (int) dump_of[par];
+                    o[4*w+2] = h->orig[a];
                     o[4*w+3] = rank[g];
                     w++;
                 }

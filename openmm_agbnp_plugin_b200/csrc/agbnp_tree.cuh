@@ -33,12 +33,16 @@ constexpr int MAX_LEVELS = 10;      // level index 1..8 used (MAX_ORDER 8)
 // persisted per-node records for the gamma sweep and for the topology dump: two float4 per node,
 //   rec[2*o]   = (coefp*sfp, dvv1, a_i/a_1i, bits of the sorted index of the node's last atom)        (vdW radii)
 //   rec[2*o+1] = (dv1 x, y, z, bits of: parent slot (low 16 bits, 0xffff for the root) | has-children flag << 16)
+// The unit of tree work is an ITEM = (root atom, part k of K): the subtrees below different level-2 nodes of a root never
+// interact, so a large root is split into K parts; part k builds the root and all of its level-2 nodes (cheap, and needed
+// for the sibling lists) but owns and expands only the level-2 nodes at sorted positions t with t mod K == k.  The root's
+// own terms belong to part 0.  Everything a sweep adds is linear in the owned nodes, so the parts just add up.
 struct TreeStore {
     int cap;                 // node capacity
     int* cursor;             // bump allocator
-    int* root_off;           // [nh] first node of the root's subtree (slot 0 = the root atom itself)
-    int* root_cnt;           // [nh] nodes in the subtree including slot 0; 0 if not built
-    short* root_lvs;         // [nh*MAX_LEVELS] first slot of each level, root_lvs[r*MAX_LEVELS+l], l = 1..nlev+1
+    int* root_off;           // [items] first node of the item's subtree (slot 0 = the root atom itself)
+    int* root_cnt;           // [items] nodes stored for the item including slot 0; 0 if not built
+    short* root_lvs;         // [items*MAX_LEVELS] first slot of each level, root_lvs[i*MAX_LEVELS+l], l = 1..nlev+1
     float4* rec;             // [2*cap]
     short* rank;             // [cap] rank among siblings (topology dump only)
 };
@@ -87,7 +91,8 @@ __global__ void __launch_bounds__(256) k_blocklist(BlockListArgs A) {
 
 struct TreeArgs {
     int nh, nhb, np;
-    const int* root_order;            // [nh] work index -> root (most expensive first), or nullptr = identity
+    const int2* items;                // [nitems] (root, part | parts << 8), most expensive first
+    int nitems;
     const int* bcount;                // k_blocklist output
     const unsigned short* blist;
     const float4* posq;
@@ -269,7 +274,13 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
 // k_tree: build + vdW rescan + up-sweeps for every heavy root atom (reference S1-S3:
 // gaussvol.cpp:103-250,254-327,389-519,589-606; ReferenceAGBNPKernels.cpp:290-380)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
+// SMEM_WORK: work arrays in shared memory, CTAs of 2 warps (the normal case; TREE_SMEM_CTAS per SM bounds the registers);
+// otherwise work arrays in global scratch, CTAs of 8 warps
+#ifndef TREE_SMEM_CTAS
+#define TREE_SMEM_CTAS 8
+#endif
+template <bool SMEM_WORK>
+__global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CTAS : 2) k_tree(TreeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int nbrmax = A.nbrmax, cap = A.cap, wcap = A.wcap;
@@ -290,15 +301,18 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
     int hw_nn = 0, hw_slots = 0, hw_w = 0;
 
     for (;;) {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(A.work_counter, 1);
-        r = __shfl_sync(FULL, r, 0);
+        int item = 0;
+        if (lane == 0) item = atomicAdd(A.work_counter, 1);
+        item = __shfl_sync(FULL, item, 0);
         if (A.shard_count > 1) {
-            r = ((r >> 5)*A.shard_count + A.shard_rank)*TILE + (r & 31);
-            if (r >= A.nhb*TILE) break;
-            if (r >= A.nh) continue;
-        } else if (r >= A.nh) break;
-        if (A.root_order) r = A.root_order[r];
+            item = ((item >> 5)*A.shard_count + A.shard_rank)*TILE + (item & 31);
+            if (item >= ((A.nitems+TILE-1) & ~(TILE-1))) break;
+            if (item >= A.nitems) continue;
+        } else if (item >= A.nitems) break;
+        const int2 itm = A.items[item];
+        const int r = itm.x;
+#define part (itm.y & 0xff)
+#define nparts (itm.y >> 8)
 
         const float4 pr = A.posq[r];
         const int orig_r = A.orig[r];
@@ -351,13 +365,14 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
             g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
             g.f0 = make_float4((float) g.aL, (float) g.vL, 0.f, 0.f); g.f1 = make_float4(0.f, gam_r, 0.f, 0.f);
             G[0] = g;
-            swL[0] = make_float4((float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
-            swS[0] = make_float4((float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            const float own = part == 0 ? 1.f : 0.f;              // the root's own terms belong to part 0
+            swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            swS[0] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
             rk[0] = 0;
             W.parent[0] = -1; W.nbr[0] = 0; W.cstart[0] = 1; W.ccount[0] = 0; W.perm[0] = 0; W.gend[0] = 1;
             W.lvs[1] = 0;
-            eL_tot += (double) (gam_r*(float) g.vL); eS_tot += (double) (gam_r*(float) g.vS);
-            vsumL += (double) (float) g.vL; vsumS += (double) (float) g.vS;
+            eL_tot += (double) (own*gam_r*(float) g.vL); eS_tot += (double) (own*gam_r*(float) g.vS);
+            vsumL += (double) (own*(float) g.vL); vsumS += (double) (own*(float) g.vS);
         }
         __syncwarp();
 
@@ -375,7 +390,8 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
                 for (int t0 = 0; t0 < width; t0 += 32) {
                     const int t = t0+lane;
                     int c = 0;
-                    if (t < width) c = (int) W.gend[t] - t - 1;
+                    // level 2 -> 3: only the level-2 nodes this part owns are expanded
+                    if (t < width && (level > 2 || t % nparts == part)) c = (int) W.gend[t] - t - 1;
                     const int inc = warp_incl_scan(c);
                     if (t < width) W.pref[t] = carry + inc - c;
                     carry += __shfl_sync(FULL, inc, 31);
@@ -384,7 +400,7 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
                 T = carry;
                 __syncwarp();
             }
-            if (level == 1) c2_tot += (lane == 0) ? (unsigned long long) T : 0ull;
+            if (level == 1) c2_tot += (lane == 0 && part == 0) ? (unsigned long long) T : 0ull;
             else c3_tot += (lane == 0) ? (unsigned long long) T : 0ull;
 
             const int new_start = nslots;
@@ -501,9 +517,11 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
                         W.parent[slot] = (short) p; W.nbr[slot] = (short) (kn+1);
                         W.cstart[slot] = 0; W.ccount[slot] = 0;
                         // energies and volumes need no tree accumulation (gaussvol.cpp:425-433 summed over the subtree)
-                        const float cg = coefp*gam;
-                        eL_tot += (double) (cg*vl); eS_tot += (double) (cg*vs);
-                        vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
+                        if (level > 1 || nparts == 1) {                   // level-2 nodes of a split root: after the sort, when ownership is known
+                            const float cg = coefp*gam;
+                            eL_tot += (double) (cg*vl); eS_tot += (double) (cg*vs);
+                            vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
+                        }
                     }
                 }
                 nslots += __popc(am);
@@ -545,6 +563,19 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
                     W.perm[cs+rank] = (short) me;
                     W.gend[cs+rank] = (short) ce;
                     rk[sl] = (short) rank;
+                    if (level == 1 && nparts > 1) {
+                        // a level-2 node of a split root: its rank is its sorted position.  Owned: account its energy terms now;
+                        // not owned: it stays as a sibling for the owned ones but contributes nothing (vol = sfp = 0)
+                        if (rank % nparts == part) {
+                            const float vl = swL[2*sl].x, vs = swS[2*sl].x, cg = coefp*swL[2*sl+1].w;
+                            eL_tot += (double) (cg*vl); eS_tot += (double) (cg*vs);
+                            vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
+                            m_tot++;
+                        } else {
+                            float4 q = swL[2*sl]; q.x = 0.f; q.y = 0.f; swL[2*sl] = q;
+                            q = swS[2*sl]; q.x = 0.f; q.y = 0.f; swS[2*sl] = q;
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -555,7 +586,8 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
         if (lane == 0) W.lvs[level+1] = nslots;
         __syncwarp();
         const int nlev = level;
-        m_tot += (lane == 0) ? (unsigned long long) (nslots-1) : 0ull;
+        if (nparts == 1) m_tot += (lane == 0) ? (unsigned long long) (nslots-1) : 0ull;
+        else m_tot += (lane == 0 && nlev >= 2) ? (unsigned long long) (nslots-W.lvs[3]) : 0ull;   // + the owned level-2 nodes counted above
 
         // ---- bottom-up sweep, both radius sets (gaussvol.cpp:400-487) ----
         tree_sweep(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS);
@@ -567,8 +599,8 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
         if (off+nslots > A.st.cap) {
             if (lane == 0) atomicOr(A.status, ST_TREE_OVERFLOW);
         } else {
-            if (lane == 0) { A.st.root_off[r] = off; A.st.root_cnt[r] = nslots; }
-            if (lane <= nlev+1 && lane >= 1) A.st.root_lvs[r*MAX_LEVELS+lane] = (short) W.lvs[lane];
+            if (lane == 0) { A.st.root_off[item] = off; A.st.root_cnt[item] = nslots; }
+            if (lane <= nlev+1 && lane >= 1) A.st.root_lvs[item*MAX_LEVELS+lane] = (short) W.lvs[lane];
             int lev = 1, lend = W.lvs[2];
             for (int s0 = 0; s0 < nslots; s0 += 32) {
                 const int sl = s0+lane;
@@ -589,7 +621,10 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
         __syncwarp();
     }
 
+#undef part
+#undef nparts
     eL_tot = warp_sum(eL_tot); eS_tot = warp_sum(eS_tot); vsumL = warp_sum(vsumL); vsumS = warp_sum(vsumS);
+    m_tot = (unsigned long long) warp_sum((double) m_tot);
     if (lane == 0) {
         // raw sums of coef*gamma*vol; nu = +-gamma/roffset (ReferenceAGBNPKernels.cpp:297,364) is applied in k_finish
         atomicAdd(&A.scalars[SC_EVOL_L], eL_tot);
@@ -612,8 +647,7 @@ __global__ void __launch_bounds__(256) k_tree(TreeArgs A) {
 // Multi-GPU: each shard stores and sweeps only the subtrees of the roots it owns; the partial forces are all-reduced.
 // ---------------------------------------------------------------------------------------------------------------
 struct GammaArgs {
-    int nh, np;
-    const int* root_order;      // as in TreeArgs
+    int nitems, np;
     TreeStore st;
     const float4* dacc;         // [np] .w = W_i + U_i
     const float* inv_vS;        // [np] 1/V_i (vdW radii), 0 for hydrogens / padding
@@ -637,8 +671,7 @@ __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
         int r = 0;
         if (lane == 0) r = atomicAdd(A.work_counter, 1);
         r = __shfl_sync(FULL, r, 0);
-        if (r >= A.nh) break;
-        if (A.root_order) r = A.root_order[r];
+        if (r >= A.nitems) break;                   // r: item index (stored subtrees are per item; not-owned nodes carry zeros)
         const int cnt = A.st.root_cnt[r];
         if (cnt <= 1) continue;             // an atom without overlaps: dv1 = 0, no force (gaussvol.cpp:472)
         const float4* rec = A.st.rec + 2*(size_t) A.st.root_off[r];
