@@ -43,9 +43,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_WORKLOAD = {"name": "hivrt", "method": 0, "cutoff": 1.0}     # BASELINE.json metric: HIV-RT, NoCutoff
+
+
 def workload():
     from openmm_agbnp_plugin_b200 import systems
-    s = systems.hivrt()
+    if _WORKLOAD["name"] == "hivrt":
+        s = systems.hivrt()
+    else:
+        s = systems.load(_WORKLOAD["name"])          # secondary configs (BASELINE configs 2-3): committed fixtures
+        s["name"] = _WORKLOAD["name"]
     s["pos"] = systems.float_rounded(s["pos"])
     return s
 
@@ -174,8 +181,9 @@ def reference_arm(args):
 
 
 def config_dict(s, args, parallelism):
-    return {"workload": "%s AGBNP1 (setVersion 1) energy+force, NoCutoff, N=%d atoms" % (s.get("name", "hivrt"), len(s["pos"])),
-            "n_atoms": int(len(s["pos"])), "nonbonded_method": "NoCutoff", "version": 1,
+    meth = "NoCutoff" if _WORKLOAD["method"] == 0 else "CutoffNonPeriodic %.2f nm" % _WORKLOAD["cutoff"]
+    return {"workload": "%s AGBNP1 (setVersion 1) energy+force, %s, N=%d atoms" % (s.get("name", "hivrt"), meth, len(s["pos"])),
+            "n_atoms": int(len(s["pos"])), "nonbonded_method": meth, "version": 1,
             "inputs": "positions jittered +-0.001 nm per step (seeded, %d sets)" % JITTER_SETS,
             "l2": "256 MiB memset between timed evaluations (outside the per-step CUDA-event brackets)",
             "parallelism": parallelism}
@@ -218,7 +226,7 @@ def b200_arm(args):
     s = workload()
     n = len(s["pos"])
     sharded = world > 1 and args.mode == "shard"
-    force = systems.make_force(s, 1, plug.AGBNPForce.NoCutoff, 1.0)
+    force = systems.make_force(s, 1, _WORKLOAD["method"], _WORKLOAD["cutoff"])
 
     # device-resident inputs: JITTER_SETS jittered coordinate sets as float4
     posq_sets = []
@@ -332,6 +340,11 @@ def b200_arm(args):
                 "launch_ms": gb_ms, "algorithmic_flop_per_launch": FLOP_GB * gb_pairs_this_rank,
                 "mufu_achieved_gops": MUFU_GB * gb_pairs_this_rank / (gb_ms * 1e-3) / 1e9, "mufu_peak_gops": peak_mufu / 1e9}
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    try:
+        # dram__bytes_read.sum + dram__bytes_write.sum of one k_gb launch, from the committed `ncu --set full` capture
+        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_gb"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     path_roofline = {"flop": flop, "mufu": mufu, "t_roof_ms": t_roof_ms, "t_eval_ms": ms_per_step, "frac": t_roof_ms / ms_per_step,
                      "peak_fp32_tflops": peak_fp32 / 1e12, "peak_ffma2_tflops": 2 * pk[1] / 1e12, "peak_mufu_gops": peak_mufu / 1e9,
                      "counters": {"P_gb": p_gb, "P_q": p_q, "C2": c2, "C3plus": c3, "M": m_nodes}}
@@ -429,7 +442,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="shard", choices=["shard", "replica"], help="N>1: shard one evaluation (default) or run replicas")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="hivrt", help="hivrt (the metric's workload, default) | 2clr | 1dwc | rnaseh | 1li2 | trpcage")
+    ap.add_argument("--cutoff", type=float, default=0.0, help="> 0: CutoffNonPeriodic with this cutoff (nm); the Reference platform, and "
+                    "therefore the CPU baseline / parity check, has no cutoff: they are skipped")
     args = ap.parse_args()
+    _WORKLOAD["name"] = args.workload
+    if args.cutoff > 0:
+        _WORKLOAD["method"], _WORKLOAD["cutoff"] = 1, args.cutoff
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         reference_arm(args)
     else:

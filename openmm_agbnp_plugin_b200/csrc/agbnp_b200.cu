@@ -519,7 +519,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         da.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count};
         da.vsf = h->d_vsf.p; da.gbacc = h->d_gbacc; da.born = h->d_born.p; da.bfp = h->d_bfp.p; da.brw = h->d_brw.p;
         da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
-        const size_t sm = 2*tab_bytes + PQ_WARPS*2*sizeof(DerivSmem);
+        const size_t sm = 2*tab_bytes + PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float));
         begin(K_DERIV);
         if (cutoff) k_deriv<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da);
         else k_deriv<false><<<h->pq_grid, PQ_THREADS, sm, s>>>(da);
@@ -777,7 +777,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
         h->gb_grid = h->num_sm*4;
         h->pq_grid = h->num_sm*4;
-        const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*2*sizeof(DerivSmem));
+        const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float)));
         CK(cudaFuncSetAttribute(k_born<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_deriv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));

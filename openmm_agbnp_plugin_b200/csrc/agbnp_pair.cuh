@@ -599,32 +599,42 @@ struct DerivSmem { float x[TILE], y[TILE], z[TILE], s[TILE], bw[TILE]; int pk[TI
 
 struct DerivMe { float px, py, pz, s, bw; int base, tj; };
 
-template <bool CUTOFF>
-__device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tabd, const DerivSmem& o, int jj, bool valid,
-                                           const DerivMe& me, int ntj, float inv_h, float& fx, float& fy, float& fz, float& wu) {
+// The force weight of a pair, w = [bw_me s_o Q'(me,o) + bw_o s_me Q'(o,me)]/d, is symmetric in (me, o).  On an
+// off-diagonal tile the row role (MODE 1) therefore stores it in a 32x33 shared-memory matrix and the column role
+// (MODE 2) only looks it up: one spline value instead of two derivatives and a value.  MODE 0: plain (diagonal tile).
+constexpr int WMAT_STRIDE = 33;         // row stride: lanes writing the same column hit different banks
+
+template <bool CUTOFF, int MODE>
+__device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, int jj,
+                                           bool valid, const DerivMe& me, int ntj, float inv_h, float& fx, float& fy, float& fz, float& wu) {
     const float dx = o.x[jj]-me.px, dy = o.y[jj]-me.py, dz = o.z[jj]-me.pz;
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
     const int pk = o.pk[jj];
     const int ts_o = pk & 0xff;
-    const int tj_o = (int) (signed char) ((pk >> 8) & 0xff);
     const float inv_d = rsqrtf(fmaxf(d2, 1e-20f));
     const float d = d2*inv_d;
     const float t = d*inv_h;
     const int k = min((int) t, I4_INTERVALS-1);
     const float fr = t-(float) k;
-    // o descreens me (needs heavy(o)); me descreens o (needs heavy(me))
-    const float q1 = spline_deriv(tabd[me.base + max(tj_o, 0)*I4_INTERVALS + k], fr);
     const int ix = (ts_o*ntj + max(me.tj, 0))*I4_INTERVALS + k;
-    const float q2 = spline_deriv(tabd[ix], fr), v2 = spline_value(tabv[ix], fr);
-    const float bwo = (valid && me.tj >= 0) ? o.bw[jj] : 0.f;
-    float w = (valid && tj_o >= 0) ? me.bw*o.s[jj]*q1 : 0.f;
-    w = fmaf(bwo*me.s, q2, w)*inv_d;
+    const float v2 = spline_value(tabv[ix], fr);
+    const float bwo = (valid && me.tj >= 0) ? o.bw[jj] : 0.f;   // me descreens o (needs heavy(me))
+    float w;
+    if (MODE == 2) w = valid ? wmat[jj*WMAT_STRIDE + lane] : 0.f;
+    else {
+        const int tj_o = (int) (signed char) ((pk >> 8) & 0xff);
+        const float q1 = spline_deriv(tabd[me.base + max(tj_o, 0)*I4_INTERVALS + k], fr);
+        const float q2 = spline_deriv(tabd[ix], fr);
+        w = (valid && tj_o >= 0) ? me.bw*o.s[jj]*q1 : 0.f;      // o descreens me (needs heavy(o))
+        w = fmaf(bwo*me.s, q2, w)*inv_d;
+        if (MODE == 1 && valid) wmat[lane*WMAT_STRIDE + jj] = w;
+    }
     wu = fmaf(bwo, v2, wu);
     fx = fmaf(dx, w, fx); fy = fmaf(dy, w, fy); fz = fmaf(dz, w, fz);
 }
 
-template <bool CUTOFF>
-__device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* tabd, const DerivSmem& o, unsigned mask,
+template <bool CUTOFF, int MODE>
+__device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, unsigned mask,
                                              float px, float py, float pz, float s_me, float bw_me, int ts_me, int tj_me,
                                              int ntj, float inv_h) {
     float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
@@ -635,8 +645,8 @@ __device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* t
         const bool two = mask != 0;
         const int j1 = two ? __ffs(mask)-1 : j0;
         mask &= mask-1;
-        deriv_term<CUTOFF>(tabv, tabd, o, j0, true, me, ntj, inv_h, fx0, fy0, fz0, wu0);
-        deriv_term<CUTOFF>(tabv, tabd, o, j1, two, me, ntj, inv_h, fx1, fy1, fz1, wu1);
+        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j0, true, me, ntj, inv_h, fx0, fy0, fz0, wu0);
+        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j1, two, me, ntj, inv_h, fx1, fy1, fz1, wu1);
     }
     return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
 }
@@ -657,6 +667,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
     float4* s_tabv = (float4*) smem_raw;
     float4* s_tabd = s_tabv + ntab;
     DerivSmem* sm = (DerivSmem*) (s_tabd + ntab);                       // [PQ_WARPS][2]
+    float* wmat = (float*) (sm + 2*PQ_WARPS) + (threadIdx.x >> 5)*WMAT_STRIDE*TILE;   // [PQ_WARPS][32*33] pair force weights
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < ntab; i += blockDim.x) { s_tabv[i] = A.c.i4v[i]; s_tabd[i] = A.c.i4d[i]; }
     __syncthreads();
@@ -693,12 +704,16 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
             __syncwarp();
             unsigned rowmask, colmask;
             pq_masks<CUTOFF>(Cc.x, Cc.y, Cc.z, px, py, pz, lim2, diag, lane, rowmask, colmask);
-            const float4 r = deriv_role<CUTOFF>(tabv, tabd, Cc, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h);
-            racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
-            if (!diag) {
+            if (diag) {
+                const float4 r = deriv_role<CUTOFF, 0>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h);
+                racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
+            } else {
+                const float4 r = deriv_role<CUTOFF, 1>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h);
+                racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
+                __syncwarp();                                   // the weights are read by other lanes
                 const int pk = Cc.pk[lane];
-                const float4 c = deriv_role<CUTOFF>(tabv, tabd, R, colmask, Cc.x[lane], Cc.y[lane], Cc.z[lane], Cc.s[lane], Cc.bw[lane],
-                                                    pk & 0xff, (int) (signed char) ((pk >> 8) & 0xff), A.c.ntj, A.c.inv_h);
+                const float4 c = deriv_role<CUTOFF, 2>(tabv, tabd, R, wmat, lane, colmask, Cc.x[lane], Cc.y[lane], Cc.z[lane], Cc.s[lane], Cc.bw[lane],
+                                                       pk & 0xff, (int) (signed char) ((pk >> 8) & 0xff), A.c.ntj, A.c.inv_h);
                 if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], c);
             }
         }
