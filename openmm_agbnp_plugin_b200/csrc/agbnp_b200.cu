@@ -75,6 +75,9 @@ struct agbnp_b200 {
     DevBuf<float> d_rc2, d_rc2max;
     DevBuf<float4> d_i4v, d_i4d;
     DevBuf<int2> d_units, d_pq_units;
+    DevBuf<int> d_pq_toff;
+    DevBuf<unsigned> d_pq_hits;
+    DevBuf<uint2> d_pq_masks;
     int nunits = 0, npq_units = 0;
     // per-evaluation arrays
     DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in, d_gbj;
@@ -367,6 +370,14 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     build_pq_units(h, pq);
     h->npq_units = (int) pq.size();
     h->d_pq_units.upload(pq, s);
+    {
+        std::vector<int> toff(pq.size());
+        int t = 0;
+        for (size_t i = 0; i < pq.size(); i++) { toff[i] = t; t += pq[i].y >> 20; }
+        h->d_pq_toff.upload(toff, s);
+        h->d_pq_hits.alloc(std::max<size_t>(1, pq.size()));
+        h->d_pq_masks.alloc((size_t) std::max(1, t)*TILE);
+    }
     CK(cudaStreamSynchronize(s));      // the host vectors above go out of scope
     // per-evaluation arrays
     if (h->d_posq.n < (size_t) np) {
@@ -483,7 +494,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     if (v1 && (phase_mask & PH_BORN)) {
         BornArgs ba{};
         ba.c = pc;
-        ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, h->cfg.shard_count};
+        ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_pq_toff.p, h->d_pq_hits.p, h->d_pq_masks.p,
+                         h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, h->cfg.shard_count};
         ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
         const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
         begin(K_BORN);
@@ -516,7 +528,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     if (v1 && (phase_mask & PH_DERIV)) {
         DerivArgs da{};
         da.c = pc;
-        da.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count};
+        da.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_pq_toff.p, h->d_pq_hits.p, h->d_pq_masks.p,
+                         h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count};
         da.vsf = h->d_vsf.p; da.gbacc = h->d_gbacc; da.born = h->d_born.p; da.bfp = h->d_bfp.p; da.brw = h->d_brw.p;
         da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
         const size_t sm = 2*tab_bytes + PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float));

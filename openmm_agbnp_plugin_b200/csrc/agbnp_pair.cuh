@@ -114,6 +114,11 @@ constexpr int PQ_WARPS = PQ_THREADS/32;
 struct PairUnits {
     const int2* units;          // (row block, first column block | number of column blocks << 20), heaviest first
     int nunits;
+    // pair-test cache: k_born and k_deriv visit the same units and tiles, so k_born stores what it found and k_deriv
+    // neither re-tests the bounding boxes nor the 32x32 atom pairs
+    const int* tile_off;        // [nunits] first tile slot of the unit (static prefix of the units' column-block counts)
+    unsigned* unit_hits;        // [nunits] bit t set: column block t of the unit is in range
+    uint2* masks;               // [tile slots][32] (row mask, column mask) of every lane
     int* work_counter;
     int shard_rank, shard_count;    // units are dealt round-robin to shards (shard_count 1: all)
 };
@@ -220,7 +225,9 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
         bool hit = false;
         if (lane < nc) hit = box_box_dist2(A.c.bbc[ra], A.c.bbh[ra], A.c.bbc[cb0+lane], A.c.bbh[cb0+lane]) < lim2;
         unsigned hits = __ballot_sync(FULL, hit);
+        if (lane == 0) A.u.unit_hits[u] = hits;
         if (!hits) continue;
+        const int toff = A.u.tile_off[u];
         __syncwarp();
         born_load(A, ra, lane, R);
         const bool row_heavy = ra < A.c.nhb;                 // hydrogen rows receive but never descreen
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
             __syncwarp();
             unsigned rowmask, colmask;
             pq_masks<CUTOFF>(Cc.x, Cc.y, Cc.z, pa.x, pa.y, pa.z, lim2, diag, lane, rowmask, colmask);
+            A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane] = make_uint2(rowmask, colmask);
             rsum += born_role<CUTOFF>(tabv, Cc, rowmask, pa.x, pa.y, pa.z, tbase_a, A.c.inv_h, npair);
             if (!diag && row_heavy) {
                 const int b = cb*TILE+lane;
@@ -684,11 +692,10 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
         if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
         const int2 un = A.u.units[u];
         const int ra = un.x;
-        const int cb0 = un.y & 0xfffff, nc = un.y >> 20;
-        bool hit = false;
-        if (lane < nc) hit = box_box_dist2(A.c.bbc[ra], A.c.bbh[ra], A.c.bbc[cb0+lane], A.c.bbh[cb0+lane]) < lim2;
-        unsigned hits = __ballot_sync(FULL, hit);
+        const int cb0 = un.y & 0xfffff;
+        unsigned hits = A.u.unit_hits[u];                         // found by k_born
         if (!hits) continue;
+        const int toff = A.u.tile_off[u];
         __syncwarp();
         deriv_load(A, ra, lane, R);
         const int a = ra*TILE+lane;
@@ -702,8 +709,8 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
             __syncwarp();
             deriv_load(A, cb, lane, Cc);
             __syncwarp();
-            unsigned rowmask, colmask;
-            pq_masks<CUTOFF>(Cc.x, Cc.y, Cc.z, px, py, pz, lim2, diag, lane, rowmask, colmask);
+            const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
+            const unsigned rowmask = mk.x, colmask = mk.y;
             if (diag) {
                 const float4 r = deriv_role<CUTOFF, 0>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h);
                 racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
