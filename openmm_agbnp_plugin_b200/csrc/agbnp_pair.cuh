@@ -127,14 +127,15 @@ __device__ __forceinline__ float pq_dist2(bool exact, float dx, float dy, float 
     return exact ? dist2_exact(dx, dy, dz) : fmaf(dz, dz, fmaf(dy, dy, dx*dx));
 }
 
-// step 1: masks of in-range pairs of one tile.  s_cx/y/z: column atoms (SoA), (px,py,pz): this lane's row atom.
+// step 1: masks of in-range pairs of one tile.  s_c: column atoms (x, y, z, -), (px,py,pz): this lane's row atom.
 template <bool CUTOFF>
-__device__ __forceinline__ void pq_masks(const float* s_cx, const float* s_cy, const float* s_cz, float px, float py, float pz,
+__device__ __forceinline__ void pq_masks(const float4* s_c, float px, float py, float pz,
                                          float lim2, bool diag, int lane, unsigned& rowmask, unsigned& colmask) {
     rowmask = 0; colmask = 0;
 #pragma unroll 8
     for (int jj = 0; jj < TILE; jj++) {
-        const float dx = s_cx[jj]-px, dy = s_cy[jj]-py, dz = s_cz[jj]-pz;
+        const float4 c = s_c[jj];                                   // one broadcast 16-byte load
+        const float dx = c.x-px, dy = c.y-py, dz = c.z-pz;
         const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
         const bool ok = d2 < lim2 && !(diag && jj == lane);
         const unsigned m = __ballot_sync(FULL, ok);
@@ -155,14 +156,15 @@ struct BornArgs {
     unsigned long long* counters;
 };
 
-struct BornSmem { float x[TILE], y[TILE], z[TILE], w[TILE]; int tj[TILE]; };     // w = s_j/(4 pi), 0 for non-screeners
+struct BornSmem { float4 p[TILE]; int tj[TILE]; };     // p = (x, y, z, s_j/(4 pi)); .w = 0 for non-screeners
 
 // contribution of partner jj (valid = the pair exists; invalid slots run the same instructions on a harmless atom)
 template <bool CUTOFF>
 __device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o, int jj, bool valid, float px, float py, float pz,
                                            int tbase, float inv_h, unsigned& npair) {
     const int tj = o.tj[jj];
-    const float dx = o.x[jj]-px, dy = o.y[jj]-py, dz = o.z[jj]-pz;
+    const float4 c = o.p[jj];
+    const float dx = c.x-px, dy = c.y-py, dz = c.z-pz;
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
     const float d = d2*rsqrtf(fmaxf(d2, 1e-20f));
     const float t = d*inv_h;
@@ -170,7 +172,7 @@ __device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o
     const bool use = valid && tj >= 0;
     const float q = spline_value(tabv[tbase + max(tj, 0)*I4_INTERVALS + k], t-(float) k);
     npair += use;
-    return use ? o.w[jj]*q : 0.f;
+    return use ? c.w*q : 0.f;
 }
 
 // everything atom "me" receives from the partners in `mask`; two partners per trip for instruction-level parallelism
@@ -194,8 +196,7 @@ __device__ __forceinline__ void born_load(const BornArgs& A, int blk, int lane, 
     const int j = blk*TILE+lane;
     const float4 p = A.c.posq[j];
     const double vj = A.vS[j];
-    s.x[lane] = p.x; s.y[lane] = p.y; s.z[lane] = p.z;
-    s.w[lane] = vj > 0 ? PIFAC*(A.accS[j].w/(float) vj) : 0.f;
+    s.p[lane] = make_float4(p.x, p.y, p.z, vj > 0 ? PIFAC*(A.accS[j].w/(float) vj) : 0.f);
     s.tj[lane] = A.c.tj[j];
 }
 
@@ -242,13 +243,14 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
             born_load(A, cb, lane, Cc);
             __syncwarp();
             unsigned rowmask, colmask;
-            pq_masks<CUTOFF>(Cc.x, Cc.y, Cc.z, pa.x, pa.y, pa.z, lim2, diag, lane, rowmask, colmask);
+            pq_masks<CUTOFF>(Cc.p, pa.x, pa.y, pa.z, lim2, diag, lane, rowmask, colmask);
             A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane] = make_uint2(rowmask, colmask);
             rsum += born_role<CUTOFF>(tabv, Cc, rowmask, pa.x, pa.y, pa.z, tbase_a, A.c.inv_h, npair);
             if (!diag && row_heavy) {
                 const int b = cb*TILE+lane;
                 const int tbase_b = (int) A.c.ts[b]*A.c.ntj*I4_INTERVALS;
-                const float csum = born_role<CUTOFF>(tabv, R, colmask, Cc.x[lane], Cc.y[lane], Cc.z[lane], tbase_b, A.c.inv_h, npair);
+                const float4 pc = Cc.p[lane];
+                const float csum = born_role<CUTOFF>(tabv, R, colmask, pc.x, pc.y, pc.z, tbase_b, A.c.inv_h, npair);
                 if (csum != 0.f) atomicAdd(&A.bsum[b], csum);
             }
         }
@@ -603,7 +605,7 @@ struct DerivArgs {
     float4* dacc;               // out [np]: fx, fy, fz, W+U (zeroed slab; float red.global)
 };
 
-struct DerivSmem { float x[TILE], y[TILE], z[TILE], s[TILE], bw[TILE]; int pk[TILE]; };    // pk = ts | (tj & 0xff) << 8
+struct DerivSmem { float4 p[TILE]; float bw[TILE]; int pk[TILE]; };    // p = (x, y, z, s); pk = ts | (tj & 0xff) << 8
 
 struct DerivMe { float px, py, pz, s, bw; int base, tj; };
 
@@ -615,7 +617,8 @@ constexpr int WMAT_STRIDE = 33;         // row stride: lanes writing the same co
 template <bool CUTOFF, int MODE>
 __device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, int jj,
                                            bool valid, const DerivMe& me, int ntj, float inv_h, float& fx, float& fy, float& fz, float& wu) {
-    const float dx = o.x[jj]-me.px, dy = o.y[jj]-me.py, dz = o.z[jj]-me.pz;
+    const float4 c = o.p[jj];
+    const float dx = c.x-me.px, dy = c.y-me.py, dz = c.z-me.pz;
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
     const int pk = o.pk[jj];
     const int ts_o = pk & 0xff;
@@ -633,7 +636,7 @@ __device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tab
         const int tj_o = (int) (signed char) ((pk >> 8) & 0xff);
         const float q1 = spline_deriv(tabd[me.base + max(tj_o, 0)*I4_INTERVALS + k], fr);
         const float q2 = spline_deriv(tabd[ix], fr);
-        w = (valid && tj_o >= 0) ? me.bw*o.s[jj]*q1 : 0.f;      // o descreens me (needs heavy(o))
+        w = (valid && tj_o >= 0) ? me.bw*c.w*q1 : 0.f;          // o descreens me (needs heavy(o))
         w = fmaf(bwo*me.s, q2, w)*inv_d;
         if (MODE == 1 && valid) wmat[lane*WMAT_STRIDE + jj] = w;
     }
@@ -662,8 +665,7 @@ __device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* t
 __device__ __forceinline__ void deriv_load(const DerivArgs& A, int blk, int lane, DerivSmem& s) {
     const int j = blk*TILE+lane;
     const float4 p = A.c.posq[j];
-    s.x[lane] = p.x; s.y[lane] = p.y; s.z[lane] = p.z;
-    s.s[lane] = A.vsf[j];
+    s.p[lane] = make_float4(p.x, p.y, p.z, A.vsf[j]);
     s.bw[lane] = A.brw[j] - PIFAC*A.kdiel*(p.w*p.w + A.gbacc[j].w*A.born[j])*A.bfp[j];
     s.pk[lane] = (int) A.c.ts[j] | (((int) A.c.tj[j] & 0xff) << 8);
 }
@@ -699,7 +701,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
         __syncwarp();
         deriv_load(A, ra, lane, R);
         const int a = ra*TILE+lane;
-        const float px = R.x[lane], py = R.y[lane], pz = R.z[lane], s_a = R.s[lane], bw_a = R.bw[lane];
+        const float px = R.p[lane].x, py = R.p[lane].y, pz = R.p[lane].z, s_a = R.p[lane].w, bw_a = R.bw[lane];
         const int ts_a = A.c.ts[a], tj_a = A.c.tj[a];
         float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
         while (hits) {
@@ -719,7 +721,8 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
                 racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
                 __syncwarp();                                   // the weights are read by other lanes
                 const int pk = Cc.pk[lane];
-                const float4 c = deriv_role<CUTOFF, 2>(tabv, tabd, R, wmat, lane, colmask, Cc.x[lane], Cc.y[lane], Cc.z[lane], Cc.s[lane], Cc.bw[lane],
+                const float4 pc = Cc.p[lane];
+                const float4 c = deriv_role<CUTOFF, 2>(tabv, tabd, R, wmat, lane, colmask, pc.x, pc.y, pc.z, pc.w, Cc.bw[lane],
                                                        pk & 0xff, (int) (signed char) ((pk >> 8) & 0xff), A.c.ntj, A.c.inv_h);
                 if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], c);
             }
