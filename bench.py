@@ -410,6 +410,31 @@ def b200_arm(args):
         line["config"]["stand_in"] = "example/hivrt_agbnp1.dms is absent from the reference checkout (.MISSING_LARGE_BLOBS); 2clr x 3 stand-in, N=17949 (SURVEY 8d)"
     if sharded:
         line["collectives_per_step"] = coll_per_step
+        # the other way to use N GPUs at this size (BASELINE config 5): N independent replicas, one handle per GPU, no
+        # communication -- reported next to the sharded number, never instead of it
+        rctx = plug.Context(force, device=local)
+        rh = rctx.kernel.handle
+
+        def rep_eval(k):
+            rc = L.agbnp_b200_execute_device(rh, posq_sets[k % JITTER_SETS].data_ptr(), sp, d_force.data_ptr(), 0, n, None, None)
+            if rc != 0:
+                raise RuntimeError(L.agbnp_b200_last_error(rh).decode())
+        e = C.c_double(0.0)
+        L.agbnp_b200_execute_device(rh, posq_sets[0].data_ptr(), sp, d_force.data_ptr(), 0, n, None, C.byref(e))
+        for k in range(5):
+            rep_eval(k)
+        L.agbnp_b200_synchronize(rh, sp); dist.barrier(); torch.cuda.synchronize()
+        r0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        r1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        for k in range(K):
+            flush.zero_()
+            r0[k].record(stream); rep_eval(k); r1[k].record(stream)
+        L.agbnp_b200_synchronize(rh, sp); dist.barrier(); torch.cuda.synchronize()
+        tr = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(r0, r1))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        line["replica_mode"] = {"value": world*K*1e3/float(tr.item()), "unit": UNIT, "ms_per_step": float(tr.item())/K, "scaling": "weak",
+                                "what": "%d independent evaluations in flight, one per GPU (max over ranks of the per-GPU time)" % world}
+        rctx.kernel.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # unjittered evaluation through the synchronous device path for the full-size parity check
         p = torch.zeros((n, 4), dtype=torch.float32)
