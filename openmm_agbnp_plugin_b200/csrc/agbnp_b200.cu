@@ -788,8 +788,14 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->have_events = true;
         CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
-        h->gb_grid = h->num_sm*4;
-        h->pq_grid = h->num_sm*4;
+#ifndef GB_CTAS
+#define GB_CTAS 4
+#endif
+        h->gb_grid = h->num_sm*GB_CTAS;
+#ifndef PQ_CTAS
+#define PQ_CTAS 5
+#endif
+        h->pq_grid = h->num_sm*PQ_CTAS;
         const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float)));
         CK(cudaFuncSetAttribute(k_born<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));

@@ -18,6 +18,9 @@ constexpr int GB_THREADS = 128;
 #ifndef GB_MIN_BLOCKS
 #define GB_MIN_BLOCKS 3
 #endif
+#ifndef GB_FAR_FACTOR
+#define GB_FAR_FACTOR 64.f          // d^2 > 64 B_i B_j: exp(-d^2/4B_iB_j) < e^-16
+#endif
 constexpr int GB_CHUNK = 8;             // column tiles per GB work unit
 constexpr int I4_INTERVALS = 15;        // AGBNP_I4LOOKUP_NA - 1
 constexpr float PIFAC = 0.07957747154594767f;   // 1/(4 pi)
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
             if (lane < cend-un.y) {
                 const float bd2 = box_box_dist2(ca, ha, A.c.bbc[un.y+lane], A.c.bbh[un.y+lane]);
                 hit = !CUTOFF || bd2 < A.c.cut2;
-                far = bd2 > 64.f*A.bmax[ra]*A.bmax[un.y+lane];
+                far = bd2 > GB_FAR_FACTOR*A.bmax[ra]*A.bmax[un.y+lane];
             }
             tiles = __ballot_sync(FULL, hit);
             fartiles = __ballot_sync(FULL, far);
