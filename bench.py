@@ -377,7 +377,7 @@ def b200_arm(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        e2e = {"value": K * (world if world > 1 else 1) / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 24 * n + 8 * 8 + 4 * 8,
+        e2e = {"value": K * (world if world > 1 else 1) / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 12 * n + 560,
                "how": "AGBNPplugin Context.setPositions + calcForcesAndEnergy (agbnp_b200_execute_host): pinned staging, H2D positions, D2H forces+energy, host wall clock"}
     else:
         pinned = [p.cpu().pin_memory() for p in posq_sets]

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -93,7 +94,7 @@ struct agbnp_b200 {
     int* d_root_cnt = nullptr;
     int* d_ctrl = nullptr;
     size_t slab_bytes = 0;
-    DevBuf<double> d_force_out;             // double[3n] for the host path
+    DevBuf<float> d_force_out;              // float[3n] for the host path
     // tree
     // tree capacities (grown on overflow): nodes per root, nodes per level, level-2 neighbors per root
     int tree_cap = 512, tree_wcap = 192, nbrmax = 64;
@@ -114,9 +115,10 @@ struct agbnp_b200 {
     bool gamma_work_global = false;
     // pinned host staging
     float4* h_posq = nullptr;
-    double* h_force = nullptr;
-    double* h_scal = nullptr;               // SC_COUNT doubles + status
-    int* h_ctrl = nullptr;
+    float* h_force = nullptr;
+    unsigned char* h_tail = nullptr;        // pinned mirror of the slab's [scalars | counters | control words] span: one copy per evaluation
+    double* h_scal = nullptr;               // -> h_tail
+    int* h_ctrl = nullptr;                  // -> h_tail + 512
     // diagnostics
     DevBuf<int2> d_pairs;
     cudaEvent_t ev[2] = {};
@@ -148,8 +150,7 @@ struct agbnp_b200 {
     ~agbnp_b200() {
         if (h_posq) cudaFreeHost(h_posq);
         if (h_force) cudaFreeHost(h_force);
-        if (h_scal) cudaFreeHost(h_scal);
-        if (h_ctrl) cudaFreeHost(h_ctrl);
+        if (h_tail) cudaFreeHost(h_tail);
         if (have_events) { for (auto& e : ev) cudaEventDestroy(e); for (auto& e : async_ev) cudaEventDestroy(e); }
         for (auto& e : prof_pool) cudaEventDestroy(e);
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
@@ -558,7 +559,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         if (sink && sink->ptr) {
             if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;
             else if (sink->layout == 1) fa.out_fixed = (unsigned long long*) sink->ptr;
-            else fa.out_f64 = (double*) sink->ptr;
+            else fa.out_set = (float*) sink->ptr;
         }
         fa.energy_accum = sink ? sink->d_energy : nullptr;
         begin(K_FINISH);
@@ -612,8 +613,8 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
 
 // read back status + scalars (synchronises the stream); returns the status bits
 int fetch_status(agbnp_b200* h, cudaStream_t s) {
-    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->h_scal, h->d_scalars, sizeof(double)*SC_COUNT, cudaMemcpyDeviceToHost, s));
+    // scalars, counters and control words are three consecutive 256-byte slots of the slab (upload_static)
+    CK(cudaMemcpyAsync(h->h_tail, h->d_scalars, 512 + sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return h->h_ctrl[CW_STATUS];
 }
@@ -654,6 +655,10 @@ void grow_ahead(agbnp_b200* h, const int* ctrl) {
 
 void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_posq_in, cudaStream_t s) {
     if (h->ahead_pending) { h->ahead_pending = false; grow(h, h->ahead, true); }
+    static const bool timing = std::getenv("AGBNP_B200_HOST_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tp0 = timing ? now() : 0;
+    double tp1 = tp0;
     const int interval = h->cfg.reorder_interval > 0 ? h->cfg.reorder_interval : 500;
     if (!h->order_valid || h->evals_since_sort >= interval) {
         std::vector<float> tmp;
@@ -665,8 +670,12 @@ void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_pos
         }
         CK(cudaDeviceSynchronize());                   // queued evaluations still read the arrays about to be replaced
         build_order(h, host_xyz, stride, s);
+        if (timing) tp1 = now();
     }
-    if (h->params_dirty) upload_static(h, s);
+    if (h->params_dirty) {
+        upload_static(h, s);
+        if (timing) std::fprintf(stderr, "prepare: build_order %.2f ms, upload_static %.2f ms\n", tp1-tp0, now()-tp1);
+    }
 }
 
 // synchronous evaluation: everything is enqueued at once (the finish kernel checks the status word on the device), one
@@ -803,9 +812,9 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         CK(cudaFuncSetAttribute(k_deriv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         alloc_tree_scratch(h);
         CK(cudaMallocHost((void**) &h->h_posq, sizeof(float4)*n));
-        CK(cudaMallocHost((void**) &h->h_force, sizeof(double)*3*n));
-        CK(cudaMallocHost((void**) &h->h_scal, sizeof(double)*SC_COUNT));
-        CK(cudaMallocHost((void**) &h->h_ctrl, sizeof(int)*CW_COUNT));
+        CK(cudaMallocHost((void**) &h->h_force, sizeof(float)*3*n));
+        CK(cudaMallocHost((void**) &h->h_tail, 512 + sizeof(int)*CW_COUNT));
+        h->h_scal = (double*) h->h_tail; h->h_ctrl = (int*) (h->h_tail + 512);
         h->d_posq_in.alloc(n);
         h->d_force_out.alloc((size_t) 3*n);
     } catch (const CudaFail& f) {
@@ -838,16 +847,30 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
     try {
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = h->own_stream;
+        static const bool timing = std::getenv("AGBNP_B200_HOST_TIMING") != nullptr;
+        static double acc[5] = {0, 0, 0, 0, 0};
+        static long ncall = 0;
+        auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = timing ? now() : 0;
         if (async_drain(h) != AGBNP_B200_OK) return AGBNP_B200_ERR_CAPACITY;
-        for (int i = 0; i < h->n; i++)
-            h->h_posq[i] = make_float4((float) pos[3*i], (float) pos[3*i+1], (float) pos[3*i+2], 0.f);
+        {
+            float* __restrict__ hp = (float*) h->h_posq;
+            const double* __restrict__ p = pos;
+            for (int i = 0; i < h->n; i++) {
+                hp[4*i] = (float) p[3*i]; hp[4*i+1] = (float) p[3*i+1]; hp[4*i+2] = (float) p[3*i+2]; hp[4*i+3] = 0.f;
+            }
+        }
         CK(cudaMemcpyAsync(h->d_posq_in.p, h->h_posq, sizeof(float4)*h->n, cudaMemcpyHostToDevice, s));
+        const double t1 = timing ? now() : 0;
         prepare(h, (const float*) h->h_posq, 4, nullptr, s);
-        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};
+        const double t2 = timing ? now() : 0;
+        double t3 = 0;
+        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};      // layout 2: float[3n], assigned
         for (int attempt = 0; ; attempt++) {
             launch_all(h, h->d_posq_in.p, s, &sink);
             if (include_forces && forces)
-                CK(cudaMemcpyAsync(h->h_force, h->d_force_out.p, sizeof(double)*3*h->n, cudaMemcpyDeviceToHost, s));
+                CK(cudaMemcpyAsync(h->h_force, h->d_force_out.p, sizeof(float)*3*h->n, cudaMemcpyDeviceToHost, s));
+            if (timing) t3 = now();
             const int status = fetch_status(h, s);          // the one synchronisation of the call
             if (status == 0) break;
             if (attempt >= 8 || !grow(h, h->h_ctrl)) {
@@ -857,8 +880,23 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         }
         h->evals_since_sort++; h->total_evals++;
         grow_ahead(h, h->h_ctrl);
-        if (include_forces && forces) for (int i = 0; i < 3*h->n; i++) forces[i] += h->h_force[i];
+        const double t4 = timing ? now() : 0;
+        if (include_forces && forces) {
+            const float* __restrict__ hf = h->h_force;
+            double* __restrict__ f = forces;
+            const int n3 = 3*h->n;
+            for (int i = 0; i < n3; i++) f[i] += (double) hf[i];
+        }
         if (energy) *energy = include_energy ? h->h_scal[SC_SPARE0] : 0.0;
+        if (timing) {
+            const double t5 = now();
+            acc[0] += t1-t0; acc[1] += t2-t1; acc[2] += t3-t2; acc[3] += t4-t3; acc[4] += t5-t4;
+            if (++ncall % 100 == 0) {
+                std::fprintf(stderr, "execute_host us/call: pack+h2d enqueue %.1f  prepare %.1f  launch %.1f  wait %.1f  unpack %.1f\n",
+                             acc[0]/100, acc[1]/100, acc[2]/100, acc[3]/100, acc[4]/100);
+                for (double& a : acc) a = 0;
+            }
+        }
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }

@@ -748,7 +748,7 @@ struct FinishArgs {
     float inv_roffset;                  // nu = +gamma/roffset (enlarged radii), -gamma/roffset (vdW radii)
     float* out_f32;                     // layout 0: float[3n] interleaved, +=
     unsigned long long* out_fixed;      // layout 1: OpenMM fixed point [3][padded_n], atomic +=
-    double* out_f64;                    // internal: double[3n] interleaved, = (host path)
+    float* out_set;                     // internal: float[3n] interleaved, = (host path)
     int padded_n;
     double* scalars;                    // SC_* terms
     const int* status;                  // capacity-overflow bits of this evaluation: nothing is delivered unless 0
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
         fx += A.gb_scale*(double) g.x + (double) d.x + (double) t.x; fy += A.gb_scale*(double) g.y + (double) d.y + (double) t.y;
         fz += A.gb_scale*(double) g.z + (double) d.z + (double) t.z;
     }
-    if (A.out_f64) { A.out_f64[3*o+0] = fx; A.out_f64[3*o+1] = fy; A.out_f64[3*o+2] = fz; }
+    if (A.out_set) { A.out_set[3*o+0] = (float) fx; A.out_set[3*o+1] = (float) fy; A.out_set[3*o+2] = (float) fz; }
     if (A.out_f32) { A.out_f32[3*o+0] += (float) fx; A.out_f32[3*o+1] += (float) fy; A.out_f32[3*o+2] += (float) fz; }
     if (A.out_fixed) {
         atomicAdd(&A.out_fixed[o], (unsigned long long) (long long) (fx*FORCE_SCALE));
