@@ -286,9 +286,11 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
     const int nbrmax = A.nbrmax, cap = A.cap, wcap = A.wcap;
     const int gwarp = blockIdx.x*nwarp + warp;
 
+    // the address space of the work arrays is a compile-time fact: in the shared-memory instantiation every access is an
+    // LDS/STS with 32-bit addressing instead of a generic LD/ST
     TreeWork W;
-    W.bind(A.wk_global ? A.wk_global + (size_t) gwarp*A.wk_stride : smem_raw + (size_t) warp*tree_work_bytes(nbrmax, cap, wcap),
-           nbrmax, cap, wcap);
+    if (SMEM_WORK) W.bind(smem_raw + (size_t) warp*tree_work_bytes(nbrmax, cap, wcap), nbrmax, cap, wcap);
+    else W.bind(A.wk_global + (size_t) gwarp*A.wk_stride, nbrmax, cap, wcap);
     unsigned char* stage = A.stage + (size_t) gwarp*A.stage_stride;
     NodeGauss* G = (NodeGauss*) stage;
     float4* swL = (float4*) (G+cap);
