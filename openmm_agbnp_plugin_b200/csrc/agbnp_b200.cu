@@ -196,7 +196,7 @@ void alloc_tree_scratch(agbnp_b200* h) {
         if (h->gamma_work_global) gctas = 4;
         h->gamma_grid = h->num_sm*(int) gctas;
         if (h->gamma_work_global) h->d_gamma_scratch.alloc((size_t) h->gamma_grid*h->gamma_warps*pw); else h->d_gamma_scratch.release();
-        CK(cudaFuncSetAttribute(k_tree_gamma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CK(cudaFuncSetAttribute(k_tree_gamma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) std::max<size_t>(h->gamma_work_global ? 0 : h->gamma_warps*pw, 1024)));
     }
 }
@@ -500,8 +500,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
         const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
         begin(K_BORN);
-        if (cutoff) k_born<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
-        else k_born<false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba);
+        if (pc.tab_smem) { if (cutoff) k_born<true, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); else k_born<false, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); }
+        else { if (cutoff) k_born<true, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); else k_born<false, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); }
         end(K_BORN);
     }
     if (v1 && (phase_mask & PH_BORNFIN)) {
@@ -535,8 +535,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
         const size_t sm = 2*tab_bytes + PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float));
         begin(K_DERIV);
-        if (cutoff) k_deriv<true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da);
-        else k_deriv<false><<<h->pq_grid, PQ_THREADS, sm, s>>>(da);
+        if (pc.tab_smem) { if (cutoff) k_deriv<true, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); else k_deriv<false, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); }
+        else { if (cutoff) k_deriv<true, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); else k_deriv<false, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); }
         end(K_DERIV);
     }
     if (v1 && (phase_mask & PH_GAMMA)) {
@@ -546,7 +546,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         gm.scratch = h->gamma_work_global ? h->d_gamma_scratch.p : nullptr;
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
         begin(K_GAMMA);
-        k_tree_gamma<<<h->gamma_grid, 32*h->gamma_warps, h->gamma_work_global ? 0 : h->gamma_warps*gm.scratch_stride, s>>>(gm);
+        if (h->gamma_work_global) k_tree_gamma<false><<<h->gamma_grid, 32*h->gamma_warps, 0, s>>>(gm);
+        else k_tree_gamma<true><<<h->gamma_grid, 32*h->gamma_warps, h->gamma_warps*gm.scratch_stride, s>>>(gm);
         end(K_GAMMA);
     }
     if (phase_mask & PH_FINISH) {
@@ -806,10 +807,14 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
 #endif
         h->pq_grid = h->num_sm*PQ_CTAS;
         const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float)));
-        CK(cudaFuncSetAttribute(k_born<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
-        CK(cudaFuncSetAttribute(k_born<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
-        CK(cudaFuncSetAttribute(k_deriv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
-        CK(cudaFuncSetAttribute(k_deriv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_born<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_born<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_born<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_born<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_deriv<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_deriv<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_deriv<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_deriv<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         alloc_tree_scratch(h);
         CK(cudaMallocHost((void**) &h->h_posq, sizeof(float4)*n));
         CK(cudaMallocHost((void**) &h->h_force, sizeof(float)*3*n));

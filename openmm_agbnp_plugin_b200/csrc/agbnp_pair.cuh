@@ -203,16 +203,19 @@ __device__ __forceinline__ void born_load(const BornArgs& A, int blk, int lane, 
     s.tj[lane] = A.c.tj[j];
 }
 
-template <bool CUTOFF>
+// TAB_SMEM: the spline tables are staged in shared memory (the normal case; a compile-time fact so that the lookups are
+// LDS instead of generic loads); otherwise (too many radius classes) they are read from global memory through L1
+template <bool CUTOFF, bool TAB_SMEM>
 __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ntab = A.c.tab_smem ? A.c.ntables*I4_INTERVALS : 0;
+    const int ntab = TAB_SMEM ? A.c.ntables*I4_INTERVALS : 0;
     float4* s_tabv = (float4*) smem_raw;                                // [ntables*15]
     BornSmem* sm = (BornSmem*) (s_tabv + ntab);                         // [PQ_WARPS][2]: row block, column block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < ntab; i += blockDim.x) s_tabv[i] = A.c.i4v[i];
     __syncthreads();
-    const float4* tabv = A.c.tab_smem ? s_tabv : A.c.i4v;
+    const float4* tabv;
+    if (TAB_SMEM) tabv = s_tabv; else tabv = A.c.i4v;
     BornSmem& R = sm[2*warp];
     BornSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
@@ -673,10 +676,10 @@ __device__ __forceinline__ void deriv_load(const DerivArgs& A, int blk, int lane
     s.pk[lane] = (int) A.c.ts[j] | (((int) A.c.tj[j] & 0xff) << 8);
 }
 
-template <bool CUTOFF>
+template <bool CUTOFF, bool TAB_SMEM>
 __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ntab = A.c.tab_smem ? A.c.ntables*I4_INTERVALS : 0;
+    const int ntab = TAB_SMEM ? A.c.ntables*I4_INTERVALS : 0;
     float4* s_tabv = (float4*) smem_raw;
     float4* s_tabd = s_tabv + ntab;
     DerivSmem* sm = (DerivSmem*) (s_tabd + ntab);                       // [PQ_WARPS][2]
@@ -684,8 +687,8 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < ntab; i += blockDim.x) { s_tabv[i] = A.c.i4v[i]; s_tabd[i] = A.c.i4d[i]; }
     __syncthreads();
-    const float4* tabv = A.c.tab_smem ? s_tabv : A.c.i4v;
-    const float4* tabd = A.c.tab_smem ? s_tabd : A.c.i4d;
+    const float4 *tabv, *tabd;
+    if (TAB_SMEM) { tabv = s_tabv; tabd = s_tabd; } else { tabv = A.c.i4v; tabd = A.c.i4d; }
     DerivSmem& R = sm[2*warp];
     DerivSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;

@@ -662,11 +662,13 @@ struct GammaArgs {
 
 __host__ __device__ inline size_t gamma_work_bytes(int cap) { return (size_t) cap*(sizeof(float) + sizeof(float4)); }
 
+template <bool SMEM_WORK>
 __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    unsigned char* wk = A.scratch ? A.scratch + (size_t) (blockIdx.x*nwarp+warp)*A.scratch_stride
-                                  : smem_raw + (size_t) warp*gamma_work_bytes(A.cap);
+    unsigned char* wk;
+    if (SMEM_WORK) wk = smem_raw + (size_t) warp*gamma_work_bytes(A.cap);
+    else wk = A.scratch + (size_t) (blockIdx.x*nwarp+warp)*A.scratch_stride;
     float4* hu = (float4*) wk;                      // [cap] children sums (F', P'x, P'y, P'z) per parent slot
     float* gam = (float*) (hu + A.cap);             // [cap] gamma_1..n per slot
     for (;;) {
