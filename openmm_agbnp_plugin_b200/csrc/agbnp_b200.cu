@@ -68,7 +68,7 @@ struct agbnp_b200 {
     std::vector<float> box_lo, box_hi;      // block bounding boxes at sort time (host; unit ordering only)
 
     // static sorted arrays
-    DevBuf<int> d_orig;
+    DevBuf<int> d_orig, d_origbin;
     DevBuf<float> d_charge, d_radius, d_alpha, d_gamma;
     DevBuf<double> d_aL, d_vL, d_aS, d_vS;
     DevBuf<unsigned char> d_rcbin, d_ts;
@@ -337,6 +337,11 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         tj[k] = (signed char) sp.i4.type_screener[o];
     }
     h->d_orig.upload(h->orig, s);
+    {
+        std::vector<int> ob(np, -1);
+        for (int k = 0; k < np; k++) if (h->orig[k] >= 0) ob[k] = h->orig[k] | ((int) rcbin[k] << 24);
+        h->d_origbin.upload(ob, s);
+    }
     h->d_charge.upload(charge, s); h->d_radius.upload(radius, s); h->d_alpha.upload(alpha, s); h->d_gamma.upload(gamma, s);
     h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s); h->d_inv_vS.upload(inv_vS, s);
     h->d_rcbin.upload(rcbin, s); h->d_ts.upload(ts, s); h->d_tj.upload(tj, s);
@@ -467,7 +472,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
         ta.items = h->d_items.p; ta.nitems = (int) h->items.size(); ta.bcount = h->d_bcount.p; ta.blist = h->d_blist.p;
-        ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.rcbin = h->d_rcbin.p;
+        ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.origbin = h->d_origbin.p; ta.rcbin = h->d_rcbin.p;
         ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;
         ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
         ta.volmina = h->k.volmina; ta.volminb = h->k.volminb; ta.min_gvol = h->k.min_gvol;
@@ -772,6 +777,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
     if (cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count) {
         g_create_error = "agbnp_b200: bad shard rank/count"; return AGBNP_B200_ERR_ARG;
     }
+    if (n >= (1 << 24)) { g_create_error = "agbnp_b200: more than 2^24 particles are not supported"; return AGBNP_B200_ERR_ARG; }
     if (cfg->nonbonded_method == AGBNP_B200_CUTOFF_NONPERIODIC && !(cfg->cutoff > 0)) {
         g_create_error = "agbnp_b200: cutoff must be positive"; return AGBNP_B200_ERR_ARG;
     }

@@ -97,6 +97,7 @@ struct TreeArgs {
     const unsigned short* blist;
     const float4* posq;
     const int* orig;
+    const int* origbin;               // caller's index | radius bin << 24: one load decides both level-2 tests
     const unsigned char* rcbin;
     const double *aL, *vL, *aS, *vS;
     const float* gamma;
@@ -338,10 +339,11 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                 m &= m-1;
                 const int j = bb*TILE+lane;
                 const float4 pj = A.posq[j];
-                const int oj = A.orig[j];
+                const int ob = A.origbin[j];
+                const int oj = ob < 0 ? -1 : (ob & 0xffffff);
                 const float dx = pj.x-pr.x, dy = pj.y-pr.y, dz = pj.z-pr.z;
                 const float d2 = dx*dx + dy*dy + dz*dz;
-                const bool ok = (oj > orig_r) && (d2 < A.rc2[rb*A.nbins + A.rcbin[j]]);
+                const bool ok = (oj > orig_r) && (d2 < __ldg(A.rc2 + rb*A.nbins + ((ob >> 24) & 0x7f)));
                 const unsigned am = __ballot_sync(FULL, ok);
                 if (ok) {
                     const int p = nn + __popc(am & lanemask_lt());
