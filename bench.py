@@ -242,6 +242,9 @@ def b200_arm(args):
 
     if sharded:
         sk = sharding.CudaShardKernel(force, local, rank, world)
+        if os.environ.get("AGBNP_B200_PEER", "1") != "0":
+            if not sk.setup_peer_exchange():         # one-shot all-reduces over NVLink peer memory instead of NCCL
+                log("bench: peer-memory exchange unavailable on this box, using NCCL all-reduces")
         ev = sharding.ShardedEvaluator(sk, position_owner=0)
         handle = sk.handle
 
@@ -402,7 +405,7 @@ def b200_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic" if s.get("name", "").startswith("hivrt-standin") else "example/hivrt_agbnp1.dms",
-            "config": config_dict(s, args, "1 GPU" if world == 1 else ("one evaluation sharded over %d GPUs, NCCL" % world if sharded else "%d independent replicas" % world)),
+            "config": config_dict(s, args, "1 GPU" if world == 1 else ("one evaluation sharded over %d GPUs, %s" % (world, "peer-memory exchanges over NVLink (NCCL for the position broadcast)" if getattr(sk, "peer", False) else "NCCL all-reduces") if sharded else "%d independent replicas" % world)),
             "ns_per_day": value * NS_PER_DAY_PER_EVAL_PER_S, "roofline": roofline, "path_roofline": path_roofline, "roofline_tree": roofline_tree,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "kernels_us": kernels_us, "mean_energy_kj_mol": e_mean,
             "host_wall_ms_per_step": t_wall / K * 1e3}

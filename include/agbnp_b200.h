@@ -167,6 +167,20 @@ int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* byte
 int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int force_layout, int padded_n,
                             double* d_energy, double* h_energy);
 
+/* ---- peer-memory exchange over NVLink (optional replacement of the all-reduces above; same node, one process per GPU).
+ * Every shard owns a "mailbox" in its own HBM with one slot per (exchange buffer, source shard).  An exchange of buffer X is
+ *   push: each shard stores its partial X into its slot of every PEER's mailbox (plain P2P stores over NVLink), fences,
+ *         and raises a per-(buffer, source) epoch flag in the peer's mailbox;
+ *   sum : each shard waits for the flags of all peers, then adds the peers' slots to its own partial -- a one-shot
+ *         all-reduce whose latency is one NVLink store + one flag round trip instead of a ring/tree of NCCL steps.
+ * Set-up: every shard exports a CUDA IPC handle of its mailbox (64 bytes), the caller gathers the handles of all shards
+ * (any host-side all-gather) and hands them to every shard. */
+int agbnp_b200_peer_export(agbnp_b200* h, void* ipc_handle_64_bytes);
+int agbnp_b200_peer_import(agbnp_b200* h, const void* ipc_handles /* [shard_count][64] */, int shard_count);
+int agbnp_b200_peer_exchange(agbnp_b200* h, int which /* agbnp_b200_buffer */, void* stream);
+/* positions (device float4[N], caller's order) from shard `owner` to every shard's own d_posq, same mechanism */
+int agbnp_b200_peer_broadcast(agbnp_b200* h, void* d_posq, int owner, void* stream);
+
 /* library / build identification, e.g. "agbnp_b200 0.1 sm_100a" */
 const char* agbnp_b200_version(void);
 

@@ -52,6 +52,10 @@ def lib():
         L.agbnp_b200_shard_phase.argtypes = [vp, C.c_int, vp, vp]
         L.agbnp_b200_shard_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.agbnp_b200_shard_finish.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, dp]
+        L.agbnp_b200_peer_export.argtypes = [vp, vp]
+        L.agbnp_b200_peer_import.argtypes = [vp, vp, C.c_int]
+        L.agbnp_b200_peer_exchange.argtypes = [vp, C.c_int, vp]
+        L.agbnp_b200_peer_broadcast.argtypes = [vp, vp, C.c_int, vp]
         _lib = L
     return _lib
 

@@ -22,6 +22,90 @@
 
 using namespace agbnp_b200_impl;
 
+namespace agbnp_b200_impl {
+
+// ---------------------------------------------------------------------------------------------------------------
+// one-shot all-reduce over peer memory (see include/agbnp_b200.h, "peer-memory exchange")
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX = 8, PEER_KINDS = 7, PEER_KIND_POSITIONS = 6;     // kinds 0..5 = agbnp_b200_buffer, 6 = positions broadcast
+struct PeerBox {
+    int rank, count;
+    unsigned char* mail[PEER_MAX];      // base of every shard's mailbox (mail[rank] is local)
+    size_t kind_off[PEER_KINDS];        // offset of a buffer kind's slots; slot of source s at kind_off + s*kind_bytes
+    size_t kind_bytes[PEER_KINDS];
+    size_t flag_off;                    // int flags[PEER_KINDS][PEER_MAX] at the end of the mailbox
+    int* counter;                       // local: CTAs of the running push that have finished
+};
+
+template <class T> __device__ __forceinline__ T peer_add(T a, T b) { return a+b; }
+template <> __device__ __forceinline__ float4 peer_add<float4>(float4 a, float4 b) { return make_float4(a.x+b.x, a.y+b.y, a.z+b.z, a.w+b.w); }
+
+// One kernel per exchange: every CTA pushes its slice of the partial buffer into the peers' mailboxes; the last CTA to
+// finish raises this shard's flag at every peer; then every CTA waits for the peers' flags and adds their slices.
+// The grid never exceeds the SM count, so all CTAs are resident and the spin cannot starve the CTA that raises the flag.
+template <class T>
+__global__ void __launch_bounds__(256) k_peer_allreduce(T* buf, size_t n, PeerBox pb, int kind, int epoch) {
+    for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) {
+        const T v = buf[i];
+        for (int p = 0; p < pb.count; p++)
+            if (p != pb.rank) ((T*) (pb.mail[p] + pb.kind_off[kind] + (size_t) pb.rank*pb.kind_bytes[kind]))[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(pb.counter, 1);
+        if (done == (int) gridDim.x-1) {                    // every CTA has fenced its stores: raise the flags
+            *pb.counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < pb.count; p++)
+                if (p != pb.rank) *(volatile int*) (pb.mail[p] + pb.flag_off + sizeof(int)*(kind*PEER_MAX + pb.rank)) = epoch;
+        }
+        const volatile int* flags = (const volatile int*) (pb.mail[pb.rank] + pb.flag_off) + kind*PEER_MAX;
+        for (int q = 0; q < pb.count; q++)
+            if (q != pb.rank) while (flags[q] < epoch) { }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const unsigned char* base = pb.mail[pb.rank] + pb.kind_off[kind];
+    for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) {
+        T acc = buf[i];
+        for (int q = 0; q < pb.count; q++)
+            if (q != pb.rank) acc = peer_add(acc, __ldcg((const T*) (base + (size_t) q*pb.kind_bytes[kind]) + i));
+        buf[i] = acc;
+    }
+}
+
+// broadcast of the positions from their owner: the owner stores them into every peer's mailbox and raises its flag there;
+// the others wait for it and copy the slot into their own position buffer
+__global__ void __launch_bounds__(256) k_peer_broadcast(float4* buf, size_t n, PeerBox pb, int owner, int epoch) {
+    const int kind = PEER_KIND_POSITIONS;
+    if (pb.rank == owner) {
+        for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) {
+            const float4 v = buf[i];
+            for (int p = 0; p < pb.count; p++) if (p != owner) ((float4*) (pb.mail[p] + pb.kind_off[kind]))[i] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(pb.counter, 1) == (int) gridDim.x-1) {
+            *pb.counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < pb.count; p++)
+                if (p != owner) *(volatile int*) (pb.mail[p] + pb.flag_off + sizeof(int)*(kind*PEER_MAX + owner)) = epoch;
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            const volatile int* flags = (const volatile int*) (pb.mail[pb.rank] + pb.flag_off) + kind*PEER_MAX;
+            while (flags[owner] < epoch) { }
+            __threadfence_system();
+        }
+        __syncthreads();
+        const float4* src = (const float4*) (pb.mail[pb.rank] + pb.kind_off[kind]);
+        for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) buf[i] = __ldcg(src+i);
+    }
+}
+
+} // namespace agbnp_b200_impl
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -146,6 +230,14 @@ struct agbnp_b200 {
     std::vector<GraphEntry> graphs;
     long long launch_gen = 0, graph_clock = 0;
     bool use_graph = true;
+    // peer-memory exchange
+    PeerBox peer{};
+    unsigned char* d_mailbox = nullptr;
+    size_t mailbox_bytes = 0;
+    int* d_peer_counter = nullptr;
+    int peer_epoch[PEER_KINDS] = {};
+    bool peer_ready = false;
+    std::vector<void*> peer_opened;
 
     ~agbnp_b200() {
         if (h_posq) cudaFreeHost(h_posq);
@@ -154,6 +246,9 @@ struct agbnp_b200 {
         if (have_events) { for (auto& e : ev) cudaEventDestroy(e); for (auto& e : async_ev) cudaEventDestroy(e); }
         for (auto& e : prof_pool) cudaEventDestroy(e);
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+        for (void* p : peer_opened) cudaIpcCloseMemHandle(p);
+        if (d_mailbox) cudaFree(d_mailbox);
+        if (d_peer_counter) cudaFree(d_peer_counter);
         if (h_async) cudaFreeHost(h_async);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -1181,5 +1276,98 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
 }
 
 long long agbnp_b200_launch_count(const agbnp_b200* h) { return h ? h->launches : -1; }
+
+namespace {
+// bytes of every exchange buffer; they depend only on the padded atom count, which is fixed at creation
+void peer_layout(agbnp_b200* h) {
+    const int nh = (int) std::count(h->sp.ishydrogen.begin(), h->sp.ishydrogen.end(), 0);
+    const size_t np = (size_t) ((nh+TILE-1)/TILE*TILE + (h->n-nh+TILE-1)/TILE*TILE);
+    size_t bytes[PEER_KINDS];
+    bytes[AGBNP_B200_BUF_SELFVOL] = sizeof(float4)*2*np; bytes[AGBNP_B200_BUF_YQ] = sizeof(float4)*np;
+    bytes[AGBNP_B200_BUF_FORCE] = sizeof(float4)*np; bytes[AGBNP_B200_BUF_ENERGY] = sizeof(double)*SC_COUNT;
+    bytes[AGBNP_B200_BUF_WU] = sizeof(float4)*np; bytes[AGBNP_B200_BUF_BSUM] = (sizeof(float)*np + 15)/16*16;
+    bytes[PEER_KIND_POSITIONS] = sizeof(float4)*(size_t) h->n;
+    size_t o = 0;
+    for (int k = 0; k < PEER_KINDS; k++) { h->peer.kind_off[k] = o; h->peer.kind_bytes[k] = bytes[k]; o += (bytes[k]*h->cfg.shard_count + 255)/256*256; }
+    h->peer.flag_off = o;
+    h->mailbox_bytes = o + sizeof(int)*PEER_KINDS*PEER_MAX;
+}
+}
+
+int agbnp_b200_peer_export(agbnp_b200* h, void* ipc_handle) {
+    if (!h || !ipc_handle) return AGBNP_B200_ERR_ARG;
+    if (h->cfg.shard_count > PEER_MAX) { h->err = "agbnp_b200_peer_export: at most 8 shards"; return AGBNP_B200_ERR_ARG; }
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        if (!h->d_mailbox) {
+            peer_layout(h);
+            CK(cudaMalloc((void**) &h->d_mailbox, h->mailbox_bytes));
+            CK(cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
+            CK(cudaMalloc((void**) &h->d_peer_counter, sizeof(int)));
+            CK(cudaMemset(h->d_peer_counter, 0, sizeof(int)));
+            CK(cudaDeviceSynchronize());
+        }
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, h->d_mailbox));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        std::memcpy(ipc_handle, &hd, 64);
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_peer_import(agbnp_b200* h, const void* ipc_handles, int shard_count) {
+    if (!h || !ipc_handles || shard_count != h->cfg.shard_count || !h->d_mailbox) return AGBNP_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        h->peer.rank = h->cfg.shard_rank; h->peer.count = shard_count; h->peer.counter = h->d_peer_counter;
+        for (int p = 0; p < shard_count; p++) {
+            if (p == h->cfg.shard_rank) { h->peer.mail[p] = h->d_mailbox; continue; }
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, (const unsigned char*) ipc_handles + 64*(size_t) p, 64);
+            void* ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->peer.mail[p] = (unsigned char*) ptr;
+            h->peer_opened.push_back(ptr);
+        }
+        h->peer_ready = true;
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_peer_broadcast(agbnp_b200* h, void* d_posq, int owner, void* stream) {
+    if (!h || !d_posq || owner < 0 || owner >= h->cfg.shard_count) return AGBNP_B200_ERR_ARG;
+    if (!h->peer_ready) { h->err = "agbnp_b200_peer_broadcast: peer_export / peer_import first"; return AGBNP_B200_ERR_ARG; }
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        const int epoch = ++h->peer_epoch[PEER_KIND_POSITIONS];
+        k_peer_broadcast<<<(int) std::min<size_t>(64, ((size_t) h->n+255)/256), 256, 0, (cudaStream_t) stream>>>((float4*) d_posq, (size_t) h->n, h->peer, owner, epoch);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_peer_exchange(agbnp_b200* h, int which, void* stream) {
+    if (!h || which < 0 || which >= PEER_KIND_POSITIONS) return AGBNP_B200_ERR_ARG;
+    if (!h->peer_ready) { h->err = "agbnp_b200_peer_exchange: peer_export / peer_import first"; return AGBNP_B200_ERR_ARG; }
+    void* ptr = nullptr; size_t bytes = 0;
+    const int rc = agbnp_b200_shard_buffer(h, which, &ptr, &bytes);
+    if (rc != AGBNP_B200_OK) return rc;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        cudaStream_t s = (cudaStream_t) stream;
+        const int epoch = ++h->peer_epoch[which];
+        if (which == AGBNP_B200_BUF_ENERGY) {
+            k_peer_allreduce<double><<<1, 256, 0, s>>>((double*) ptr, bytes/sizeof(double), h->peer, which, epoch);
+        } else {
+            const size_t nvec = bytes/sizeof(float4);       // np is a multiple of 32: every buffer is whole float4s
+            const int grid = (int) std::min<size_t>(64, (nvec+255)/256);
+            k_peer_allreduce<float4><<<grid, 256, 0, s>>>((float4*) ptr, nvec, h->peer, which, epoch);
+        }
+        h->launches += 1;
+        CK(cudaGetLastError());
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
 
 } // extern "C"

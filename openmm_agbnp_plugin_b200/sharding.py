@@ -45,6 +45,7 @@ class CudaShardKernel:
         self.kernel.initialize(None, force)
         self.device = device
         self._buffers = {}
+        self.peer = False
 
     @property
     def handle(self):
@@ -68,6 +69,33 @@ class CudaShardKernel:
             self._buffers[name] = torch.as_tensor(_DevPtr(ptr.value, nbytes.value, typestr, itemsize),
                                                   device=torch.device("cuda", self.device))
         return self._buffers[name]
+
+    def setup_peer_exchange(self, group=None):
+        """Replace the NCCL all-reduces by the library's one-shot exchange over NVLink peer memory (include/agbnp_b200.h,
+        "peer-memory exchange"): export this shard's mailbox, gather everybody's CUDA IPC handles, import them."""
+        L = _lib.lib()
+        mine = (C.c_ubyte * 64)()
+        ok = L.agbnp_b200_peer_export(self.handle, C.cast(mine, C.c_void_p)) == _lib.OK
+        world = dist.get_world_size(group)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(mine) if ok else b"", group=group)
+        if ok and all(len(g) == 64 for g in gathered):
+            blob = b"".join(gathered)
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            ok = L.agbnp_b200_peer_import(self.handle, C.cast(buf, C.c_void_p), world) == _lib.OK
+        else:
+            ok = False
+        # every shard must take the same path: fall back to NCCL together if any import failed (no peer access)
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok), group=group)
+        self.peer = all(flags)
+        return self.peer
+
+    def broadcast(self, d_posq, owner, stream):
+        self._check(_lib.lib().agbnp_b200_peer_broadcast(self.handle, C.c_void_p(d_posq.data_ptr()), owner, C.c_void_p(stream)))
+
+    def exchange(self, name, stream):
+        self._check(_lib.lib().agbnp_b200_peer_exchange(self.handle, _lib.BUF[name], C.c_void_p(stream)))
 
     def finish(self, stream, d_force, layout, padded_n, d_energy, want_energy):
         """Returns (rc, energy); rc != 0 means this shard overflowed a capacity (already grown) and the evaluation must
@@ -106,13 +134,21 @@ class ShardedEvaluator:
         """posq: float4-per-atom tensor on this rank's device (contents only matter on `position_owner` when
         broadcast_positions is set).  Returns the total energy (want_energy) or None (asynchronous)."""
         if self.world > 1 and broadcast_positions:
-            dist.broadcast(posq, src=self.position_owner, group=self.group)
+            if getattr(self.k, "peer", False):
+                self.k.broadcast(posq, self.position_owner, stream)
+            else:
+                dist.broadcast(posq, src=self.position_owner, group=self.group)
             self.collectives += 1
         for _ in range(max_attempts):
+            peer = self.world > 1 and getattr(self.k, "peer", False)
             for ph in range(N_PHASES):
                 self.k.phase(ph, posq if ph == 0 else None, stream)
                 for name in EXCHANGES[ph]:
-                    self._all_reduce(self.k.buffer(name))
+                    if peer:
+                        self.k.exchange(name, stream)       # push to the peers' mailboxes + sum, on the evaluation's stream
+                        self.collectives += 1
+                    else:
+                        self._all_reduce(self.k.buffer(name))
             rc, e = self.k.finish(stream, d_force, layout, padded_n, d_energy, want_energy)
             if not want_energy:
                 return None
