@@ -180,6 +180,14 @@ int agbnp_b200_peer_import(agbnp_b200* h, const void* ipc_handles /* [shard_coun
 int agbnp_b200_peer_exchange(agbnp_b200* h, int which /* agbnp_b200_buffer */, void* stream);
 /* positions (device float4[N], caller's order) from shard `owner` to every shard's own d_posq, same mechanism */
 int agbnp_b200_peer_broadcast(agbnp_b200* h, void* d_posq, int owner, void* stream);
+/* One whole sharded evaluation, asynchronous, in one call: position broadcast from `owner`, then the five phases with their
+ * peer-memory exchanges and the finish kernel, enqueued back to back (the exchange kernels keep their epochs in device
+ * memory, so no launch argument changes between evaluations).  Every shard must call it the same number of times.
+ * A capacity overflow suppresses the delivery on the shard that overflowed only; use the phase-by-phase entry points
+ * with agbnp_b200_shard_finish(h_energy != NULL) when the outcome must be agreed on (sharding.py does, once per context
+ * and whenever it wants the energy on the host). */
+int agbnp_b200_shard_evaluate(agbnp_b200* h, void* d_posq, int owner, void* stream, void* d_force, int force_layout,
+                              int padded_n, double* d_energy);
 
 /* library / build identification, e.g. "agbnp_b200 0.1 sm_100a" */
 const char* agbnp_b200_version(void);

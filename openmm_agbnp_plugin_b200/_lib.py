@@ -56,6 +56,7 @@ def lib():
         L.agbnp_b200_peer_import.argtypes = [vp, vp, C.c_int]
         L.agbnp_b200_peer_exchange.argtypes = [vp, C.c_int, vp]
         L.agbnp_b200_peer_broadcast.argtypes = [vp, vp, C.c_int, vp]
+        L.agbnp_b200_shard_evaluate.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp]
         _lib = L
     return _lib
 

@@ -34,7 +34,9 @@ struct PeerBox {
     size_t kind_off[PEER_KINDS];        // offset of a buffer kind's slots; slot of source s at kind_off + s*kind_bytes
     size_t kind_bytes[PEER_KINDS];
     size_t flag_off;                    // int flags[PEER_KINDS][PEER_MAX] at the end of the mailbox
-    int* counter;                       // local: CTAs of the running push that have finished
+    int* counter;                       // local: [0] CTAs of the running kernel that have pushed, [1] that have finished
+    int* epochs;                        // local: [PEER_KINDS] exchanges of each kind completed so far (device-side, so that the
+                                        // launches carry no changing argument and a whole sharded evaluation is one CUDA graph)
 };
 
 template <class T> __device__ __forceinline__ T peer_add(T a, T b) { return a+b; }
@@ -44,7 +46,8 @@ template <> __device__ __forceinline__ float4 peer_add<float4>(float4 a, float4 
 // finish raises this shard's flag at every peer; then every CTA waits for the peers' flags and adds their slices.
 // The grid never exceeds the SM count, so all CTAs are resident and the spin cannot starve the CTA that raises the flag.
 template <class T>
-__global__ void __launch_bounds__(256) k_peer_allreduce(T* buf, size_t n, PeerBox pb, int kind, int epoch) {
+__global__ void __launch_bounds__(256) k_peer_allreduce(T* buf, size_t n, PeerBox pb, int kind) {
+    const int epoch = pb.epochs[kind]+1;        // advanced by the last CTA to leave, i.e. after every CTA has read it
     for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) {
         const T v = buf[i];
         for (int p = 0; p < pb.count; p++)
@@ -73,12 +76,15 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(T* buf, size_t n, PeerBo
             if (q != pb.rank) acc = peer_add(acc, __ldcg((const T*) (base + (size_t) q*pb.kind_bytes[kind]) + i));
         buf[i] = acc;
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(pb.counter+1, 1) == (int) gridDim.x-1) { pb.counter[1] = 0; pb.epochs[kind] = epoch; }
 }
 
 // broadcast of the positions from their owner: the owner stores them into every peer's mailbox and raises its flag there;
 // the others wait for it and copy the slot into their own position buffer
-__global__ void __launch_bounds__(256) k_peer_broadcast(float4* buf, size_t n, PeerBox pb, int owner, int epoch) {
+__global__ void __launch_bounds__(256) k_peer_broadcast(float4* buf, size_t n, PeerBox pb, int owner) {
     const int kind = PEER_KIND_POSITIONS;
+    const int epoch = pb.epochs[kind]+1;
     if (pb.rank == owner) {
         for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) {
             const float4 v = buf[i];
@@ -102,6 +108,8 @@ __global__ void __launch_bounds__(256) k_peer_broadcast(float4* buf, size_t n, P
         const float4* src = (const float4*) (pb.mail[pb.rank] + pb.kind_off[kind]);
         for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) buf[i] = __ldcg(src+i);
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(pb.counter+1, 1) == (int) gridDim.x-1) { pb.counter[1] = 0; pb.epochs[kind] = epoch; }
 }
 
 } // namespace agbnp_b200_impl
@@ -226,7 +234,7 @@ struct agbnp_b200 {
     bool ahead_pending = false;
     // CUDA graphs of the whole kernel sequence, keyed by everything the launches bake in: `launch_gen` (bumped whenever
     // a buffer, capacity or launch shape changes) and the caller's pointers
-    struct GraphEntry { long long gen; const void* posq; void* sink; int layout, padded_n; double* d_energy; cudaGraphExec_t exec; int kernels; long long last_use; };
+    struct GraphEntry { long long gen; const void* posq; void* sink; int layout, padded_n; double* d_energy; bool sharded; cudaGraphExec_t exec; int kernels; long long last_use; };
     std::vector<GraphEntry> graphs;
     long long launch_gen = 0, graph_clock = 0;
     bool use_graph = true;
@@ -235,7 +243,6 @@ struct agbnp_b200 {
     unsigned char* d_mailbox = nullptr;
     size_t mailbox_bytes = 0;
     int* d_peer_counter = nullptr;
-    int peer_epoch[PEER_KINDS] = {};
     bool peer_ready = false;
     std::vector<void*> peer_opened;
 
@@ -674,12 +681,43 @@ constexpr int PH_ALL = PH_TREE|PH_BORN|PH_BORNFIN|PH_GB|PH_DERIV|PH_GAMMA|PH_FIN
 
 // one whole evaluation on stream s: a cached CUDA graph of the kernel sequence (one launch instead of eight; the capture
 // happens on the handle's own stream because the caller's may be the legacy default stream, which cannot be captured)
-void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
-    if (!h->use_graph || h->prof_mask) { enqueue(h, d_posq_in, s, PH_ALL, sink); return; }
+void peer_enqueue(agbnp_b200* h, int which, cudaStream_t s) {
+    void* ptr = nullptr; size_t bytes = 0;
+    if (agbnp_b200_shard_buffer(h, which, &ptr, &bytes) != AGBNP_B200_OK) throw CudaFail{h->err};
+    if (which == AGBNP_B200_BUF_ENERGY) {
+        k_peer_allreduce<double><<<1, 256, 0, s>>>((double*) ptr, bytes/sizeof(double), h->peer, which);
+    } else {
+        const size_t nvec = bytes/sizeof(float4);       // np is a multiple of 32: every buffer is whole float4s
+        const int grid = (int) std::min<size_t>(64, (nvec+255)/256);
+        k_peer_allreduce<float4><<<grid, 256, 0, s>>>((float4*) ptr, nvec, h->peer, which);
+    }
+    h->launches += 1;
+    CK(cudaGetLastError());
+}
+
+
+// a whole sharded evaluation: the phases with the peer-memory exchange after each
+void enqueue_sharded(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
+    enqueue(h, d_posq_in, s, PH_TREE, nullptr);            peer_enqueue(h, AGBNP_B200_BUF_SELFVOL, s);
+    enqueue(h, d_posq_in, s, PH_BORN, nullptr);            peer_enqueue(h, AGBNP_B200_BUF_BSUM, s);
+    enqueue(h, d_posq_in, s, PH_BORNFIN|PH_GB, nullptr);   peer_enqueue(h, AGBNP_B200_BUF_YQ, s);
+    enqueue(h, d_posq_in, s, PH_DERIV, nullptr);           peer_enqueue(h, AGBNP_B200_BUF_WU, s);
+    enqueue(h, d_posq_in, s, PH_GAMMA, nullptr);           peer_enqueue(h, AGBNP_B200_BUF_FORCE, s);
+    peer_enqueue(h, AGBNP_B200_BUF_ENERGY, s);
+    enqueue(h, d_posq_in, s, PH_FINISH, sink);
+}
+
+void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink, bool sharded = false) {
+    // a sharded evaluation is bounded by the waits of its exchange kernels, not by launch latency: measured on 2 and 8 B200 a
+    // graph of it is no faster than the plain launches (490 vs 466 us, 372 vs 367 us), so it is launched directly
+    if (!h->use_graph || h->prof_mask || sharded) {
+        if (sharded) enqueue_sharded(h, d_posq_in, s, sink); else enqueue(h, d_posq_in, s, PH_ALL, sink);
+        return;
+    }
     agbnp_b200::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
         if (g.gen == h->launch_gen && g.posq == d_posq_in && g.sink == sink->ptr && g.layout == sink->layout &&
-            g.padded_n == sink->padded_n && g.d_energy == sink->d_energy) { hit = &g; break; }
+            g.padded_n == sink->padded_n && g.d_energy == sink->d_energy && g.sharded == sharded) { hit = &g; break; }
     if (!hit) {
         // drop graphs of an older configuration, and the least recently used one beyond 16
         for (size_t i = 0; i < h->graphs.size(); ) {
@@ -695,10 +733,10 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
         const long long before = h->launches;
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-        try { enqueue(h, d_posq_in, h->own_stream, PH_ALL, sink); }
+        try { if (sharded) enqueue_sharded(h, d_posq_in, h->own_stream, sink); else enqueue(h, d_posq_in, h->own_stream, PH_ALL, sink); }
         catch (...) { cudaStreamEndCapture(h->own_stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
         CK(cudaStreamEndCapture(h->own_stream, &graph));
-        agbnp_b200::GraphEntry e{h->launch_gen, d_posq_in, sink->ptr, sink->layout, sink->padded_n, sink->d_energy, nullptr,
+        agbnp_b200::GraphEntry e{h->launch_gen, d_posq_in, sink->ptr, sink->layout, sink->padded_n, sink->d_energy, sharded, nullptr,
                                  (int) (h->launches-before), 0};
         h->launches = before;
         const cudaError_t ce = cudaGraphInstantiate(&e.exec, graph, 0);
@@ -1303,8 +1341,8 @@ int agbnp_b200_peer_export(agbnp_b200* h, void* ipc_handle) {
             peer_layout(h);
             CK(cudaMalloc((void**) &h->d_mailbox, h->mailbox_bytes));
             CK(cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
-            CK(cudaMalloc((void**) &h->d_peer_counter, sizeof(int)));
-            CK(cudaMemset(h->d_peer_counter, 0, sizeof(int)));
+            CK(cudaMalloc((void**) &h->d_peer_counter, sizeof(int)*(2+PEER_KINDS)));
+            CK(cudaMemset(h->d_peer_counter, 0, sizeof(int)*(2+PEER_KINDS)));
             CK(cudaDeviceSynchronize());
         }
         cudaIpcMemHandle_t hd;
@@ -1319,7 +1357,7 @@ int agbnp_b200_peer_import(agbnp_b200* h, const void* ipc_handles, int shard_cou
     if (!h || !ipc_handles || shard_count != h->cfg.shard_count || !h->d_mailbox) return AGBNP_B200_ERR_ARG;
     try {
         CK(cudaSetDevice(h->cfg.device));
-        h->peer.rank = h->cfg.shard_rank; h->peer.count = shard_count; h->peer.counter = h->d_peer_counter;
+        h->peer.rank = h->cfg.shard_rank; h->peer.count = shard_count; h->peer.counter = h->d_peer_counter; h->peer.epochs = h->d_peer_counter+2;
         for (int p = 0; p < shard_count; p++) {
             if (p == h->cfg.shard_rank) { h->peer.mail[p] = h->d_mailbox; continue; }
             cudaIpcMemHandle_t hd;
@@ -1339,8 +1377,7 @@ int agbnp_b200_peer_broadcast(agbnp_b200* h, void* d_posq, int owner, void* stre
     if (!h->peer_ready) { h->err = "agbnp_b200_peer_broadcast: peer_export / peer_import first"; return AGBNP_B200_ERR_ARG; }
     try {
         CK(cudaSetDevice(h->cfg.device));
-        const int epoch = ++h->peer_epoch[PEER_KIND_POSITIONS];
-        k_peer_broadcast<<<(int) std::min<size_t>(64, ((size_t) h->n+255)/256), 256, 0, (cudaStream_t) stream>>>((float4*) d_posq, (size_t) h->n, h->peer, owner, epoch);
+        k_peer_broadcast<<<(int) std::min<size_t>(64, ((size_t) h->n+255)/256), 256, 0, (cudaStream_t) stream>>>((float4*) d_posq, (size_t) h->n, h->peer, owner);
         h->launches += 1;
         CK(cudaGetLastError());
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
@@ -1350,22 +1387,39 @@ int agbnp_b200_peer_broadcast(agbnp_b200* h, void* d_posq, int owner, void* stre
 int agbnp_b200_peer_exchange(agbnp_b200* h, int which, void* stream) {
     if (!h || which < 0 || which >= PEER_KIND_POSITIONS) return AGBNP_B200_ERR_ARG;
     if (!h->peer_ready) { h->err = "agbnp_b200_peer_exchange: peer_export / peer_import first"; return AGBNP_B200_ERR_ARG; }
-    void* ptr = nullptr; size_t bytes = 0;
-    const int rc = agbnp_b200_shard_buffer(h, which, &ptr, &bytes);
-    if (rc != AGBNP_B200_OK) return rc;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        peer_enqueue(h, which, (cudaStream_t) stream);
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_shard_evaluate(agbnp_b200* h, void* d_posq, int owner, void* stream, void* d_force, int force_layout, int padded_n,
+                              double* d_energy) {
+    if (!h || !d_posq || owner < 0 || owner >= h->cfg.shard_count) return AGBNP_B200_ERR_ARG;
+    if (d_force && force_layout != 0 && force_layout != 1) { h->err = "agbnp_b200_shard_evaluate: bad force layout"; return AGBNP_B200_ERR_ARG; }
+    if (!h->peer_ready) { h->err = "agbnp_b200_shard_evaluate: peer_export / peer_import first"; return AGBNP_B200_ERR_ARG; }
     try {
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = (cudaStream_t) stream;
-        const int epoch = ++h->peer_epoch[which];
-        if (which == AGBNP_B200_BUF_ENERGY) {
-            k_peer_allreduce<double><<<1, 256, 0, s>>>((double*) ptr, bytes/sizeof(double), h->peer, which, epoch);
-        } else {
-            const size_t nvec = bytes/sizeof(float4);       // np is a multiple of 32: every buffer is whole float4s
-            const int grid = (int) std::min<size_t>(64, (nvec+255)/256);
-            k_peer_allreduce<float4><<<grid, 256, 0, s>>>((float4*) ptr, nvec, h->peer, which, epoch);
-        }
+        k_peer_broadcast<<<(int) std::min<size_t>(64, ((size_t) h->n+255)/256), 256, 0, s>>>((float4*) d_posq, (size_t) h->n, h->peer, owner);
         h->launches += 1;
-        CK(cudaGetLastError());
+        prepare(h, nullptr, 0, d_posq, s);                  // (re)sorting reads the broadcast positions; same evaluation count on every shard
+        ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
+        // deferred validation, as in the asynchronous single-GPU path: the status words of this evaluation follow it to
+        // pinned memory and are examined ASYNC_DEPTH-1 calls later (capacities grow ahead of need from the high-water marks)
+        const long long k = h->async_issued;
+        if (k >= agbnp_b200::ASYNC_DEPTH-1) {
+            const int rc = async_retire(h, k-(agbnp_b200::ASYNC_DEPTH-1));
+            if (rc != AGBNP_B200_OK) return rc;
+        }
+        launch_all(h, (const float4*) d_posq, s, &sink, true);
+        const int slot = (int) (k % agbnp_b200::ASYNC_DEPTH);
+        CK(cudaMemcpyAsync(h->h_async + slot*CW_COUNT, h->d_ctrl, sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(h->async_ev[slot], s));
+        h->async_pending[slot] = true;
+        h->async_issued++;
+        h->evals_since_sort++; h->total_evals++;
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }

@@ -94,6 +94,12 @@ class CudaShardKernel:
     def broadcast(self, d_posq, owner, stream):
         self._check(_lib.lib().agbnp_b200_peer_broadcast(self.handle, C.c_void_p(d_posq.data_ptr()), owner, C.c_void_p(stream)))
 
+    def evaluate_graph(self, d_posq, owner, stream, d_force, layout, padded_n, d_energy):
+        """One asynchronous sharded evaluation in one library call (agbnp_b200_shard_evaluate)."""
+        self._check(_lib.lib().agbnp_b200_shard_evaluate(self.handle, C.c_void_p(d_posq.data_ptr()), owner, C.c_void_p(stream),
+                                                        C.c_void_p(d_force.data_ptr() if d_force is not None else 0), layout, padded_n,
+                                                        C.c_void_p(d_energy.data_ptr() if d_energy is not None else 0)))
+
     def exchange(self, name, stream):
         self._check(_lib.lib().agbnp_b200_peer_exchange(self.handle, _lib.BUF[name], C.c_void_p(stream)))
 
@@ -133,6 +139,11 @@ class ShardedEvaluator:
                  broadcast_positions=True, max_attempts=8):
         """posq: float4-per-atom tensor on this rank's device (contents only matter on `position_owner` when
         broadcast_positions is set).  Returns the total energy (want_energy) or None (asynchronous)."""
+        if self.world > 1 and not want_energy and broadcast_positions and getattr(self.k, "peer", False) and hasattr(self.k, "evaluate_graph"):
+            # asynchronous evaluation over peer memory: broadcast, phases and exchanges enqueued by one library call
+            self.k.evaluate_graph(posq, self.position_owner, stream, d_force, layout, padded_n, d_energy)
+            self.collectives += 1 + sum(len(x) for x in EXCHANGES)
+            return None
         if self.world > 1 and broadcast_positions:
             if getattr(self.k, "peer", False):
                 self.k.broadcast(posq, self.position_owner, stream)
