@@ -179,7 +179,8 @@ def owned_rows(n_blocks, rank, world):
 
 
 def owned_roots(n_heavy, n_heavy_blocks, rank, world, tile=32):
-    """Sorted heavy-atom indices whose overlap subtrees a shard builds (block-cyclic deal; mirror of k_tree)."""
+    """Positions in the tree work-item list (most expensive first) that a shard processes: a block-cyclic deal in blocks of
+    32 (mirror of k_tree).  With no root split into parts the items are the heavy roots themselves."""
     out = []
     for b in range(rank, n_heavy_blocks, world):
         out.extend(range(b * tile, min((b + 1) * tile, n_heavy)))
