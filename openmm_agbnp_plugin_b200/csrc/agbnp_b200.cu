@@ -124,13 +124,16 @@ struct CudaFail { std::string msg; };
 
 template <class T> struct DevBuf {
     T* p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
+    // (re)size; an allocation that is large enough is kept: cudaFree synchronises the device and cudaMalloc of tens of MB
+    // takes a millisecond, and the periodic re-sort calls this for every order-dependent array
     void alloc(size_t count) {
+        if (count <= cap && p) { n = count; return; }
         release();
-        n = count;
+        n = cap = count;
         if (count) CK(cudaMalloc((void**) &p, count*sizeof(T)));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
     void upload(const std::vector<T>& h, cudaStream_t s) {
         if (h.size() > n) alloc(h.size());
         if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size()*sizeof(T), cudaMemcpyHostToDevice, s));
@@ -798,7 +801,7 @@ void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_pos
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tp0 = timing ? now() : 0;
     double tp1 = tp0;
-    const int interval = h->cfg.reorder_interval > 0 ? h->cfg.reorder_interval : 500;
+    const int interval = h->cfg.reorder_interval > 0 ? h->cfg.reorder_interval : 1000;
     if (!h->order_valid || h->evals_since_sort >= interval) {
         std::vector<float> tmp;
         if (!host_xyz) {
