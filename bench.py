@@ -405,7 +405,7 @@ def b200_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic" if s.get("name", "").startswith("hivrt-standin") else "example/hivrt_agbnp1.dms",
-            "config": config_dict(s, args, "1 GPU" if world == 1 else ("one evaluation sharded over %d GPUs, %s" % (world, "peer-memory exchanges over NVLink (NCCL for the position broadcast)" if getattr(sk, "peer", False) else "NCCL all-reduces") if sharded else "%d independent replicas" % world)),
+            "config": config_dict(s, args, "1 GPU" if world == 1 else ("one evaluation sharded over %d GPUs, %s" % (world, "peer-memory exchanges and position broadcast over NVLink" if getattr(sk, "peer", False) else "NCCL all-reduces") if sharded else "%d independent replicas" % world)),
             "ns_per_day": value * NS_PER_DAY_PER_EVAL_PER_S, "roofline": roofline, "path_roofline": path_roofline, "roofline_tree": roofline_tree,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "kernels_us": kernels_us, "mean_energy_kj_mol": e_mean,
             "host_wall_ms_per_step": t_wall / K * 1e3}
