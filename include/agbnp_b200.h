@@ -98,7 +98,8 @@ int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, v
  * are delivered on the stream by the last kernel of the evaluation, and only if no internal capacity overflowed (the
  * check is on the device).  The status words follow the evaluation to pinned memory and are examined a few calls later
  * and by agbnp_b200_synchronize: capacities are grown ahead of need from the high-water marks every evaluation reports
- * (so an overflow needs a >33% jump in local packing between two evaluations); if one happens anyway the call that
+ * (a capacity grows as soon as a high-water mark passes 90% of it, so an overflow needs a >11% jump in local packing
+ * between two evaluations); if one happens anyway the call that
  * notices it returns ERR_CAPACITY naming the evaluation, which must be re-issued.  With h_energy != NULL (and in
  * agbnp_b200_execute_host) the call is synchronous and re-runs an overflowed evaluation itself.
  * agbnp_b200_synchronize waits for the stream and retires every pending status. */
@@ -142,7 +143,8 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);
 
 /* ---- multi-GPU plumbing: one process per GPU; the caller runs the phases and does the collectives between
  * them on the exported device buffers (NCCL through torch.distributed in this repo's host layer, sharding.py).
- * Work split: overlap-tree roots are dealt block-cyclically (each shard builds, sweeps and stores only its subtrees);
+ * Work split: overlap-tree work items (roots, or parts of large roots) are dealt block-cyclically in most-expensive-first
+ * order (each shard builds, sweeps and stores only its subtrees);
  * the work units of the Born-radius, GB and derivative pair passes are dealt round-robin.
  *   phase 0: gather/sort, tree build + rescan + sweeps for the owned roots   -> all-reduce SELFVOL (8*np floats)
  *   phase 1: Born-radius pair sums for the owned units                        -> all-reduce BSUM    (np floats)
