@@ -291,7 +291,11 @@ void alloc_tree_scratch(agbnp_b200* h) {
     h->d_tree_stage.alloc(nwarps*tree_stage_bytes(h->tree_cap));
     if (h->tree_work_global) h->d_tree_work.alloc(nwarps*per_warp); else h->d_tree_work.release();
     const size_t smem = h->tree_work_global ? 0 : h->tree_warps*per_warp;
-    CK(cudaFuncSetAttribute(k_tree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
+    // the attribute belongs to the function, not to the handle: several handles in one process (replicas, shards on one
+    // device) may need different amounts, so it only ever grows
+    static size_t tree_smem_max[64] = {};
+    size_t& tmax = tree_smem_max[h->cfg.device & 63];
+    if (smem > tmax) { tmax = smem; CK(cudaFuncSetAttribute(k_tree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024))); }
     // k_tree_gamma: per-warp gamma_1..n and children sums, in shared memory while they fit
     {
         const size_t pw = gamma_work_bytes(h->tree_cap);
@@ -301,8 +305,10 @@ void alloc_tree_scratch(agbnp_b200* h) {
         if (h->gamma_work_global) gctas = 4;
         h->gamma_grid = h->num_sm*(int) gctas;
         if (h->gamma_work_global) h->d_gamma_scratch.alloc((size_t) h->gamma_grid*h->gamma_warps*pw); else h->d_gamma_scratch.release();
-        CK(cudaFuncSetAttribute(k_tree_gamma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) std::max<size_t>(h->gamma_work_global ? 0 : h->gamma_warps*pw, 1024)));
+        static size_t gamma_smem_max[64] = {};
+        size_t& gmax = gamma_smem_max[h->cfg.device & 63];
+        const size_t gs = h->gamma_work_global ? 0 : h->gamma_warps*pw;
+        if (gs > gmax) { gmax = gs; CK(cudaFuncSetAttribute(k_tree_gamma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(gs, 1024))); }
     }
 }
 

@@ -311,3 +311,25 @@ def test_verlet_energy_conservation():
     assert ke > 300.0                                             # the system really moved
     assert np.abs(tot-tot[0]).max() <= 2e-4*ke + 2e-6*abs(pe0)   # measured: 2e-5 of the kinetic energy
     sim.close()
+
+
+def test_two_contexts_with_different_capacities():
+    """Handles are independent (replica mode): one context growing its tree capacities (a dense cluster needs
+    far more shared memory / scratch per warp) must not disturb another context of the same process."""
+    s = load_system("trpcage")
+    pos = systems.float_rounded(s["pos"])
+    ctx_a, e_a, f_a = _gpu(s, pos, 1)
+    n = 120
+    cpos = systems.float_rounded(_spaced_cloud(n, 1.05, 0.12, 5))
+    c = dict(radius=np.full(n, 0.17), gamma=np.full(n, 48.9528), alpha=np.full(n, -0.2), charge=np.zeros(n),
+             ishydrogen=np.zeros(n, dtype=np.int32), pos=cpos)
+    ctx_b, e_b, f_b = _gpu(c, cpos, 0)
+    o = portlib.OracleKernel(0, *sys_args(c))
+    e_ref, _ = o.execute(cpos)
+    assert abs(e_b - e_ref) <= E_TOL * abs(e_ref)
+    ctx_a.setPositions(pos)
+    e_a2 = ctx_a.calcForcesAndEnergy()
+    assert abs(e_a2 - e_a) <= 1e-6 * abs(e_a)
+    assert relrms(ctx_a.getForces(), f_a) <= 1e-5
+    ctx_b.setPositions(cpos)
+    assert abs(ctx_b.calcForcesAndEnergy() - e_b) <= 1e-6 * abs(e_b)
