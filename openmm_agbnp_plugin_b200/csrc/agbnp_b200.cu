@@ -241,6 +241,7 @@ struct agbnp_b200 {
     std::vector<GraphEntry> graphs;
     long long launch_gen = 0, graph_clock = 0;
     bool use_graph = true;
+    bool use_pdl = true;             // programmatic dependent launch between the kernels of an evaluation (AGBNP_B200_NO_PDL=1: off)
     // peer-memory exchange
     PeerBox peer{};
     unsigned char* d_mailbox = nullptr;
@@ -552,6 +553,19 @@ cudaEvent_t prof_take(agbnp_b200* h) {
     return h->prof_pool[h->prof_used++];
 }
 
+// one kernel of an evaluation.  With programmatic dependent launch the kernel may be scheduled while its predecessor in the
+// stream is still draining; it blocks in pdl_acquire() until that grid has completed (agbnp_device.cuh).
+template <typename Args>
+void launch(agbnp_b200* h, void (*kern)(Args), int grid, int block, size_t smem, cudaStream_t s, const Args& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) grid); cfg.blockDim = dim3((unsigned) block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->use_pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, a));
+}
+
 // enqueue one evaluation (phase_mask: Phase bits).
 // Nothing here synchronises; k_finish delivers to the caller's sink only if no capacity overflowed (device-side check).
 void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_mask, const ForceSink* sink) {
@@ -574,11 +588,11 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p,
                     (float4*) h->d_slab.p, (int) (h->slab_bytes/sizeof(float4))};
         begin(K_PREP);
-        k_prep<<<(h->nb+7)/8, 256, 0, s>>>(pa);
+        launch(h, k_prep, (h->nb+7)/8, 256, 0, s, pa);
         end(K_PREP);
         BlockListArgs bl{h->nhb, h->d_bbc.p, h->d_bbh.p, h->rc2_global, h->d_bcount.p, h->d_blist.p};
         begin(K_BLIST);
-        k_blocklist<<<(h->nhb+7)/8, 256, 0, s>>>(bl);
+        launch(h, k_blocklist, (h->nhb+7)/8, 256, 0, s, bl);
         end(K_BLIST);
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
@@ -603,8 +617,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ta.hw_nbr = h->d_ctrl+CW_MAX_NBR; ta.hw_nodes = h->d_ctrl+CW_MAX_NODES; ta.hw_width = h->d_ctrl+CW_MAX_WIDTH;
         const size_t smem = h->tree_work_global ? 0 : h->tree_warps*ta.wk_stride;
         begin(K_TREE);
-        if (h->tree_work_global) k_tree<false><<<h->tree_grid, 32*h->tree_warps, 0, s>>>(ta);
-        else k_tree<true><<<h->tree_grid, 32*h->tree_warps, smem, s>>>(ta);
+        if (h->tree_work_global) launch(h, k_tree<false>, h->tree_grid, 32*h->tree_warps, 0, s, ta);
+        else launch(h, k_tree<true>, h->tree_grid, 32*h->tree_warps, smem, s, ta);
         end(K_TREE);
     }
     const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
@@ -616,8 +630,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
         const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
         begin(K_BORN);
-        if (pc.tab_smem) { if (cutoff) k_born<true, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); else k_born<false, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); }
-        else { if (cutoff) k_born<true, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); else k_born<false, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(ba); }
+        if (pc.tab_smem) { if (cutoff) launch(h, k_born<true, true>, h->pq_grid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, true>, h->pq_grid, PQ_THREADS, sm, s, ba); }
+        else { if (cutoff) launch(h, k_born<true, false>, h->pq_grid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, false>, h->pq_grid, PQ_THREADS, sm, s, ba); }
         end(K_BORN);
     }
     if (v1 && (phase_mask & PH_BORNFIN)) {
@@ -628,7 +642,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         bf.kdiel = (float) h->k.dielectric_factor; bf.hb_radius = (float) h->k.hb_radius;
         bf.scalars = h->d_scalars; bf.own_begin = pc.row_begin*TILE; bf.own_end = pc.row_end*TILE;
         begin(K_BORNFIN);
-        k_born_finish<<<(h->np+255)/256, 256, 0, s>>>(bf);
+        launch(h, k_born_finish, (h->np+255)/256, 256, 0, s, bf);
         end(K_BORNFIN);
     }
     if (v1 && (phase_mask & PH_GB)) {
@@ -638,8 +652,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ga.gbacc = h->d_gbacc; ga.scalars = h->d_scalars; ga.counters = h->d_counters; ga.kdiel = h->k.dielectric_factor; ga.bmax = h->d_bmax.p;
         ga.work_counter = h->d_ctrl+CW_WORK_GB;
         begin(K_GB);
-        if (cutoff) k_gb<true><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
-        else k_gb<false><<<h->gb_grid, GB_THREADS, 0, s>>>(ga);
+        if (cutoff) launch(h, k_gb<true>, h->gb_grid, GB_THREADS, 0, s, ga);
+        else launch(h, k_gb<false>, h->gb_grid, GB_THREADS, 0, s, ga);
         end(K_GB);
     }
     if (v1 && (phase_mask & PH_DERIV)) {
@@ -651,8 +665,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
         const size_t sm = 2*tab_bytes + PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float));
         begin(K_DERIV);
-        if (pc.tab_smem) { if (cutoff) k_deriv<true, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); else k_deriv<false, true><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); }
-        else { if (cutoff) k_deriv<true, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); else k_deriv<false, false><<<h->pq_grid, PQ_THREADS, sm, s>>>(da); }
+        if (pc.tab_smem) { if (cutoff) launch(h, k_deriv<true, true>, h->pq_grid, PQ_THREADS, sm, s, da); else launch(h, k_deriv<false, true>, h->pq_grid, PQ_THREADS, sm, s, da); }
+        else { if (cutoff) launch(h, k_deriv<true, false>, h->pq_grid, PQ_THREADS, sm, s, da); else launch(h, k_deriv<false, false>, h->pq_grid, PQ_THREADS, sm, s, da); }
         end(K_DERIV);
     }
     if (v1 && (phase_mask & PH_GAMMA)) {
@@ -662,8 +676,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         gm.scratch = h->gamma_work_global ? h->d_gamma_scratch.p : nullptr;
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
         begin(K_GAMMA);
-        if (h->gamma_work_global) k_tree_gamma<false><<<h->gamma_grid, 32*h->gamma_warps, 0, s>>>(gm);
-        else k_tree_gamma<true><<<h->gamma_grid, 32*h->gamma_warps, h->gamma_warps*gm.scratch_stride, s>>>(gm);
+        if (h->gamma_work_global) launch(h, k_tree_gamma<false>, h->gamma_grid, 32*h->gamma_warps, 0, s, gm);
+        else launch(h, k_tree_gamma<true>, h->gamma_grid, 32*h->gamma_warps, h->gamma_warps*gm.scratch_stride, s, gm);
         end(K_GAMMA);
     }
     if (phase_mask & PH_FINISH) {
@@ -680,7 +694,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         }
         fa.energy_accum = sink ? sink->d_energy : nullptr;
         begin(K_FINISH);
-        k_finish<<<(h->np+255)/256, 256, 0, s>>>(fa);
+        launch(h, k_finish, (h->np+255)/256, 256, 0, s, fa);
         end(K_FINISH);
     }
     CK(cudaGetLastError());
@@ -942,6 +956,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         h->num_sm = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         { const char* ng = std::getenv("AGBNP_B200_NO_GRAPH"); h->use_graph = !(ng && ng[0] == '1'); }
+        { const char* ng = std::getenv("AGBNP_B200_NO_PDL"); h->use_pdl = !(ng && ng[0] == '1'); }
         for (auto& e2 : h->ev) CK(cudaEventCreate(&e2));
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->have_events = true;
@@ -1006,13 +1021,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = timing ? now() : 0;
         if (async_drain(h) != AGBNP_B200_OK) return AGBNP_B200_ERR_CAPACITY;
-        {
-            float* __restrict__ hp = (float*) h->h_posq;
-            const double* __restrict__ p = pos;
-            for (int i = 0; i < h->n; i++) {
-                hp[4*i] = (float) p[3*i]; hp[4*i+1] = (float) p[3*i+1]; hp[4*i+2] = (float) p[3*i+2]; hp[4*i+3] = 0.f;
-            }
-        }
+        pack_positions(pos, (float*) h->h_posq, h->n);
         CK(cudaMemcpyAsync(h->d_posq_in.p, h->h_posq, sizeof(float4)*h->n, cudaMemcpyHostToDevice, s));
         const double t1 = timing ? now() : 0;
         prepare(h, (const float*) h->h_posq, 4, nullptr, s);
@@ -1034,12 +1043,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         h->evals_since_sort++; h->total_evals++;
         grow_ahead(h, h->h_ctrl);
         const double t4 = timing ? now() : 0;
-        if (include_forces && forces) {
-            const float* __restrict__ hf = h->h_force;
-            double* __restrict__ f = forces;
-            const int n3 = 3*h->n;
-            for (int i = 0; i < n3; i++) f[i] += (double) hf[i];
-        }
+        if (include_forces && forces) add_forces(h->h_force, forces, 3*h->n);
         if (energy) *energy = include_energy ? h->h_scal[SC_SPARE0] : 0.0;
         if (timing) {
             const double t5 = now();

@@ -26,6 +26,14 @@ enum ScalarSlot { SC_EVOL_L = 0, SC_EVOL_S = 1, SC_EGB = 2, SC_EVDW = 3, SC_VOL_
 // work counters (unsigned long long)
 enum CounterSlot { CT_PGB = 0, CT_PQ = 1, CT_C2 = 2, CT_C3 = 3, CT_M = 4, CT_TILES_GB = 5, CT_TILES_Q = 6, CT_SPARE = 7, CT_COUNT = 8 };
 
+// Programmatic dependent launch (sm_90+): every kernel of an evaluation lets its successor be scheduled at once
+// (pdl_release, first instruction) and itself waits for its predecessor -- completion AND memory visibility of the whole
+// grid -- before it touches anything an earlier kernel reads or writes (pdl_acquire).  Launch latency and prologues that
+// read only per-context constants (spline tables) hide behind the predecessor's tail.  Without the launch attribute both
+// are no-ops.  Every CTA executes pdl_acquire, so completion stays transitive along the kernel chain.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_acquire() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 

@@ -40,6 +40,8 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
+    pdl_release();
+    pdl_acquire();                  // the previous evaluation's k_finish still reads the slab this kernel zeroes
     const int lane = threadIdx.x & 31;
     const int gid = blockIdx.x*blockDim.x + threadIdx.x;
     for (int i = gid; i < A.slab_vec; i += gridDim.x*blockDim.x) A.slab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -212,7 +214,9 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
     float4* s_tabv = (float4*) smem_raw;                                // [ntables*15]
     BornSmem* sm = (BornSmem*) (s_tabv + ntab);                         // [PQ_WARPS][2]: row block, column block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < ntab; i += blockDim.x) s_tabv[i] = A.c.i4v[i];
+    pdl_release();
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) s_tabv[i] = A.c.i4v[i];      // per-context constants: before the wait
+    pdl_acquire();
     __syncthreads();
     const float4* tabv;
     if (TAB_SMEM) tabv = s_tabv; else tabv = A.c.i4v;
@@ -287,6 +291,8 @@ struct BornFinishArgs {
 };
 
 __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
+    pdl_release();
+    pdl_acquire();
     const int a = blockIdx.x*blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     float evdw = 0.f, eself = 0.f, br_real = 0.f;
@@ -479,6 +485,8 @@ __device__ __forceinline__ void gb_tile(const GBArgs& A, const GBStage& st, int 
 template <bool CUTOFF>
 __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
     __shared__ GBStage s_stage[GB_THREADS/32][2];
+    pdl_release();
+    pdl_acquire();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int li = lane >> 3, lj = lane & 7;
     GBStage* stage = s_stage[warp];
@@ -685,7 +693,9 @@ __global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
     DerivSmem* sm = (DerivSmem*) (s_tabd + ntab);                       // [PQ_WARPS][2]
     float* wmat = (float*) (sm + 2*PQ_WARPS) + (threadIdx.x >> 5)*WMAT_STRIDE*TILE;   // [PQ_WARPS][32*33] pair force weights
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < ntab; i += blockDim.x) { s_tabv[i] = A.c.i4v[i]; s_tabd[i] = A.c.i4d[i]; }
+    pdl_release();
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) { s_tabv[i] = A.c.i4v[i]; s_tabd[i] = A.c.i4d[i]; }   // constants: before the wait
+    pdl_acquire();
     __syncthreads();
     const float4 *tabv, *tabd;
     if (TAB_SMEM) { tabv = s_tabv; tabd = s_tabd; } else { tabv = A.c.i4v; tabd = A.c.i4d; }
@@ -760,6 +770,8 @@ struct FinishArgs {
 };
 
 __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
+    pdl_release();
+    pdl_acquire();
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
     if (A.status && *A.status != 0) return;
     if (k == 0) {

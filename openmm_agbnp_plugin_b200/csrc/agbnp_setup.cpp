@@ -282,4 +282,29 @@ void morton_order(const float* xyz, int stride, const std::vector<int>& ishydrog
     for (auto& p : hy) hydrogen_sorted.push_back(p.second);
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <emmintrin.h>
+#define AGBNP_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define AGBNP_CLONES
+#endif
+
+void pack_positions(const double* pos, float* posq, int n) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    for (int i = 0; i < n; i++) {
+        const __m128 xy = _mm_cvtpd_ps(_mm_loadu_pd(pos + 3*(size_t) i));         // x, y, 0, 0
+        const __m128 z = _mm_cvtpd_ps(_mm_load_sd(pos + 3*(size_t) i + 2));         // z, 0, 0, 0
+        _mm_storeu_ps(posq + 4*(size_t) i, _mm_movelh_ps(xy, z));                  // x, y, z, 0
+    }
+#else
+    for (int i = 0; i < n; i++) {
+        posq[4*i] = (float) pos[3*i]; posq[4*i+1] = (float) pos[3*i+1]; posq[4*i+2] = (float) pos[3*i+2]; posq[4*i+3] = 0.f;
+    }
+#endif
+}
+
+AGBNP_CLONES void add_forces(const float* __restrict__ src, double* __restrict__ dst, int n3) {
+    for (int i = 0; i < n3; i++) dst[i] += (double) src[i];
+}
+
 } // namespace agbnp_b200_impl

@@ -70,5 +70,10 @@ struct SystemParams {
 void morton_order(const float* xyz /*stride 4 or 3*/, int stride, const std::vector<int>& ishydrogen,
                   std::vector<int>& heavy_sorted, std::vector<int>& hydrogen_sorted);
 
+// host-buffer marshalling of agbnp_b200_execute_host (compiled by the host compiler alone so that it can carry an AVX2
+// clone next to the baseline one; chosen at load time)
+void pack_positions(const double* pos /*[3n]*/, float* posq /*[4n], w = 0*/, int n);
+void add_forces(const float* src, double* dst /* += */, int n3);
+
 } // namespace agbnp_b200_impl
 #endif

@@ -71,6 +71,8 @@ struct BlockListArgs {
 };
 
 __global__ void __launch_bounds__(256) k_blocklist(BlockListArgs A) {
+    pdl_release();
+    pdl_acquire();
     const int lane = threadIdx.x & 31;
     const int rb = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     if (rb >= A.nhb) return;
@@ -283,6 +285,8 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
 template <bool SMEM_WORK>
 __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CTAS : 2) k_tree(TreeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_release();
+    pdl_acquire();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int nbrmax = A.nbrmax, cap = A.cap, wcap = A.wcap;
     const int gwarp = blockIdx.x*nwarp + warp;
@@ -334,25 +338,34 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                 hit = point_box_dist2(pr.x, pr.y, pr.z, A.bbc[b], A.bbh[b]) < rcmax;
             }
             unsigned m = __ballot_sync(FULL, hit);
-            while (m) {
-                const int bb = __shfl_sync(FULL, b, __ffs(m)-1);
+            while (m) {                                           // two listed blocks per trip: their loads overlap
+                const int i0 = __ffs(m)-1;
                 m &= m-1;
-                const int j = bb*TILE+lane;
-                const float4 pj = A.posq[j];
-                const int ob = A.origbin[j];
-                const int oj = ob < 0 ? -1 : (ob & 0xffffff);
-                const float dx = pj.x-pr.x, dy = pj.y-pr.y, dz = pj.z-pr.z;
-                const float d2 = dx*dx + dy*dy + dz*dz;
-                const bool ok = (oj > orig_r) && (d2 < __ldg(A.rc2 + rb*A.nbins + ((ob >> 24) & 0x7f)));
-                const unsigned am = __ballot_sync(FULL, ok);
-                if (ok) {
-                    const int p = nn + __popc(am & lanemask_lt());
-                    if (p < nbrmax) {
-                        W.nbi[p] = j; W.nbx[p] = pj.x; W.nby[p] = pj.y; W.nbz[p] = pj.z;
-                        W.nba[p] = (float) A.aL[j]; W.nbv[p] = (float) A.vL[j];
-                    }
+                const bool two = m != 0;
+                const int i1 = two ? __ffs(m)-1 : i0;
+                m &= m-1;
+                const int j0 = __shfl_sync(FULL, b, i0)*TILE+lane, j1 = __shfl_sync(FULL, b, i1)*TILE+lane;
+                const float4 p0 = A.posq[j0], p1 = A.posq[j1];
+                const int ob0 = A.origbin[j0], ob1 = A.origbin[j1];
+                const float dx0 = p0.x-pr.x, dy0 = p0.y-pr.y, dz0 = p0.z-pr.z;
+                const float dx1 = p1.x-pr.x, dy1 = p1.y-pr.y, dz1 = p1.z-pr.z;
+                const float d20 = dx0*dx0 + dy0*dy0 + dz0*dz0, d21 = dx1*dx1 + dy1*dy1 + dz1*dz1;
+                const bool ok0 = ((ob0 < 0 ? -1 : (ob0 & 0xffffff)) > orig_r) && (d20 < __ldg(A.rc2 + rb*A.nbins + ((ob0 >> 24) & 0x7f)));
+                const bool ok1 = two && ((ob1 < 0 ? -1 : (ob1 & 0xffffff)) > orig_r) && (d21 < __ldg(A.rc2 + rb*A.nbins + ((ob1 >> 24) & 0x7f)));
+                const unsigned am0 = __ballot_sync(FULL, ok0), am1 = __ballot_sync(FULL, ok1);
+                float a0 = 0.f, v0 = 0.f, a1 = 0.f, v1 = 0.f;
+                if (ok0) { a0 = (float) A.aL[j0]; v0 = (float) A.vL[j0]; }
+                if (ok1) { a1 = (float) A.aL[j1]; v1 = (float) A.vL[j1]; }
+                if (ok0) {
+                    const int p = nn + __popc(am0 & lanemask_lt());
+                    if (p < nbrmax) { W.nbi[p] = j0; W.nbx[p] = p0.x; W.nby[p] = p0.y; W.nbz[p] = p0.z; W.nba[p] = a0; W.nbv[p] = v0; }
                 }
-                nn += __popc(am);
+                nn += __popc(am0);
+                if (ok1) {
+                    const int p = nn + __popc(am1 & lanemask_lt());
+                    if (p < nbrmax) { W.nbi[p] = j1; W.nbx[p] = p1.x; W.nby[p] = p1.y; W.nbz[p] = p1.z; W.nba[p] = a1; W.nbv[p] = v1; }
+                }
+                nn += __popc(am1);
             }
         }
         hw_nn = max(hw_nn, nn);
@@ -662,17 +675,20 @@ struct GammaArgs {
     int* work_counter;
 };
 
-__host__ __device__ inline size_t gamma_work_bytes(int cap) { return (size_t) cap*(sizeof(float) + sizeof(float4)); }
+__host__ __device__ inline size_t gamma_work_bytes(int cap) { return ((size_t) cap*(sizeof(float) + sizeof(float4) + sizeof(short)) + 15) & ~(size_t) 15; }
 
 template <bool SMEM_WORK>
 __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_release();
+    pdl_acquire();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     unsigned char* wk;
     if (SMEM_WORK) wk = smem_raw + (size_t) warp*gamma_work_bytes(A.cap);
     else wk = A.scratch + (size_t) (blockIdx.x*nwarp+warp)*A.scratch_stride;
     float4* hu = (float4*) wk;                      // [cap] children sums (F', P'x, P'y, P'z) per parent slot
     float* gam = (float*) (hu + A.cap);             // [cap] gamma_1..n per slot
+    short* par = (short*) (gam + A.cap);            // [cap] parent slot
     for (;;) {
         int r = 0;
         if (lane == 0) r = atomicAdd(A.work_counter, 1);
@@ -684,15 +700,30 @@ __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
         const short* lvs = A.st.root_lvs + r*MAX_LEVELS;
         int nlev = 1;
         while (nlev+1 < MAX_LEVELS && lvs[nlev+1] < cnt) nlev++;
-        // top-down gamma1i (gaussvol.cpp:338-343)
-        for (int lev = 1; lev <= nlev; lev++) {
-            const int b = lvs[lev], e = lev == nlev ? cnt : lvs[lev+1];
-            for (int sl = b+lane; sl < e; sl += 32) {
-                const int ja = __float_as_int(rec[2*sl].w);
-                const int p = __float_as_int(rec[2*sl+1].w) & 0xffff;
-                const float nu = A.dacc[ja].w*A.inv_vS[ja];
-                gam[sl] = (p != 0xffff ? gam[p] : 0.f) + nu;
+        // nu of every slot's last atom first: the gathers rec -> atom -> (W+U, 1/V) of all slots are independent of each
+        // other, so four of them per lane are in flight at once instead of one dependent chain per level
+        for (int s0 = 0; s0 < cnt; s0 += 128) {
+            int ja[4], pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int sl = min(s0 + 32*q + lane, cnt-1);
+                ja[q] = __float_as_int(__ldg(&rec[2*sl].w));
+                pk[q] = __float_as_int(__ldg(&rec[2*sl+1].w));
             }
+            float nu[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) nu[q] = __ldg(&A.dacc[ja[q]].w)*__ldg(&A.inv_vS[ja[q]]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int sl = s0 + 32*q + lane;
+                if (sl < cnt) { gam[sl] = nu[q]; par[sl] = (short) (pk[q] & 0xffff); }
+            }
+        }
+        __syncwarp();
+        // top-down gamma1i (gaussvol.cpp:338-343): shared memory only
+        for (int lev = 2; lev <= nlev; lev++) {
+            const int b = lvs[lev], e = lev == nlev ? cnt : lvs[lev+1];
+            for (int sl = b+lane; sl < e; sl += 32) gam[sl] += gam[par[sl]];
             __syncwarp();
         }
         // bottom-up energy-gradient sweep; children sums by segmented warp scans (see tree_sweep)

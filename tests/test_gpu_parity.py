@@ -125,7 +125,8 @@ def test_hivrt_size_properties():
     assert fsum < 1e-3 * np.abs(f).max() * np.sqrt(len(pos))
     ctx.setPositions(pos)
     e_again = ctx.calcForcesAndEnergy()
-    assert abs(e_again - e) <= 1e-7 * abs(e)
+    # float red.global accumulation order varies from run to run: measured spread 1.2e-7 relative
+    assert abs(e_again - e) <= 5e-7 * abs(e)
     shifted = systems.float_rounded(pos + np.array([0.25, -0.5, 0.125]))      # exactly representable shifts
     ctx.setPositions(shifted)
     e_shift = ctx.calcForcesAndEnergy()
