@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libagbnp_b200.so")
+# AGBNP_B200_LIB: another build of the same library (tuning experiments: tools/build_variant.sh); never a fallback
+LIB_PATH = os.environ.get("AGBNP_B200_LIB") or os.path.join(_HERE, "lib", "libagbnp_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "agbnp_b200.h")
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_PARAM_CHANGE = 0, -1, -2, -3, -4

@@ -163,7 +163,8 @@ struct agbnp_b200 {
     std::vector<float> box_lo, box_hi;      // block bounding boxes at sort time (host; unit ordering only)
 
     // static sorted arrays
-    DevBuf<int> d_orig, d_origbin;
+    DevBuf<int> d_orig;
+    DevBuf<int4> d_l2rec;
     DevBuf<float> d_charge, d_radius, d_alpha, d_gamma;
     DevBuf<double> d_aL, d_vL, d_aS, d_vS;
     DevBuf<unsigned char> d_rcbin, d_ts;
@@ -450,9 +451,15 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     }
     h->d_orig.upload(h->orig, s);
     {
-        std::vector<int> ob(np, -1);
-        for (int k = 0; k < np; k++) if (h->orig[k] >= 0) ob[k] = h->orig[k] | ((int) rcbin[k] << 24);
-        h->d_origbin.upload(ob, s);
+        std::vector<int4> ob(np, make_int4(-1, 0, 0, 0));
+        for (int k = 0; k < np; k++) {
+            if (h->orig[k] < 0) continue;
+            const float af = (float) aL[k], vf = (float) vL[k];
+            int ai, vi;
+            std::memcpy(&ai, &af, 4); std::memcpy(&vi, &vf, 4);
+            ob[k] = make_int4(h->orig[k] | ((int) rcbin[k] << 24), ai, vi, 0);
+        }
+        h->d_l2rec.upload(ob, s);
     }
     h->d_charge.upload(charge, s); h->d_radius.upload(radius, s); h->d_alpha.upload(alpha, s); h->d_gamma.upload(gamma, s);
     h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s); h->d_inv_vS.upload(inv_vS, s);
@@ -597,7 +604,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
         ta.items = h->d_items.p; ta.nitems = (int) h->items.size(); ta.bcount = h->d_bcount.p; ta.blist = h->d_blist.p;
-        ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.origbin = h->d_origbin.p; ta.rcbin = h->d_rcbin.p;
+        ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.l2rec = h->d_l2rec.p; ta.rcbin = h->d_rcbin.p;
         ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;
         ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
         ta.volmina = h->k.volmina; ta.volminb = h->k.volminb; ta.min_gvol = h->k.min_gvol;
@@ -663,10 +670,24 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
                          h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count};
         da.vsf = h->d_vsf.p; da.gbacc = h->d_gbacc; da.born = h->d_born.p; da.bfp = h->d_bfp.p; da.brw = h->d_brw.p;
         da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
-        const size_t sm = 2*tab_bytes + PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float));
+        // launch shape: the warps per CTA (and CTAs per SM) that put the most warps on an SM within 227 KB of shared memory
+        // and 32 warps of 64 registers; ties go to the smaller CTAs
+        int dw = PQ_WARPS, dc = 1;
+        {
+            static const int force_w = std::getenv("AGBNP_B200_DERIV_WARPS") ? std::atoi(std::getenv("AGBNP_B200_DERIV_WARPS")) : 0;
+            int best = 0;
+            for (int w = 4; w <= DERIV_MAX_THREADS/32; w++) {
+                if (force_w && w != force_w) continue;
+                const size_t per_cta = 2*tab_bytes + w*DERIV_WARP_SMEM + 1024;
+                const int c = (int) std::min<size_t>((size_t) 227*1024/per_cta, (size_t) (32/w));
+                if (c*w > best || (c*w == best && c > dc)) { best = c*w; dw = w; dc = c; }
+            }
+        }
+        const size_t sm = 2*tab_bytes + dw*DERIV_WARP_SMEM;
+        const int dgrid = h->num_sm*dc;
         begin(K_DERIV);
-        if (pc.tab_smem) { if (cutoff) launch(h, k_deriv<true, true>, h->pq_grid, PQ_THREADS, sm, s, da); else launch(h, k_deriv<false, true>, h->pq_grid, PQ_THREADS, sm, s, da); }
-        else { if (cutoff) launch(h, k_deriv<true, false>, h->pq_grid, PQ_THREADS, sm, s, da); else launch(h, k_deriv<false, false>, h->pq_grid, PQ_THREADS, sm, s, da); }
+        if (pc.tab_smem) { if (cutoff) launch(h, k_deriv<true, true>, dgrid, 32*dw, sm, s, da); else launch(h, k_deriv<false, true>, dgrid, 32*dw, sm, s, da); }
+        else { if (cutoff) launch(h, k_deriv<true, false>, dgrid, 32*dw, sm, s, da); else launch(h, k_deriv<false, false>, dgrid, 32*dw, sm, s, da); }
         end(K_DERIV);
     }
     if (v1 && (phase_mask & PH_GAMMA)) {
@@ -969,15 +990,16 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
 #define PQ_CTAS 5
 #endif
         h->pq_grid = h->num_sm*PQ_CTAS;
-        const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*(2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float)));
+        const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*DERIV_WARP_SMEM);
+        const int deriv_smem = (int) prop.sharedMemPerBlockOptin;
         CK(cudaFuncSetAttribute(k_born<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
-        CK(cudaFuncSetAttribute(k_deriv<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
-        CK(cudaFuncSetAttribute(k_deriv<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
-        CK(cudaFuncSetAttribute(k_deriv<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
-        CK(cudaFuncSetAttribute(k_deriv<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        CK(cudaFuncSetAttribute(k_deriv<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, deriv_smem));
+        CK(cudaFuncSetAttribute(k_deriv<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, deriv_smem));
+        CK(cudaFuncSetAttribute(k_deriv<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, deriv_smem));
+        CK(cudaFuncSetAttribute(k_deriv<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, deriv_smem));
         alloc_tree_scratch(h);
         CK(cudaMallocHost((void**) &h->h_posq, sizeof(float4)*n));
         CK(cudaMallocHost((void**) &h->h_force, sizeof(float)*3*n));

@@ -21,7 +21,10 @@ constexpr int GB_THREADS = 128;
 #ifndef GB_FAR_FACTOR
 #define GB_FAR_FACTOR 64.f          // d^2 > 64 B_i B_j: exp(-d^2/4B_iB_j) < e^-16
 #endif
-constexpr int GB_CHUNK = 8;             // column tiles per GB work unit
+#ifndef GB_CHUNK_TILES
+#define GB_CHUNK_TILES 8
+#endif
+constexpr int GB_CHUNK = GB_CHUNK_TILES;    // column tiles per GB work unit (<= 32: one bit per tile)
 constexpr int I4_INTERVALS = 15;        // AGBNP_I4LOOKUP_NA - 1
 constexpr float PIFAC = 0.07957747154594767f;   // 1/(4 pi)
 
@@ -627,6 +630,10 @@ struct DerivMe { float px, py, pz, s, bw; int base, tj; };
 // off-diagonal tile the row role (MODE 1) therefore stores it in a 32x33 shared-memory matrix and the column role
 // (MODE 2) only looks it up: one spline value instead of two derivatives and a value.  MODE 0: plain (diagonal tile).
 constexpr int WMAT_STRIDE = 33;         // row stride: lanes writing the same column hit different banks
+// k_deriv holds 64 registers per thread, i.e. 32 warps fit one SM, but every warp needs 5.8 KB of shared memory next to the
+// CTA's two spline tables: the host picks the warps per CTA that bring the most warps onto an SM (deriv_shape)
+constexpr int DERIV_MAX_THREADS = 1024;
+constexpr size_t DERIV_WARP_SMEM = 2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float);
 
 template <bool CUTOFF, int MODE>
 __device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, int jj,
@@ -685,13 +692,14 @@ __device__ __forceinline__ void deriv_load(const DerivArgs& A, int blk, int lane
 }
 
 template <bool CUTOFF, bool TAB_SMEM>
-__global__ void __launch_bounds__(PQ_THREADS) k_deriv(DerivArgs A) {
+__global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ntab = TAB_SMEM ? A.c.ntables*I4_INTERVALS : 0;
     float4* s_tabv = (float4*) smem_raw;
     float4* s_tabd = s_tabv + ntab;
-    DerivSmem* sm = (DerivSmem*) (s_tabd + ntab);                       // [PQ_WARPS][2]
-    float* wmat = (float*) (sm + 2*PQ_WARPS) + (threadIdx.x >> 5)*WMAT_STRIDE*TILE;   // [PQ_WARPS][32*33] pair force weights
+    const int nwarp = blockDim.x >> 5;
+    DerivSmem* sm = (DerivSmem*) (s_tabd + ntab);                       // [nwarp][2]
+    float* wmat = (float*) (sm + 2*nwarp) + (threadIdx.x >> 5)*WMAT_STRIDE*TILE;      // [nwarp][32*33] pair force weights
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_release();
     for (int i = threadIdx.x; i < ntab; i += blockDim.x) { s_tabv[i] = A.c.i4v[i]; s_tabd[i] = A.c.i4d[i]; }   // constants: before the wait

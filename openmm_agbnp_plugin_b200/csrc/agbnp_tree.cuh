@@ -99,7 +99,8 @@ struct TreeArgs {
     const unsigned short* blist;
     const float4* posq;
     const int* orig;
-    const int* origbin;               // caller's index | radius bin << 24: one load decides both level-2 tests
+    const int4* l2rec;                // (caller's index | radius bin << 24, bits of float aL, bits of float vL, -): one load serves
+                                      // both level-2 tests and the screen's operands
     const unsigned char* rcbin;
     const double *aL, *vL, *aS, *vS;
     const float* gamma;
@@ -338,34 +339,36 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                 hit = point_box_dist2(pr.x, pr.y, pr.z, A.bbc[b], A.bbh[b]) < rcmax;
             }
             unsigned m = __ballot_sync(FULL, hit);
-            while (m) {                                           // two listed blocks per trip: their loads overlap
-                const int i0 = __ffs(m)-1;
-                m &= m-1;
-                const bool two = m != 0;
-                const int i1 = two ? __ffs(m)-1 : i0;
-                m &= m-1;
-                const int j0 = __shfl_sync(FULL, b, i0)*TILE+lane, j1 = __shfl_sync(FULL, b, i1)*TILE+lane;
-                const float4 p0 = A.posq[j0], p1 = A.posq[j1];
-                const int ob0 = A.origbin[j0], ob1 = A.origbin[j1];
-                const float dx0 = p0.x-pr.x, dy0 = p0.y-pr.y, dz0 = p0.z-pr.z;
-                const float dx1 = p1.x-pr.x, dy1 = p1.y-pr.y, dz1 = p1.z-pr.z;
-                const float d20 = dx0*dx0 + dy0*dy0 + dz0*dz0, d21 = dx1*dx1 + dy1*dy1 + dz1*dz1;
-                const bool ok0 = ((ob0 < 0 ? -1 : (ob0 & 0xffffff)) > orig_r) && (d20 < __ldg(A.rc2 + rb*A.nbins + ((ob0 >> 24) & 0x7f)));
-                const bool ok1 = two && ((ob1 < 0 ? -1 : (ob1 & 0xffffff)) > orig_r) && (d21 < __ldg(A.rc2 + rb*A.nbins + ((ob1 >> 24) & 0x7f)));
-                const unsigned am0 = __ballot_sync(FULL, ok0), am1 = __ballot_sync(FULL, ok1);
-                float a0 = 0.f, v0 = 0.f, a1 = 0.f, v1 = 0.f;
-                if (ok0) { a0 = (float) A.aL[j0]; v0 = (float) A.vL[j0]; }
-                if (ok1) { a1 = (float) A.aL[j1]; v1 = (float) A.vL[j1]; }
-                if (ok0) {
-                    const int p = nn + __popc(am0 & lanemask_lt());
-                    if (p < nbrmax) { W.nbi[p] = j0; W.nbx[p] = p0.x; W.nby[p] = p0.y; W.nbz[p] = p0.z; W.nba[p] = a0; W.nbv[p] = v0; }
+            while (m) {                                           // four listed blocks per trip: their loads overlap
+                int jq[4];
+                bool act[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    act[q] = m != 0;
+                    const int i = act[q] ? __ffs(m)-1 : 0;
+                    m &= m-1;
+                    jq[q] = __shfl_sync(FULL, b, i)*TILE+lane;
                 }
-                nn += __popc(am0);
-                if (ok1) {
-                    const int p = nn + __popc(am1 & lanemask_lt());
-                    if (p < nbrmax) { W.nbi[p] = j1; W.nbx[p] = p1.x; W.nby[p] = p1.y; W.nbz[p] = p1.z; W.nba[p] = a1; W.nbv[p] = v1; }
+                float4 pj[4];
+                int4 rc[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) { pj[q] = A.posq[jq[q]]; rc[q] = A.l2rec[jq[q]]; }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int ob = rc[q].x;
+                    const float dx = pj[q].x-pr.x, dy = pj[q].y-pr.y, dz = pj[q].z-pr.z;
+                    const float d2 = dx*dx + dy*dy + dz*dz;
+                    const bool ok = act[q] && ((ob < 0 ? -1 : (ob & 0xffffff)) > orig_r) && (d2 < __ldg(A.rc2 + rb*A.nbins + ((ob >> 24) & 0x7f)));
+                    const unsigned am = __ballot_sync(FULL, ok);
+                    if (ok) {
+                        const int p = nn + __popc(am & lanemask_lt());
+                        if (p < nbrmax) {
+                            W.nbi[p] = jq[q]; W.nbx[p] = pj[q].x; W.nby[p] = pj[q].y; W.nbz[p] = pj[q].z;
+                            W.nba[p] = __int_as_float(rc[q].y); W.nbv[p] = __int_as_float(rc[q].z);
+                        }
+                    }
+                    nn += __popc(am);
                 }
-                nn += __popc(am1);
             }
         }
         hw_nn = max(hw_nn, nn);
@@ -607,11 +610,11 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
         else m_tot += (lane == 0 && nlev >= 2) ? (unsigned long long) (nslots-W.lvs[3]) : 0ull;   // + the owned level-2 nodes counted above
 
         // ---- bottom-up sweep, both radius sets (gaussvol.cpp:400-487) ----
+        int off = 0;
+        if (lane == 0) off = atomicAdd(A.st.cursor, nslots);     // space in the store: claimed now, needed after the sweep
         tree_sweep(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS);
 
         // ---- persist what the gamma sweep needs ----
-        int off = 0;
-        if (lane == 0) off = atomicAdd(A.st.cursor, nslots);
         off = __shfl_sync(FULL, off, 0);
         if (off+nslots > A.st.cap) {
             if (lane == 0) atomicOr(A.status, ST_TREE_OVERFLOW);
