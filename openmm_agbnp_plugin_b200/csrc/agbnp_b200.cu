@@ -194,7 +194,7 @@ struct agbnp_b200 {
     // tree
     // tree capacities (grown on overflow): nodes per root, nodes per level, level-2 neighbors per root
     int tree_cap = 512, tree_wcap = 192, nbrmax = 64;
-    int tree_grid = 0, tree_warps = 4, gamma_grid = 0, gb_grid = 0, pq_grid = 0;
+    int tree_grid = 0, tree_warps = 4, gamma_grid = 0, gb_grid = 0, pq_grid = 0, gb_chunk = 8;
     bool tree_work_global = false;          // work arrays too large for shared memory: per-warp global scratch instead
     DevBuf<unsigned char> d_tree_stage, d_tree_work, d_gamma_scratch;
     TreeStore st{};
@@ -484,10 +484,15 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         }
         h->d_i4v.upload(tv, s); h->d_i4d.upload(td, s);
     }
-    // GB work units: triangular cover of the block-pair matrix in chunks of GB_CHUNK column tiles
+    // GB work units: triangular cover of the block-pair matrix in chunks of gb_chunk column tiles -- up to GB_CHUNK, fewer for
+    // small systems so that every resident warp still gets about four units (2clr: 17.6 k tiles over 1776 warps)
+    {
+        const long long tiles_total = (long long) h->nb*(h->nb+1)/2, warps = (long long) h->num_sm*GB_MIN_BLOCKS*(GB_THREADS/32);
+        h->gb_chunk = (int) std::max<long long>(1, std::min<long long>(GB_CHUNK, tiles_total/(4*std::max<long long>(warps, 1))));
+    }
     std::vector<int2> units;
     for (int ra = 0; ra < h->nb; ra++)
-        for (int c = ra; c < h->nb; c += GB_CHUNK) units.push_back(make_int2(ra, c));
+        for (int c = ra; c < h->nb; c += h->gb_chunk) units.push_back(make_int2(ra, c));
     h->nunits = (int) units.size();
     h->d_units.upload(units, s);
     // range-limited pair passes: heavy rows x heavy columns cb >= ra, then hydrogen rows x heavy columns (agbnp_pair.cuh)
@@ -636,9 +641,12 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
                          h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, h->cfg.shard_count};
         ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
         const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
+        int bocc = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bocc, k_born<false, true>, PQ_THREADS, sm));
+        const int bgrid = std::min(h->pq_grid, h->num_sm*std::max(1, bocc));      // resident CTAs only (first_unit)
         begin(K_BORN);
-        if (pc.tab_smem) { if (cutoff) launch(h, k_born<true, true>, h->pq_grid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, true>, h->pq_grid, PQ_THREADS, sm, s, ba); }
-        else { if (cutoff) launch(h, k_born<true, false>, h->pq_grid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, false>, h->pq_grid, PQ_THREADS, sm, s, ba); }
+        if (pc.tab_smem) { if (cutoff) launch(h, k_born<true, true>, bgrid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, true>, bgrid, PQ_THREADS, sm, s, ba); }
+        else { if (cutoff) launch(h, k_born<true, false>, bgrid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, false>, bgrid, PQ_THREADS, sm, s, ba); }
         end(K_BORN);
     }
     if (v1 && (phase_mask & PH_BORNFIN)) {
@@ -654,7 +662,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     }
     if (v1 && (phase_mask & PH_GB)) {
         GBArgs ga{};
-        ga.c = pc; ga.gbj = h->d_gbj.p; ga.units = h->d_units.p; ga.nunits = h->nunits;
+        ga.c = pc; ga.gbj = h->d_gbj.p; ga.units = h->d_units.p; ga.nunits = h->nunits; ga.chunk = h->gb_chunk;
         ga.shard_rank = h->cfg.shard_rank; ga.shard_count = h->cfg.shard_count;
         ga.gbacc = h->d_gbacc; ga.scalars = h->d_scalars; ga.counters = h->d_counters; ga.kdiel = h->k.dielectric_factor; ga.bmax = h->d_bmax.p;
         ga.work_counter = h->d_ctrl+CW_WORK_GB;

@@ -34,6 +34,23 @@ enum CounterSlot { CT_PGB = 0, CT_PQ = 1, CT_C2 = 2, CT_C3 = 3, CT_M = 4, CT_TIL
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_acquire() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Work stealing of the persistent kernels, two flavours.
+// (a) claim_unit: every unit comes from the atomic counter.
+// (b) first_unit / next_unit: a warp's first unit is its own global index, later ones come from the counter offset by the
+//     number of warps -- no burst of thousands of same-address atomics at the start of the kernel (20 % of k_born's stall
+//     samples).  Measured: (b) helps the range-limited pair passes and the tree build of small systems (RNase H: k_born
+//     26 -> 21 us, k_deriv 30 -> 24 us; Trp-cage k_tree 57 -> 50 us) and is neutral for them on 18 k atoms; k_gb and the gamma
+//     sweep lose 5-10 % with it (their warps then run in lockstep through equal-sized units, and the math-bound and the
+//     latency-bound phases of the warps of a scheduler no longer overlap), so those two keep (a).
+// The counter starts at 0 for every evaluation; grids using (b) must be fully resident.
+__device__ __forceinline__ int claim_unit(int* counter, int lane) {
+    int u = 0;
+    if (lane == 0) u = atomicAdd(counter, 1);
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+__device__ __forceinline__ int first_unit() { return (int) (blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5)); }
+__device__ __forceinline__ int next_unit(int* counter, int lane) { return claim_unit(counter, lane) + (int) (gridDim.x*(blockDim.x >> 5)); }
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 

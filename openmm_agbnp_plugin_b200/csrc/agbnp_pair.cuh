@@ -227,11 +227,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
     BornSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
     unsigned npair = 0;
-    for (;;) {
-        int u = 0;
-        if (lane == 0) u = atomicAdd(A.u.work_counter, 1);
-        u = __shfl_sync(FULL, u, 0);
-        if (u >= A.u.nunits) break;
+    for (int u = first_unit(); u < A.u.nunits; u = next_unit(A.u.work_counter, lane)) {
         if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
         const int2 un = A.u.units[u];
         const int ra = un.x;
@@ -357,8 +353,9 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
 struct GBArgs {
     PairCommon c;
     const float4* gbj;          // [3*np] GB atom records in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib}
-    const int2* units;          // (row block, first column block): triangular cover in chunks of GB_CHUNK column tiles
+    const int2* units;          // (row block, first column block): triangular cover in chunks of `chunk` column tiles
     int nunits;
+    int chunk;                  // column tiles per unit (<= GB_CHUNK), chosen on the host so that every warp gets several units
     int shard_rank, shard_count;
     float4* gbacc;              // out [np]: (fx, fy, fz)/(-2k) (GB pair force), Y_i
     double kdiel;               // k = 4.184*332/10*(-1/2)(1 - 1/80)  (ReferenceAGBNPKernels.cpp:465-468)
@@ -495,15 +492,11 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
     GBStage* stage = s_stage[warp];
     double e_acc = 0.0;
     unsigned long long npair = 0, ntile = 0;
-    for (;;) {
-        int u = 0;
-        if (lane == 0) u = atomicAdd(A.work_counter, 1);
-        u = __shfl_sync(FULL, u, 0);
-        if (u >= A.nunits) break;
+    for (int u = claim_unit(A.work_counter, lane); u < A.nunits; u = claim_unit(A.work_counter, lane)) {
         if (A.shard_count > 1 && (u % A.shard_count) != A.shard_rank) continue;
         const int2 un = A.units[u];
         const int ra = un.x;
-        const int cend = min(un.y+GB_CHUNK, A.c.nb);
+        const int cend = min(un.y+A.chunk, A.c.nb);
         const float4 ca = A.c.bbc[ra], ha = A.c.bbh[ra];
         // column tiles of this unit that take part (cutoff: bounding boxes within range), as a bit mask
         unsigned tiles = 0, fartiles = 0;
@@ -710,11 +703,7 @@ __global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
     DerivSmem& R = sm[2*warp];
     DerivSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
-    for (;;) {
-        int u = 0;
-        if (lane == 0) u = atomicAdd(A.u.work_counter, 1);
-        u = __shfl_sync(FULL, u, 0);
-        if (u >= A.u.nunits) break;
+    for (int u = first_unit(); u < A.u.nunits; u = next_unit(A.u.work_counter, lane)) {
         if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
         const int2 un = A.u.units[u];
         const int ra = un.x;

@@ -308,13 +308,13 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
     unsigned long long c2_tot = 0, c3_tot = 0, m_tot = 0;
     int hw_nn = 0, hw_slots = 0, hw_w = 0;
 
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(A.work_counter, 1);
-        item = __shfl_sync(FULL, item, 0);
+    // raw claim -> item: with shards, items are dealt block-cyclically (blocks of 32 in longest-first order)
+    const int raw_end = A.shard_count > 1 ? (A.nitems+TILE-1)/TILE*TILE : A.nitems;
+    for (int raw = first_unit(); ; raw = next_unit(A.work_counter, lane)) {
+        int item = raw;
         if (A.shard_count > 1) {
-            item = ((item >> 5)*A.shard_count + A.shard_rank)*TILE + (item & 31);
-            if (item >= ((A.nitems+TILE-1) & ~(TILE-1))) break;
+            item = ((raw >> 5)*A.shard_count + A.shard_rank)*TILE + (raw & 31);
+            if (item >= raw_end) break;
             if (item >= A.nitems) continue;
         } else if (item >= A.nitems) break;
         const int2 itm = A.items[item];
@@ -692,11 +692,8 @@ __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
     float4* hu = (float4*) wk;                      // [cap] children sums (F', P'x, P'y, P'z) per parent slot
     float* gam = (float*) (hu + A.cap);             // [cap] gamma_1..n per slot
     short* par = (short*) (gam + A.cap);            // [cap] parent slot
-    for (;;) {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(A.work_counter, 1);
-        r = __shfl_sync(FULL, r, 0);
-        if (r >= A.nitems) break;                   // r: item index (stored subtrees are per item; not-owned nodes carry zeros)
+    // r: item index (stored subtrees are per item; not-owned nodes carry zeros)
+    for (int r = claim_unit(A.work_counter, lane); r < A.nitems; r = claim_unit(A.work_counter, lane)) {
         const int cnt = A.st.root_cnt[r];
         if (cnt <= 1) continue;             // an atom without overlaps: dv1 = 0, no force (gaussvol.cpp:472)
         const float4* rec = A.st.rec + 2*(size_t) A.st.root_off[r];
