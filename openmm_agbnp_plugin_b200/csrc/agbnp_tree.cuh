@@ -186,6 +186,17 @@ struct TreeWork {
     }
 };
 
+// position of a lane within its segment (lanes with equal key are contiguous) and the largest position in the warp:
+// a segmented scan then needs only the steps d <= maxpos (sibling groups are short: usually 2-3 of the 5 steps), and a
+// lane takes the value d lanes below iff pos >= d
+__device__ __forceinline__ int seg_position(int key, int lane, int& maxpos) {
+    const int kprev = __shfl_up_sync(FULL, key, 1);
+    const unsigned heads = __ballot_sync(FULL, lane == 0 || kprev != key);
+    const int pos = lane - (31 - __clz(heads & (0xffffffffu >> (31-lane))));
+    maxpos = __reduce_max_sync(FULL, pos);
+    return pos;
+}
+
 // segmented inclusive scan step: lanes with equal key are contiguous; adds the value `d` lanes below if it belongs to the
 // same segment
 __device__ __forceinline__ void seg_step(float (&v)[10], bool take, int d) {
@@ -256,10 +267,12 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
                     }
                 } else if (lane == 0) hu_store(hu, carry_key, carry);
             }
+            int maxpos;
+            const int pos = seg_position(key, lane, maxpos);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int ku = __shfl_up_sync(FULL, key, d);
-                seg_step(v, lane >= d && ku == key, d);
+                if (d > maxpos) break;
+                seg_step(v, pos >= d, d);
             }
             const int kn = __shfl_down_sync(FULL, key, 1);
             const bool tail = valid && (lane == 31 || kn != key);
