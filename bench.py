@@ -186,7 +186,10 @@ def config_dict(s, args, parallelism):
             "n_atoms": int(len(s["pos"])), "nonbonded_method": meth, "version": 1,
             "inputs": "positions jittered +-0.001 nm per step (seeded, %d sets)" % JITTER_SETS,
             "l2": "256 MiB memset between timed evaluations (outside the per-step CUDA-event brackets)",
-            "parallelism": parallelism}
+            "parallelism": parallelism,
+            **({"tree_reuse_interval": _WORKLOAD["tree_reuse"],
+                "tree_reuse_note": "opt-in, NOT the reference's semantics: tree topology kept between builds (SURVEY 8f-3)"}
+               if _WORKLOAD.get("tree_reuse") else {})}
 
 
 def cpu_baseline(s, e_gpu, f_gpu):
@@ -473,7 +476,12 @@ def main():
     ap.add_argument("--workload", default="hivrt", help="hivrt (the metric's workload, default) | 2clr | 1dwc | rnaseh | 1li2 | trpcage")
     ap.add_argument("--cutoff", type=float, default=0.0, help="> 0: CutoffNonPeriodic with this cutoff (nm); the Reference platform, and "
                     "therefore the CPU baseline / parity check, has no cutoff: they are skipped")
+    ap.add_argument("--tree-reuse", type=int, default=0, help="> 1: OPT-IN tree reuse (not the reference's semantics): the overlap tree is "
+                    "rebuilt every K-th evaluation and re-evaluated on its stored topology in between; reported in config")
     args = ap.parse_args()
+    if args.tree_reuse > 1:
+        os.environ["AGBNP_B200_TREE_REUSE"] = str(args.tree_reuse)
+        _WORKLOAD["tree_reuse"] = args.tree_reuse
     _WORKLOAD["name"] = args.workload
     if args.cutoff > 0:
         _WORKLOAD["method"], _WORKLOAD["cutoff"] = 1, args.cutoff

@@ -49,6 +49,11 @@ typedef struct {
     int shard_rank;
     int shard_count;
     int reorder_interval;  /* evaluations between spatial re-sorts of the internal atom order; <= 0: library default */
+    /* OPT-IN, not the reference's semantics (it rebuilds the overlap tree in every evaluation): > 1 keeps the tree's
+     * topology for this many evaluations and only re-evaluates the stored overlaps at the new positions in between
+     * (for MD, where atoms move ~1e-3 nm per step).  <= 1: build every time (default).  The
+     * environment variable AGBNP_B200_TREE_REUSE sets it when this field is <= 0. */
+    int tree_reuse_interval;
 } agbnp_b200_config;
 
 /* fill with the reference defaults: version 1, NoCutoff, cutoff 1.0 nm, device 0, shard 0 of 1 */

@@ -107,12 +107,14 @@ class CalcAGBNPForceKernel:
     def Name():
         return "CalcAGBNPForce"
 
-    def __init__(self, name="CalcAGBNPForce", platform=None, device=0, shard_rank=0, shard_count=1):
+    def __init__(self, name="CalcAGBNPForce", platform=None, device=0, shard_rank=0, shard_count=1, tree_reuse_interval=0):
         self.name = name
         self.platform = platform
         self.device = device
         self.shard_rank = shard_rank
         self.shard_count = shard_count
+        # opt-in, NOT the reference's semantics: keep the overlap tree's topology for this many evaluations (MD)
+        self.tree_reuse_interval = tree_reuse_interval
         self.handle = None
 
     def _err(self):
@@ -129,6 +131,7 @@ class CalcAGBNPForceKernel:
         cfg.device = self.device
         cfg.shard_rank = self.shard_rank
         cfg.shard_count = self.shard_count
+        cfg.tree_reuse_interval = self.tree_reuse_interval
         radius, gamma, alpha, charge, ish = force._arrays()
         h = C.c_void_p()
         rc = L.agbnp_b200_create(C.byref(cfg), len(radius), _dp(radius), _dp(gamma), _dp(alpha), _dp(charge),
@@ -200,9 +203,9 @@ class Context:
     Context(force, device=0) plays the role of AGBNPForce::createImpl + AGBNPForceImpl::initialize
     (openmmapi/src/AGBNPForceImpl.cpp:27-30): it creates the platform kernel by name and initializes it."""
 
-    def __init__(self, force, device=0, shard_rank=0, shard_count=1):
+    def __init__(self, force, device=0, shard_rank=0, shard_count=1, tree_reuse_interval=0):
         self.force = force
-        self.kernel = CalcAGBNPForceKernel(CalcAGBNPForceKernel.Name(), None, device, shard_rank, shard_count)
+        self.kernel = CalcAGBNPForceKernel(CalcAGBNPForceKernel.Name(), None, device, shard_rank, shard_count, tree_reuse_interval)
         self.kernel.initialize(None, force)
         n = force.getNumParticles()
         self.positions = np.zeros((n, 3))

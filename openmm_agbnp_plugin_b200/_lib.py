@@ -17,7 +17,8 @@ BUF = dict(SELFVOL=0, YQ=1, FORCE=2, ENERGY=3, WU=4, BSUM=5)
 
 class Config(C.Structure):
     _fields_ = [("version", C.c_int), ("nonbonded_method", C.c_int), ("cutoff", C.c_double), ("device", C.c_int),
-                ("shard_rank", C.c_int), ("shard_count", C.c_int), ("reorder_interval", C.c_int)]
+                ("shard_rank", C.c_int), ("shard_count", C.c_int), ("reorder_interval", C.c_int),
+                ("tree_reuse_interval", C.c_int)]
 
 
 _lib = None

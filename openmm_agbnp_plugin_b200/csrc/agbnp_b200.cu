@@ -198,6 +198,12 @@ struct agbnp_b200 {
     bool tree_work_global = false;          // work arrays too large for shared memory: per-warp global scratch instead
     DevBuf<unsigned char> d_tree_stage, d_tree_work, d_gamma_scratch;
     TreeStore st{};
+    // opt-in tree reuse (cfg.tree_reuse_interval > 1): evaluations between builds re-evaluate the stored tree (k_tree_rescan)
+    bool tree_built = false;                // a build evaluation has been enqueued for the current order / capacities
+    int evals_since_build = 0;
+    bool cur_eval_rescan = false;           // decision for the evaluation being enqueued (begin_eval)
+    DevBuf<int> d_tree_ok;                  // device flag: the stored tree comes from a build evaluation without overflow
+    size_t slab_keep_off = 0;               // slab offset of root_cnt: a rescan evaluation zeroes the slab only up to here
     DevBuf<int> d_root_off, d_bcount;
     DevBuf<int2> d_items;
     std::vector<int2> items;                // tree work items (root, part | parts << 8), most expensive first (host)
@@ -238,7 +244,7 @@ struct agbnp_b200 {
     bool ahead_pending = false;
     // CUDA graphs of the whole kernel sequence, keyed by everything the launches bake in: `launch_gen` (bumped whenever
     // a buffer, capacity or launch shape changes) and the caller's pointers
-    struct GraphEntry { long long gen; const void* posq; void* sink; int layout, padded_n; double* d_energy; bool sharded; cudaGraphExec_t exec; int kernels; long long last_use; };
+    struct GraphEntry { long long gen; const void* posq; void* sink; int layout, padded_n; double* d_energy; bool sharded, rescan; cudaGraphExec_t exec; int kernels; long long last_use; };
     std::vector<GraphEntry> graphs;
     long long launch_gen = 0, graph_clock = 0;
     bool use_graph = true;
@@ -270,6 +276,7 @@ namespace {
 
 void alloc_store(agbnp_b200* h, int cap) {
     h->launch_gen++;
+    h->tree_built = false;
     h->d_st_rec.alloc((size_t) 2*cap);
     h->d_st_rank.alloc(cap);
     TreeStore& s = h->st;
@@ -281,6 +288,7 @@ void alloc_store(agbnp_b200* h, int cap) {
 // choose the launch shape of k_tree for the current capacities and (re)allocate its per-warp buffers
 void alloc_tree_scratch(agbnp_b200* h) {
     h->launch_gen++;
+    h->tree_built = false;
     const size_t per_warp = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
     const size_t smem_sm = 200*1024;                       // of 227 KB; leaves room for L1
     // CTAs of 2 warps (warps never cooperate); 128 registers/thread bound the residency at 16 warps per SM
@@ -328,6 +336,7 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
     for (int i = 0; i < h->nh; i++) h->orig[i] = hv[i];
     for (int i = 0; i < h->nhy; i++) h->orig[h->nhp+i] = hy[i];
     h->order_valid = true;
+    h->tree_built = false;                  // the stored tree is indexed by the old order
     h->params_dirty = true;
     h->evals_since_sort = 0;
     (void) s;
@@ -431,6 +440,7 @@ void build_pq_units(agbnp_b200* h, std::vector<int2>& out) {
 
 void upload_static(agbnp_b200* h, cudaStream_t s) {
     h->launch_gen++;
+    h->tree_built = false;
     const SystemParams& sp = h->sp;
     const int np = h->np;
     std::vector<float> charge(np, 0.f), radius(np, 0.15f), alpha(np, 0.f), gamma(np, 0.f);
@@ -520,6 +530,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         const size_t o_ctrl = take(sizeof(int)*CW_COUNT);
         const size_t o_dacc = take(sizeof(float4)*np), o_bsum = take(sizeof(float)*np), o_rcnt = take(sizeof(int)*h->max_items);
         h->slab_bytes = o;
+        h->slab_keep_off = o_rcnt;
         h->d_slab.alloc(o);
         unsigned char* b = h->d_slab.p;
         h->d_accL = (float4*) (b+o_accL); h->d_accS = h->d_accL+np; h->d_gacc = (float4*) (b+o_gacc);
@@ -578,6 +589,15 @@ void launch(agbnp_b200* h, void (*kern)(Args), int grid, int block, size_t smem,
     CK(cudaLaunchKernelEx(&cfg, kern, a));
 }
 
+// decide, once per evaluation and before anything is enqueued, whether its tree phase builds or rescans
+void begin_eval(agbnp_b200* h) {
+    const bool want = h->cfg.tree_reuse_interval > 1 && !h->tree_work_global && h->tree_built &&
+                      h->evals_since_build < h->cfg.tree_reuse_interval;
+    h->cur_eval_rescan = want;
+    if (want) h->evals_since_build++;
+    else { h->tree_built = true; h->evals_since_build = 1; }
+}
+
 // enqueue one evaluation (phase_mask: Phase bits).
 // Nothing here synchronises; k_finish delivers to the caller's sink only if no capacity overflowed (device-side check).
 void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_mask, const ForceSink* sink) {
@@ -597,11 +617,26 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     };
     PairCommon pc = pair_common(h);
     if (phase_mask & PH_TREE) {
+        const bool rescan = h->cur_eval_rescan;
+        // a rescan evaluation keeps root_cnt (the tail of the slab): it says which stored subtrees exist
         PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p,
-                    (float4*) h->d_slab.p, (int) (h->slab_bytes/sizeof(float4))};
+                    (float4*) h->d_slab.p, (int) ((rescan ? h->slab_keep_off : h->slab_bytes)/sizeof(float4))};
         begin(K_PREP);
         launch(h, k_prep, (h->nb+7)/8, 256, 0, s, pa);
         end(K_PREP);
+        if (rescan) {
+            RescanArgs ra{};
+            ra.items = h->d_items.p; ra.nitems = (int) h->items.size(); ra.posq = h->d_posq.p;
+            ra.aL = h->d_aL.p; ra.vL = h->d_vL.p; ra.aS = h->d_aS.p; ra.vS = h->d_vS.p; ra.gamma = h->d_gamma.p;
+            ra.volmina = h->k.volmina; ra.volminb = h->k.volminb; ra.swd = 1.0/(h->k.volminb-h->k.volmina);
+            ra.cap = h->tree_cap; ra.stage = h->d_tree_stage.p; ra.stage_stride = tree_stage_bytes(h->tree_cap);
+            ra.accL = h->d_accL; ra.accS = h->d_accS; ra.scalars = h->d_scalars; ra.counters = h->d_counters;
+            ra.st = h->st; ra.st.cursor = h->d_ctrl+CW_TREE_CURSOR;
+            ra.work_counter = h->d_ctrl+CW_WORK_TREE; ra.status = h->d_ctrl+CW_STATUS; ra.tree_ok = h->d_tree_ok.p;
+            begin(K_TREE);
+            launch(h, k_tree_rescan, h->tree_grid, 32*h->tree_warps, h->tree_warps*rescan_work_bytes(h->tree_cap), s, ra);
+            end(K_TREE);
+        } else {
         BlockListArgs bl{h->nhb, h->d_bbc.p, h->d_bbh.p, h->rc2_global, h->d_bcount.p, h->d_blist.p};
         begin(K_BLIST);
         launch(h, k_blocklist, (h->nhb+7)/8, 256, 0, s, bl);
@@ -632,6 +667,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         if (h->tree_work_global) launch(h, k_tree<false>, h->tree_grid, 32*h->tree_warps, 0, s, ta);
         else launch(h, k_tree<true>, h->tree_grid, 32*h->tree_warps, smem, s, ta);
         end(K_TREE);
+        }
     }
     const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
     if (v1 && (phase_mask & PH_BORN)) {
@@ -714,6 +750,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.accL = h->d_accL; fa.accS = h->d_accS; fa.scalars = h->d_scalars;
         fa.inv_roffset = (float) (1.0/h->k.roffset);
         fa.status = h->d_ctrl+CW_STATUS;
+        fa.tree_ok_out = h->cur_eval_rescan ? nullptr : h->d_tree_ok.p;     // a build evaluation (in)validates the stored tree
         if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; fa.gb_scale = -2.0*h->k.dielectric_factor; }
         fa.padded_n = sink ? sink->padded_n : 0;
         if (sink && sink->ptr) {
@@ -760,6 +797,7 @@ void enqueue_sharded(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, con
 }
 
 void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink, bool sharded = false) {
+    begin_eval(h);
     // a sharded evaluation is bounded by the waits of its exchange kernels, not by launch latency: measured on 2 and 8 B200 a
     // graph of it is no faster than the plain launches (490 vs 466 us, 372 vs 367 us), so it is launched directly
     if (!h->use_graph || h->prof_mask || sharded) {
@@ -769,7 +807,7 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
     agbnp_b200::GraphEntry* hit = nullptr;
     for (auto& g : h->graphs)
         if (g.gen == h->launch_gen && g.posq == d_posq_in && g.sink == sink->ptr && g.layout == sink->layout &&
-            g.padded_n == sink->padded_n && g.d_energy == sink->d_energy && g.sharded == sharded) { hit = &g; break; }
+            g.padded_n == sink->padded_n && g.d_energy == sink->d_energy && g.sharded == sharded && g.rescan == h->cur_eval_rescan) { hit = &g; break; }
     if (!hit) {
         // drop graphs of an older configuration, and the least recently used one beyond 16
         for (size_t i = 0; i < h->graphs.size(); ) {
@@ -788,7 +826,7 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
         try { if (sharded) enqueue_sharded(h, d_posq_in, h->own_stream, sink); else enqueue(h, d_posq_in, h->own_stream, PH_ALL, sink); }
         catch (...) { cudaStreamEndCapture(h->own_stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
         CK(cudaStreamEndCapture(h->own_stream, &graph));
-        agbnp_b200::GraphEntry e{h->launch_gen, d_posq_in, sink->ptr, sink->layout, sink->padded_n, sink->d_energy, sharded, nullptr,
+        agbnp_b200::GraphEntry e{h->launch_gen, d_posq_in, sink->ptr, sink->layout, sink->padded_n, sink->d_energy, sharded, h->cur_eval_rescan, nullptr,
                                  (int) (h->launches-before), 0};
         h->launches = before;
         const cudaError_t ce = cudaGraphInstantiate(&e.exec, graph, 0);
@@ -881,6 +919,7 @@ int run_checked(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
             grow_ahead(h, h->h_ctrl);
             return AGBNP_B200_OK;
         }
+        h->tree_built = false;
         if (!grow(h, h->h_ctrl)) { h->err = "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")"; return AGBNP_B200_ERR_CAPACITY; }
     }
     h->err = "agbnp_b200: capacity growth did not converge";
@@ -895,6 +934,7 @@ int async_retire(agbnp_b200* h, long long k) {
     h->async_pending[slot] = false;
     const int* ctrl = h->h_async + slot*CW_COUNT;
     if (ctrl[CW_STATUS] != 0) {
+        h->tree_built = false;
         const bool ok = grow(h, ctrl);
         h->async_fault = true;
         h->err = std::string("agbnp_b200: asynchronous evaluation ") + std::to_string(k) + " overflowed an internal capacity (status "
@@ -940,7 +980,7 @@ const char* agbnp_b200_version(void) { return "agbnp_b200 0.1 sm_100a"; }
 
 void agbnp_b200_default_config(agbnp_b200_config* cfg) {
     cfg->version = 1; cfg->nonbonded_method = AGBNP_B200_NOCUTOFF; cfg->cutoff = 1.0; cfg->device = 0;
-    cfg->shard_rank = 0; cfg->shard_count = 1; cfg->reorder_interval = 0;
+    cfg->shard_rank = 0; cfg->shard_count = 1; cfg->reorder_interval = 0; cfg->tree_reuse_interval = 0;
 }
 
 const char* agbnp_b200_last_error(const agbnp_b200* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -968,6 +1008,10 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
     }
     agbnp_b200* h = new agbnp_b200();
     h->cfg = *cfg;
+    if (h->cfg.tree_reuse_interval <= 0) {      // opt-in without touching the caller's code (the C++ host layer, bench.py)
+        const char* tr = std::getenv("AGBNP_B200_TREE_REUSE");
+        if (tr) h->cfg.tree_reuse_interval = std::atoi(tr);
+    }
     h->k = Constants::make();
     h->n = n;
     std::string e = h->sp.init(cfg->version, n, radius, gamma, alpha, charge, ishydrogen, h->k);
@@ -990,6 +1034,8 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->have_events = true;
         CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
+        h->d_tree_ok.alloc(1);
+        CK(cudaMemset(h->d_tree_ok.p, 0, sizeof(int)));
 #ifndef GB_CTAS
 #define GB_CTAS 4
 #endif
@@ -1065,6 +1111,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
             if (timing) t3 = now();
             const int status = fetch_status(h, s);          // the one synchronisation of the call
             if (status == 0) break;
+            h->tree_built = false;
             if (attempt >= 8 || !grow(h, h->h_ctrl)) {
                 h->err = "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")";
                 return AGBNP_B200_ERR_CAPACITY;
@@ -1313,6 +1360,7 @@ int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* s
         if (phase == 0) {
             if (!d_posq) return AGBNP_B200_ERR_ARG;
             prepare(h, nullptr, 0, d_posq, s);
+            begin_eval(h);
         }
         enqueue(h, (const float4*) d_posq, s, masks[phase], nullptr);
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }

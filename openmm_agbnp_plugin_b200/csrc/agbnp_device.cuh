@@ -19,7 +19,8 @@ constexpr double FORCE_SCALE = 4294967296.0;  // 2^32, OpenMM's fixed-point forc
 constexpr unsigned FULL = 0xffffffffu;
 
 // status bits written by kernels when a capacity is exceeded (host grows the buffer and re-runs the evaluation)
-enum StatusBits { ST_NBR_OVERFLOW = 1, ST_NODE_OVERFLOW = 2, ST_LEVEL_OVERFLOW = 4, ST_TREE_OVERFLOW = 8, ST_PAIRLIST_OVERFLOW = 16 };
+enum StatusBits { ST_NBR_OVERFLOW = 1, ST_NODE_OVERFLOW = 2, ST_LEVEL_OVERFLOW = 4, ST_TREE_OVERFLOW = 8, ST_PAIRLIST_OVERFLOW = 16,
+                  ST_TREE_STALE = 32 /* a rescan found no valid stored tree (its build evaluation overflowed): rebuild */ };
 
 // energy / diagnostic scalar slots (double)
 enum ScalarSlot { SC_EVOL_L = 0, SC_EVOL_S = 1, SC_EGB = 2, SC_EVDW = 3, SC_VOL_L = 4, SC_VOL_S = 5, SC_SPARE0 = 6, SC_SPARE1 = 7, SC_COUNT = 8 };

@@ -762,6 +762,7 @@ struct FinishArgs {
     int padded_n;
     double* scalars;                    // SC_* terms
     const int* status;                  // capacity-overflow bits of this evaluation: nothing is delivered unless 0
+    int* tree_ok_out;                   // build evaluations: 1 if the tree was built without overflow (read by k_tree_rescan)
     double* energy_accum;               // optional device accumulator (+=)
     double* energy_out;                 // optional device/pinned-mapped slot (=)
 };
@@ -770,7 +771,9 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     pdl_release();
     pdl_acquire();
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
-    if (A.status && *A.status != 0) return;
+    const bool bad = A.status && *A.status != 0;
+    if (k == 0 && A.tree_ok_out) *A.tree_ok_out = bad ? 0 : 1;
+    if (bad) return;
     if (k == 0) {
         // E1 + E2 (ReferenceAGBNPKernels.cpp:188,233,266) + GB + vdW
         const double e = (A.scalars[SC_EVOL_L] - A.scalars[SC_EVOL_S])*(double) A.inv_roffset + A.scalars[SC_EGB] + A.scalars[SC_EVDW];

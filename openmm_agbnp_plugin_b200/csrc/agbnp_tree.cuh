@@ -219,8 +219,10 @@ __device__ __forceinline__ void hu_store(float4* hu, int node, const float (&v)[
 // A node hands (psi, dvv1 F, dv1 F + P a_1/a_1i) to its parent (gaussvol.cpp:476-484).  Siblings are contiguous, so the
 // sums over a parent's children are a segmented warp scan over the child level; the last child of each parent stores
 // the totals into hu[4*parent ..] (global staging, one plain store per parent, read back one level later).
+// STORED: the node's last atom comes from `ja_arr` (k_tree_rescan) instead of the level-2 neighbor list.
+template <bool STORED>
 __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL, const float4* swS, float4* hu, int nlev, int r, int lane,
-                                           float4* accL, float4* accS) {
+                                           float4* accL, float4* accS, const int* ja_arr = nullptr) {
     for (int lev = nlev; lev >= 1; lev--) {
         const int b = W.lvs[lev], e = W.lvs[lev+1];
         const float coefp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
@@ -239,8 +241,9 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
                 const float4 l0 = swL[2*sl], l1 = swL[2*sl+1], s0v = swS[2*sl], s1v = swS[2*sl+1];
                 float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, h2 = h0;
                 if (W.ccount[sl] > 0) { h0 = hu[4*sl]; h1 = hu[4*sl+1]; h2 = hu[4*sl+2]; }
-                const int ia = W.nbr[sl];
-                const int ja = ia == 0 ? r : W.nbi[ia-1];
+                int ja;
+                if (STORED) ja = ja_arr[sl];
+                else { const int ia = W.nbr[sl]; ja = ia == 0 ? r : W.nbi[ia-1]; }
                 key = W.parent[sl];
                 {   // enlarged radii
                     const float ps = coefp*l0.x + h0.x, F = coefp*l0.y*l1.w + h0.y, px = h0.z, py = h0.w, pz = h1.x;
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
         // ---- bottom-up sweep, both radius sets (gaussvol.cpp:400-487) ----
         int off = 0;
         if (lane == 0) off = atomicAdd(A.st.cursor, nslots);     // space in the store: claimed now, needed after the sweep
-        tree_sweep(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS);
+        tree_sweep<false>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS);
 
         // ---- persist what the gamma sweep needs ----
         off = __shfl_sync(FULL, off, 0);
@@ -670,6 +673,179 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
         atomicMax(A.hw_nbr, hw_nn);
         atomicMax(A.hw_nodes, hw_slots);
         atomicMax(A.hw_width, hw_w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_tree_rescan (opt-in, agbnp_b200_config::tree_reuse_interval > 1): the overlap tree of an EARLIER evaluation is kept
+// -- same nodes, same parent / sibling structure -- and only re-evaluated at the new positions: every stored node's two
+// Gaussians from its parent's and its last atom's (the arithmetic of k_tree's node creation, gaussvol.cpp:234-245 and
+// :261-279, i.e. what the reference's rescan_tree_v does for the vdW radii, here for both radius sets), then the same
+// bottom-up sweep.  No candidate search, no screen, no acceptance test, no sort.  An overlap that would newly pass the
+// inclusion threshold is missing until the next build (its switched volume starts at 0, gaussvol.cpp:26-29), one that
+// would be dropped stays with switched volume 0: between builds the energy is that of the frozen overlap set.  This is
+// NOT the reference's semantics (it rebuilds every evaluation), hence opt-in; SURVEY 8f rank 3.
+// ---------------------------------------------------------------------------------------------------------------
+struct RescanArgs {
+    const int2* items;
+    int nitems;
+    const float4* posq;
+    const double *aL, *vL, *aS, *vS;
+    const float* gamma;
+    double volmina, volminb, swd;
+    int cap;
+    unsigned char* stage;             // k_tree's per-warp global staging
+    size_t stage_stride;
+    float4 *accL, *accS;
+    double* scalars;
+    unsigned long long* counters;
+    TreeStore st;
+    int* work_counter;
+    int* status;
+    const int* tree_ok;               // 1: the stored tree comes from a build evaluation that completed without overflow
+};
+
+__host__ __device__ inline size_t rescan_work_bytes(int cap) {
+    return (((size_t) cap*(sizeof(int) + 2*sizeof(short)) + (MAX_LEVELS+2)*sizeof(int)) + 15) & ~(size_t) 15;
+}
+
+__global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_release();
+    pdl_acquire();
+    if (*A.tree_ok == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(A.status, ST_TREE_STALE);
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int cap = A.cap;
+    const int gwarp = blockIdx.x*nwarp + warp;
+    unsigned char* wk = smem_raw + (size_t) warp*rescan_work_bytes(cap);
+    int* ja = (int*) wk;                            // [cap] sorted index of the node's last atom
+    TreeWork W{};
+    W.parent = (short*) (ja + cap);                 // [cap]
+    W.ccount = W.parent + cap;                      // [cap] 1 if the node has children
+    W.lvs = (int*) (W.ccount + cap);                // [MAX_LEVELS+2]
+    unsigned char* stage = A.stage + (size_t) gwarp*A.stage_stride;
+    NodeGauss* G = (NodeGauss*) stage;
+    float4* swL = (float4*) (G+cap);
+    float4* swS = swL + 2*(size_t) cap;
+    float4* hu = swS + 2*(size_t) cap;
+
+    double eL_tot = 0, eS_tot = 0, vsumL = 0, vsumS = 0;
+    unsigned long long m_tot = 0;
+    for (int item = first_unit(); item < A.nitems; item = next_unit(A.work_counter, lane)) {
+        const int cnt = A.st.root_cnt[item];
+        if (cnt <= 0) continue;                     // not this shard's item
+        const int off = A.st.root_off[item];
+        float4* rec = A.st.rec + 2*(size_t) off;
+        const short* rank = A.st.rank + off;
+        const short* slv = A.st.root_lvs + item*MAX_LEVELS;
+        int nlev = 1;
+        while (nlev+1 < MAX_LEVELS && slv[nlev+1] < cnt) nlev++;
+        const int2 itm = A.items[item];
+        const int r = itm.x, part = itm.y & 0xff, nparts = itm.y >> 8;
+        const float4 pr = A.posq[r];
+        __syncwarp();                               // the previous item is done with the work arrays
+        if (lane >= 1 && lane <= nlev) W.lvs[lane] = slv[lane];
+        if (lane == 0) W.lvs[nlev+1] = cnt;
+        for (int sl = lane; sl < cnt; sl += 32) {
+            const int pk = __float_as_int(rec[2*sl+1].w);
+            ja[sl] = __float_as_int(rec[2*sl].w);
+            W.parent[sl] = (short) (pk & 0xffff);   // 0xffff (the root) becomes -1
+            W.ccount[sl] = (short) ((pk >> 16) & 1);
+        }
+        // slot 0: the root atom (gaussvol.cpp:130-148)
+        const float gam_r = A.gamma[r];
+        if (lane == 0) {
+            NodeGauss g;
+            g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
+            g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
+            g.f0 = make_float4((float) g.aL, (float) g.vL, 0.f, 0.f); g.f1 = make_float4(0.f, gam_r, 0.f, 0.f);
+            G[0] = g;
+            const float own = part == 0 ? 1.f : 0.f;
+            swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            swS[0] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            eL_tot += (double) (own*gam_r*(float) g.vL); eS_tot += (double) (own*gam_r*(float) g.vS);
+            vsumL += (double) (own*(float) g.vL); vsumS += (double) (own*(float) g.vS);
+        }
+        __syncwarp();
+        // top-down: every stored node from its parent and its last atom
+        for (int lev = 2; lev <= nlev; lev++) {
+            const int b = W.lvs[lev], e = W.lvs[lev+1];
+            const float cf = (lev & 1) ? 1.f : -1.f;
+            const float coefp = cf/(float) lev;
+            for (int sl = b+lane; sl < e; sl += 32) {
+                const int p = W.parent[sl], j = ja[sl];
+                const NodeGauss* gp = G+p;
+                const double a1 = gp->aL, v1 = gp->vL, x1 = gp->xL, y1 = gp->yL, z1 = gp->zL;
+                const double b1 = gp->aS, w1 = gp->vS, u1 = gp->xS, q1 = gp->yS, r1 = gp->zS;
+                const double a2 = A.aL[j], v2 = A.vL[j], b2 = A.aS[j], w2 = A.vS[j];
+                const float gam = gp->f1.y + A.gamma[j];                      // gaussvol.cpp:244
+                const float4 pj = A.posq[j];
+                const double x2 = (double) pj.x - (double) pr.x, y2 = (double) pj.y - (double) pr.y, z2 = (double) pj.z - (double) pr.z;
+                const double dx = x2-x1, dy = y2-y1, dz = z2-z1;
+                double deltai, df, s, sp;
+                const double gvol = overlap_volume(a1, v1, a2, v2, dx*dx + dy*dy + dz*dz, deltai, df);
+                pol_switch(gvol, A.volmina, A.volminb, A.swd, s, sp);
+                NodeGauss g;
+                g.aL = a1+a2; g.vL = gvol;
+                g.xL = (x1*a1 + x2*a2)*deltai; g.yL = (y1*a1 + y2*a2)*deltai; g.zL = (z1*a1 + z2*a2)*deltai;
+                const double mL = 2.0*df*gvol;
+                float vl = (float) (s*gvol), sfl = (float) (sp*gvol + s);
+                const double ex = x2-u1, ey = y2-q1, ez = z2-r1;
+                double dS, dfS, sS, spS;
+                const double gS = overlap_volume(b1, w1, b2, w2, ex*ex + ey*ey + ez*ez, dS, dfS);
+                pol_switch(gS, A.volmina, A.volminb, A.swd, sS, spS);
+                g.aS = b1+b2; g.vS = gS;
+                g.xS = (u1*b1 + x2*b2)*dS; g.yS = (q1*b1 + y2*b2)*dS; g.zS = (r1*b1 + z2*b2)*dS;
+                g.f0 = make_float4((float) g.aL, (float) g.vL, (float) g.xL, (float) g.yL);
+                g.f1 = make_float4((float) g.zL, gam, 0.f, 0.f);
+                G[sl] = g;
+                const double mS = 2.0*dfS*gS;
+                float vs = (float) (sS*gS), sfs = (float) (spS*gS + sS);
+                // a level-2 node of a split root that this part does not own stays as a parent-less sibling: no terms of its own
+                const bool owned = lev > 2 || nparts == 1 || ((int) rank[sl] % nparts) == part;
+                if (!owned) { vl = 0.f; sfl = 0.f; vs = 0.f; sfs = 0.f; }
+                swL[2*sl] = make_float4(vl, sfl, (float) (v1 > 0 ? gvol/v1 : 0.0), (float) a2/(float) g.aL);
+                swL[2*sl+1] = make_float4((float) ((x2-x1)*mL), (float) ((y2-y1)*mL), (float) ((z2-z1)*mL), gam);
+                swS[2*sl] = make_float4(vs, sfs, (float) (w1 > 0 ? gS/w1 : 0.0), (float) b2/(float) g.aS);
+                swS[2*sl+1] = make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam);
+                if (owned) {
+                    const float cg = coefp*gam;
+                    eL_tot += (double) (cg*vl); eS_tot += (double) (cg*vs);
+                    vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
+                    m_tot++;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) atomicAdd(A.st.cursor, cnt);  // the control word reports the size of the tree, as after a build
+        tree_sweep<true>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS, ja);
+        // refresh what the gamma sweep reads (topology words unchanged)
+        {
+            int lev = 1, lend = W.lvs[2];
+            for (int s0 = 0; s0 < cnt; s0 += 32) {
+                const int sl = s0+lane;
+                if (sl < cnt) {
+                    while (sl >= lend) { lev++; lend = W.lvs[lev+1]; }
+                    const float cp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
+                    const float4 q0 = swS[2*sl], q1 = swS[2*sl+1];
+                    const float w1 = rec[2*sl+1].w;
+                    rec[2*sl] = make_float4(cp*q0.y, q0.z, q0.w, __int_as_float(ja[sl]));
+                    rec[2*sl+1] = make_float4(q1.x, q1.y, q1.z, w1);
+                }
+            }
+        }
+    }
+    eL_tot = warp_sum(eL_tot); eS_tot = warp_sum(eS_tot); vsumL = warp_sum(vsumL); vsumS = warp_sum(vsumS);
+    m_tot = (unsigned long long) warp_sum((double) m_tot);
+    if (lane == 0) {
+        atomicAdd(&A.scalars[SC_EVOL_L], eL_tot);
+        atomicAdd(&A.scalars[SC_EVOL_S], eS_tot);
+        atomicAdd(&A.scalars[SC_VOL_L], vsumL);
+        atomicAdd(&A.scalars[SC_VOL_S], vsumS);
+        atomicAdd(&A.counters[CT_M], m_tot);
     }
 }
 

@@ -14,11 +14,11 @@ from .AGBNPplugin import CalcAGBNPForceKernel, OpenMMException
 
 
 class VerletNVE:
-    def __init__(self, force, positions_nm, masses_amu, dt_ps=0.001, device=0, restraint_k=0.0):
+    def __init__(self, force, positions_nm, masses_amu, dt_ps=0.001, device=0, restraint_k=0.0, tree_reuse_interval=0):
         """restraint_k (kJ/mol/nm^2): optional harmonic tether of every atom to its initial position.  AGBNP alone has no
         bonded or repulsive terms, so an untethered solute collapses; the tether stands in for the rest of the force field
         (a torch expression, not part of the library) when the energy-conservation check needs a stable trajectory."""
-        self.kernel = CalcAGBNPForceKernel(CalcAGBNPForceKernel.Name(), None, device)
+        self.kernel = CalcAGBNPForceKernel(CalcAGBNPForceKernel.Name(), None, device, tree_reuse_interval=tree_reuse_interval)
         self.kernel.initialize(None, force)
         self.dev = torch.device("cuda", device)
         n = len(positions_nm)

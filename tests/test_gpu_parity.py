@@ -314,6 +314,58 @@ def test_verlet_energy_conservation():
     sim.close()
 
 
+@pytest.mark.parametrize("name,method,cutoff", [("trpcage", 0, 1.0), ("rnaseh", 1, 1.2)])
+def test_tree_reuse_tracks_the_rebuilt_tree(name, method, cutoff):
+    """Opt-in tree reuse (agbnp_b200_config::tree_reuse_interval, SURVEY 8f-3): between builds the stored overlaps are only
+    re-evaluated at the new positions.  Along an MD-like walk (+-0.001 nm per frame, cumulative) the reusing context must
+    (a) give the rebuilt tree's result bit-for-bit-in-topology on the frames where it builds (frames 0 and 5), and
+    (b) stay within the parity tolerances of a context that rebuilds every frame on the frames in between -- the
+    difference is the few overlaps that crossed the inclusion threshold since the last build, whose switched volume
+    starts at zero."""
+    s = load_system(name)
+    pos = systems.float_rounded(s["pos"])
+    ctx_ref = plug.Context(systems.make_force(s, 1, method, cutoff))
+    ctx_reu = plug.Context(systems.make_force(s, 1, method, cutoff), tree_reuse_interval=5)
+    for frame in range(7):
+        if frame:
+            pos = systems.float_rounded(systems.jitter(pos, 500 + frame))
+        ctx_ref.setPositions(pos)
+        ctx_reu.setPositions(pos)
+        e_ref, e_reu = ctx_ref.calcForcesAndEnergy(), ctx_reu.calcForcesAndEnergy()
+        m_ref, m_reu = int(ctx_ref.kernel.get("TREE_SIZE")[0]), int(ctx_reu.kernel.get("TREE_SIZE")[0])
+        if frame % 5 == 0:
+            assert m_reu == m_ref
+            assert gpu_topology(ctx_reu.kernel.get("TREE_TOPOLOGY")) == gpu_topology(ctx_ref.kernel.get("TREE_TOPOLOGY"))
+            assert abs(e_reu - e_ref) <= 5e-7 * abs(e_ref)
+        else:
+            assert abs(m_reu - m_ref) <= 0.01 * m_ref           # the frozen tree is a slightly different overlap set
+        assert abs(e_reu - e_ref) <= E_TOL * abs(e_ref)
+        assert relrms(ctx_reu.getForces(), ctx_ref.getForces()) <= F_TOL
+        for what in ("SELF_VOLUME_VDW", "BORN_RADIUS"):
+            a, b = ctx_reu.kernel.get(what), ctx_ref.kernel.get(what)
+            assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()
+
+
+def test_tree_reuse_conserves_energy():
+    """Velocity Verlet with the tree rebuilt every 10th step only: the rescanned energy is the exact energy of the frozen
+    overlap set and its forces are that energy's gradient, so KE + PE stays as constant as with a rebuild every step."""
+    from openmm_agbnp_plugin_b200 import md
+    s = load_system("trpcage")
+    pos = systems.float_rounded(s["pos"])
+    masses = np.where(s["ishydrogen"] > 0, 1.008, 12.0)
+    sim = md.VerletNVE(systems.make_force(s, 1, 0, 1.0), pos, masses, dt_ps=0.00025, tree_reuse_interval=10)
+    pe0, ke0 = sim.energies()
+    tot, ke = [pe0+ke0], 0.0
+    for _ in range(5):
+        sim.step(20)
+        pe, ke = sim.energies()
+        tot.append(pe+ke)
+    tot = np.array(tot)
+    assert ke > 300.0
+    assert np.abs(tot-tot[0]).max() <= 1e-3*ke + 2e-6*abs(pe0)
+    sim.close()
+
+
 def test_two_contexts_with_different_capacities():
     """Handles are independent (replica mode): one context growing its tree capacities (a dense cluster needs
     far more shared memory / scratch per warp) must not disturb another context of the same process."""
