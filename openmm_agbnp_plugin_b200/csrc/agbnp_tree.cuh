@@ -222,7 +222,8 @@ __device__ __forceinline__ void hu_store(float4* hu, int node, const float (&v)[
 // STORED: the node's last atom comes from `ja_arr` (k_tree_rescan) instead of the level-2 neighbor list.
 template <bool STORED>
 __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL, const float4* swS, float4* hu, int nlev, int r, int lane,
-                                           float4* accL, float4* accS, const int* ja_arr = nullptr) {
+                                           float4* accL, float4* accS, const int* ja_arr = nullptr,
+                                           float4* rec_out = nullptr, short* rank_out = nullptr, const short* rk = nullptr) {
     for (int lev = nlev; lev >= 1; lev--) {
         const int b = W.lvs[lev], e = W.lvs[lev+1];
         const float coefp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
@@ -245,6 +246,13 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
                 if (STORED) ja = ja_arr[sl];
                 else { const int ia = W.nbr[sl]; ja = ia == 0 ? r : W.nbi[ia-1]; }
                 key = W.parent[sl];
+                if (!STORED && rec_out) {
+                    // persist what the gamma sweep needs (TreeStore) while the records are in registers anyway
+                    const int pk = (key & 0xffff) | (W.ccount[sl] > 0 ? 0x10000 : 0);
+                    rec_out[2*sl] = make_float4(coefp*s0v.y, s0v.z, s0v.w, __int_as_float(ja));
+                    rec_out[2*sl+1] = make_float4(s1v.x, s1v.y, s1v.z, __int_as_float(pk));
+                    rank_out[sl] = rk[sl];
+                }
                 {   // enlarged radii
                     const float ps = coefp*l0.x + h0.x, F = coefp*l0.y*l1.w + h0.y, px = h0.z, py = h0.w, pz = h1.x;
                     const float c2a = l0.w, c2b = 1.f-l0.w;
@@ -625,35 +633,19 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
         if (nparts == 1) m_tot += (lane == 0) ? (unsigned long long) (nslots-1) : 0ull;
         else m_tot += (lane == 0 && nlev >= 2) ? (unsigned long long) (nslots-W.lvs[3]) : 0ull;   // + the owned level-2 nodes counted above
 
-        // ---- bottom-up sweep, both radius sets (gaussvol.cpp:400-487) ----
+        // ---- bottom-up sweep, both radius sets (gaussvol.cpp:400-487); it also persists what the gamma sweep needs ----
         int off = 0;
-        if (lane == 0) off = atomicAdd(A.st.cursor, nslots);     // space in the store: claimed now, needed after the sweep
-        tree_sweep<false>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS);
-
-        // ---- persist what the gamma sweep needs ----
+        if (lane == 0) off = atomicAdd(A.st.cursor, nslots);
         off = __shfl_sync(FULL, off, 0);
-        if (off+nslots > A.st.cap) {
+        const bool fits = off+nslots <= A.st.cap;
+        if (!fits) {
             if (lane == 0) atomicOr(A.status, ST_TREE_OVERFLOW);
         } else {
             if (lane == 0) { A.st.root_off[item] = off; A.st.root_cnt[item] = nslots; }
             if (lane <= nlev+1 && lane >= 1) A.st.root_lvs[item*MAX_LEVELS+lane] = (short) W.lvs[lane];
-            int lev = 1, lend = W.lvs[2];
-            for (int s0 = 0; s0 < nslots; s0 += 32) {
-                const int sl = s0+lane;
-                if (sl < nslots) {
-                    while (sl >= lend) { lev++; lend = W.lvs[lev+1]; }
-                    const float cp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
-                    const float4 q0 = swS[2*sl], q1 = swS[2*sl+1];
-                    const int ia = W.nbr[sl];
-                    const int o = off+sl;
-                    const int ja = ia == 0 ? r : W.nbi[ia-1];
-                    const int pk = ((int) W.parent[sl] & 0xffff) | (W.ccount[sl] > 0 ? 0x10000 : 0);
-                    A.st.rec[2*o] = make_float4(cp*q0.y, q0.z, q0.w, __int_as_float(ja));
-                    A.st.rec[2*o+1] = make_float4(q1.x, q1.y, q1.z, __int_as_float(pk));
-                    A.st.rank[o] = rk[sl];
-                }
-            }
         }
+        tree_sweep<false>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS, nullptr,
+                          fits ? A.st.rec + 2*(size_t) off : nullptr, fits ? A.st.rank + off : nullptr, rk);
         __syncwarp();
     }
 
@@ -705,6 +697,9 @@ struct RescanArgs {
     const int* tree_ok;               // 1: the stored tree comes from a build evaluation that completed without overflow
 };
 
+#ifndef RESCAN_UNROLL
+#define RESCAN_UNROLL 1                // measured: 2 spills at the 128-register cap and is slower (124 vs 114 us)
+#endif
 __host__ __device__ inline size_t rescan_work_bytes(int cap) {
     return (((size_t) cap*(sizeof(int) + 2*sizeof(short)) + (MAX_LEVELS+2)*sizeof(int)) + 15) & ~(size_t) 15;
 }
@@ -775,14 +770,35 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
             const int b = W.lvs[lev], e = W.lvs[lev+1];
             const float cf = (lev & 1) ? 1.f : -1.f;
             const float coefp = cf/(float) lev;
-            for (int sl = b+lane; sl < e; sl += 32) {
-                const int p = W.parent[sl], j = ja[sl];
-                const NodeGauss* gp = G+p;
-                const double a1 = gp->aL, v1 = gp->vL, x1 = gp->xL, y1 = gp->yL, z1 = gp->zL;
-                const double b1 = gp->aS, w1 = gp->vS, u1 = gp->xS, q1 = gp->yS, r1 = gp->zS;
-                const double a2 = A.aL[j], v2 = A.vL[j], b2 = A.aS[j], w2 = A.vS[j];
-                const float gam = gp->f1.y + A.gamma[j];                      // gaussvol.cpp:244
-                const float4 pj = A.posq[j];
+            // RESCAN_UNROLL chunks of 32 slots per trip: the chunks of a level are independent, and issuing their loads
+            // together keeps that many L2 round trips in flight per warp (the kernel is bound by exactly those)
+            for (int s0 = b; s0 < e; s0 += 32*RESCAN_UNROLL) {
+                int pq[RESCAN_UNROLL], jq[RESCAN_UNROLL];
+                double gin[RESCAN_UNROLL][14];
+                float gamq[RESCAN_UNROLL];
+                float4 pjq[RESCAN_UNROLL];
+#pragma unroll
+                for (int q = 0; q < RESCAN_UNROLL; q++) {
+                    const int sl = min(s0 + 32*q + lane, e-1);
+                    const int p = W.parent[sl], j = ja[sl];
+                    const NodeGauss* gp = G+p;
+                    pq[q] = p; jq[q] = j;
+                    gin[q][0] = gp->aL; gin[q][1] = gp->vL; gin[q][2] = gp->xL; gin[q][3] = gp->yL; gin[q][4] = gp->zL;
+                    gin[q][5] = gp->aS; gin[q][6] = gp->vS; gin[q][7] = gp->xS; gin[q][8] = gp->yS; gin[q][9] = gp->zS;
+                    gin[q][10] = A.aL[j]; gin[q][11] = A.vL[j]; gin[q][12] = A.aS[j]; gin[q][13] = A.vS[j];
+                    gamq[q] = gp->f1.y + A.gamma[j];                          // gaussvol.cpp:244
+                    pjq[q] = A.posq[j];
+                }
+#pragma unroll
+                for (int q = 0; q < RESCAN_UNROLL; q++) {
+                const int sl = s0 + 32*q + lane;
+                if (sl < e) {
+                const int p = pq[q], j = jq[q];
+                const double a1 = gin[q][0], v1 = gin[q][1], x1 = gin[q][2], y1 = gin[q][3], z1 = gin[q][4];
+                const double b1 = gin[q][5], w1 = gin[q][6], u1 = gin[q][7], q1 = gin[q][8], r1 = gin[q][9];
+                const double a2 = gin[q][10], v2 = gin[q][11], b2 = gin[q][12], w2 = gin[q][13];
+                const float gam = gamq[q];
+                const float4 pj = pjq[q];
                 const double x2 = (double) pj.x - (double) pr.x, y2 = (double) pj.y - (double) pr.y, z2 = (double) pj.z - (double) pr.z;
                 const double dx = x2-x1, dy = y2-y1, dz = z2-z1;
                 double deltai, df, s, sp;
@@ -809,34 +825,25 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
                 if (!owned) { vl = 0.f; sfl = 0.f; vs = 0.f; sfs = 0.f; }
                 swL[2*sl] = make_float4(vl, sfl, (float) (v1 > 0 ? gvol/v1 : 0.0), (float) a2/(float) g.aL);
                 swL[2*sl+1] = make_float4((float) ((x2-x1)*mL), (float) ((y2-y1)*mL), (float) ((z2-z1)*mL), gam);
-                swS[2*sl] = make_float4(vs, sfs, (float) (w1 > 0 ? gS/w1 : 0.0), (float) b2/(float) g.aS);
-                swS[2*sl+1] = make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam);
+                const float4 qs0 = make_float4(vs, sfs, (float) (w1 > 0 ? gS/w1 : 0.0), (float) b2/(float) g.aS);
+                const float4 qs1 = make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam);
+                swS[2*sl] = qs0; swS[2*sl+1] = qs1;
+                // what the gamma sweep reads, refreshed in place (the topology words stay; the root's record is constant)
+                rec[2*sl] = make_float4(coefp*qs0.y, qs0.z, qs0.w, __int_as_float(j));
+                rec[2*sl+1] = make_float4(qs1.x, qs1.y, qs1.z, __int_as_float(((int) p & 0xffff) | ((int) W.ccount[sl] << 16)));
                 if (owned) {
                     const float cg = coefp*gam;
                     eL_tot += (double) (cg*vl); eS_tot += (double) (cg*vs);
                     vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
                     m_tot++;
                 }
+                            }
+                }
             }
             __syncwarp();
         }
         if (lane == 0) atomicAdd(A.st.cursor, cnt);  // the control word reports the size of the tree, as after a build
         tree_sweep<true>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS, ja);
-        // refresh what the gamma sweep reads (topology words unchanged)
-        {
-            int lev = 1, lend = W.lvs[2];
-            for (int s0 = 0; s0 < cnt; s0 += 32) {
-                const int sl = s0+lane;
-                if (sl < cnt) {
-                    while (sl >= lend) { lev++; lend = W.lvs[lev+1]; }
-                    const float cp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
-                    const float4 q0 = swS[2*sl], q1 = swS[2*sl+1];
-                    const float w1 = rec[2*sl+1].w;
-                    rec[2*sl] = make_float4(cp*q0.y, q0.z, q0.w, __int_as_float(ja[sl]));
-                    rec[2*sl+1] = make_float4(q1.x, q1.y, q1.z, w1);
-                }
-            }
-        }
     }
     eL_tot = warp_sum(eL_tot); eS_tot = warp_sum(eS_tot); vsumL = warp_sum(vsumL); vsumS = warp_sum(vsumS);
     m_tot = (unsigned long long) warp_sum((double) m_tot);
