@@ -17,7 +17,10 @@
 //                     do not fit, the same code runs with these arrays in a per-warp global scratch: TreeArgs::wk_global.)
 //   global staging -- streamed, coalesced, one round trip per level: the nodes' Gaussians (read once by their children's
 //                     candidates), the per-node sweep records and the children-to-parent sums of the sweeps.
-// Only what the later "gamma" sweep (S10+S11 merged, linear in nu) needs is persisted compactly (TreeStore).
+// Only what the later "gamma" sweep (S10+S11 merged, linear in nu) needs is persisted compactly (TreeStore), by the
+// bottom-up sweep itself.  The global staging is what bounds these kernels (ncu): every pass over a level
+// waits for an L2 round trip with one chunk of 32 nodes in flight per warp -- passes over staged data are what to avoid.
+// k_tree_rescan (opt-in tree reuse) re-evaluates a stored tree at new positions without any search.
 #ifndef AGBNP_TREE_CUH_
 #define AGBNP_TREE_CUH_
 
