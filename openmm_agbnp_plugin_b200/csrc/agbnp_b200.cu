@@ -1394,6 +1394,7 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
         if (!h_energy) return AGBNP_B200_OK;        // asynchronous: status is checked by the next synchronous finish
         const int status = fetch_status(h, s);
         if (status != 0) {
+            h->tree_built = false;
             const bool ok = grow(h, h->h_ctrl);
             h->err = "agbnp_b200_shard_finish: capacity overflow (status " + std::to_string(status) + ")" + (ok ? "; capacities grown, re-run the evaluation" : "");
             return AGBNP_B200_ERR_CAPACITY;

@@ -154,3 +154,47 @@ def test_two_shards_on_one_gpu_equal_the_unsharded_result(method, cutoff):
         assert relrms(f, f_ref) <= 1e-5
     for k in ks:
         k.close()
+
+
+@pytest.mark.gpu
+def test_two_shards_with_tree_reuse(monkeypatch):
+    """Opt-in tree reuse under sharding: every shard keeps and rescans the subtrees of the items it owns; the exchanged
+    sums must still add up to the unsharded result on the rescanned frames."""
+    import openmm_agbnp_plugin_b200 as plug
+    from openmm_agbnp_plugin_b200 import systems
+    from conftest import load_system, relrms
+    s = load_system("1li2")
+    pos = systems.float_rounded(s["pos"])
+    n = len(pos)
+    force = systems.make_force(s, 1, 0, 1.0)
+    ctx = plug.Context(force)                                    # rebuilds every evaluation
+    monkeypatch.setenv("AGBNP_B200_TREE_REUSE", "4")
+    world = 2
+    ks = [sharding.CudaShardKernel(force, 0, r, world) for r in range(world)]
+    monkeypatch.delenv("AGBNP_B200_TREE_REUSE")
+    stream = torch.cuda.current_stream().cuda_stream
+    for frame in range(3):                                       # build, rescan, rescan
+        if frame:
+            pos = systems.float_rounded(systems.jitter(pos, 900 + frame))
+        ctx.setPositions(pos)
+        e_ref = ctx.calcForcesAndEnergy()
+        f_ref = ctx.getForces().copy()
+        posq = torch.zeros((n, 4), dtype=torch.float32)
+        posq[:, :3] = torch.from_numpy(pos.astype(np.float32))
+        d_posq = posq.cuda()
+        for ph in range(sharding.N_PHASES):
+            for k in ks:
+                k.phase(ph, d_posq if ph == 0 else None, stream)
+            torch.cuda.synchronize()
+            for name in sharding.EXCHANGES[ph]:
+                tot = ks[0].buffer(name) + ks[1].buffer(name)
+                for k in ks:
+                    k.buffer(name).copy_(tot)
+        for k in ks:
+            d_f = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+            rc, e = k.finish(stream, d_f, 0, n, None, True)
+            assert rc == 0
+            assert abs(e - e_ref) <= 1e-5*abs(e_ref)
+            assert relrms(d_f.cpu().numpy().astype(np.float64), f_ref) <= 1e-4
+    for k in ks:
+        k.close()
