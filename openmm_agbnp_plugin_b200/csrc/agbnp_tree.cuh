@@ -700,9 +700,6 @@ struct RescanArgs {
     const int* tree_ok;               // 1: the stored tree comes from a build evaluation that completed without overflow
 };
 
-#ifndef RESCAN_UNROLL
-#define RESCAN_UNROLL 1                // measured: 2 spills at the 128-register cap and is slower (124 vs 114 us)
-#endif
 __host__ __device__ inline size_t rescan_work_bytes(int cap) {
     return (((size_t) cap*(sizeof(int) + 2*sizeof(short)) + (MAX_LEVELS+2)*sizeof(int)) + 15) & ~(size_t) 15;
 }
@@ -768,40 +765,21 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
             vsumL += (double) (own*(float) g.vL); vsumS += (double) (own*(float) g.vS);
         }
         __syncwarp();
-        // top-down: every stored node from its parent and its last atom
+        // top-down: every stored node from its parent and its last atom.  (Measured without gain: two chunks of a level per
+        // trip -- spills at the 128-register cap, 124 vs 114 us; narrow levels kept in registers with the parent fetched by
+        // shuffle instead of through the staged G -- 113 vs 114 us.)
         for (int lev = 2; lev <= nlev; lev++) {
             const int b = W.lvs[lev], e = W.lvs[lev+1];
             const float cf = (lev & 1) ? 1.f : -1.f;
             const float coefp = cf/(float) lev;
-            // RESCAN_UNROLL chunks of 32 slots per trip: the chunks of a level are independent, and issuing their loads
-            // together keeps that many L2 round trips in flight per warp (the kernel is bound by exactly those)
-            for (int s0 = b; s0 < e; s0 += 32*RESCAN_UNROLL) {
-                int pq[RESCAN_UNROLL], jq[RESCAN_UNROLL];
-                double gin[RESCAN_UNROLL][14];
-                float gamq[RESCAN_UNROLL];
-                float4 pjq[RESCAN_UNROLL];
-#pragma unroll
-                for (int q = 0; q < RESCAN_UNROLL; q++) {
-                    const int sl = min(s0 + 32*q + lane, e-1);
-                    const int p = W.parent[sl], j = ja[sl];
-                    const NodeGauss* gp = G+p;
-                    pq[q] = p; jq[q] = j;
-                    gin[q][0] = gp->aL; gin[q][1] = gp->vL; gin[q][2] = gp->xL; gin[q][3] = gp->yL; gin[q][4] = gp->zL;
-                    gin[q][5] = gp->aS; gin[q][6] = gp->vS; gin[q][7] = gp->xS; gin[q][8] = gp->yS; gin[q][9] = gp->zS;
-                    gin[q][10] = A.aL[j]; gin[q][11] = A.vL[j]; gin[q][12] = A.aS[j]; gin[q][13] = A.vS[j];
-                    gamq[q] = gp->f1.y + A.gamma[j];                          // gaussvol.cpp:244
-                    pjq[q] = A.posq[j];
-                }
-#pragma unroll
-                for (int q = 0; q < RESCAN_UNROLL; q++) {
-                const int sl = s0 + 32*q + lane;
-                if (sl < e) {
-                const int p = pq[q], j = jq[q];
-                const double a1 = gin[q][0], v1 = gin[q][1], x1 = gin[q][2], y1 = gin[q][3], z1 = gin[q][4];
-                const double b1 = gin[q][5], w1 = gin[q][6], u1 = gin[q][7], q1 = gin[q][8], r1 = gin[q][9];
-                const double a2 = gin[q][10], v2 = gin[q][11], b2 = gin[q][12], w2 = gin[q][13];
-                const float gam = gamq[q];
-                const float4 pj = pjq[q];
+            for (int sl = b+lane; sl < e; sl += 32) {
+                const int p = W.parent[sl], j = ja[sl];
+                const NodeGauss* gp = G+p;
+                const double a1 = gp->aL, v1 = gp->vL, x1 = gp->xL, y1 = gp->yL, z1 = gp->zL;
+                const double b1 = gp->aS, w1 = gp->vS, u1 = gp->xS, q1 = gp->yS, r1 = gp->zS;
+                const double a2 = A.aL[j], v2 = A.vL[j], b2 = A.aS[j], w2 = A.vS[j];
+                const float gam = gp->f1.y + A.gamma[j];                          // gaussvol.cpp:244
+                const float4 pj = A.posq[j];
                 const double x2 = (double) pj.x - (double) pr.x, y2 = (double) pj.y - (double) pr.y, z2 = (double) pj.z - (double) pr.z;
                 const double dx = x2-x1, dy = y2-y1, dz = z2-z1;
                 double deltai, df, s, sp;
@@ -823,7 +801,7 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
                 G[sl] = g;
                 const double mS = 2.0*dfS*gS;
                 float vs = (float) (sS*gS), sfs = (float) (spS*gS + sS);
-                // a level-2 node of a split root that this part does not own stays as a parent-less sibling: no terms of its own
+                // a level-2 node of a split root that this part does not own stays as a sibling: no terms of its own
                 const bool owned = lev > 2 || nparts == 1 || ((int) rank[sl] % nparts) == part;
                 if (!owned) { vl = 0.f; sfl = 0.f; vs = 0.f; sfs = 0.f; }
                 swL[2*sl] = make_float4(vl, sfl, (float) (v1 > 0 ? gvol/v1 : 0.0), (float) a2/(float) g.aL);
@@ -839,8 +817,6 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
                     eL_tot += (double) (cg*vl); eS_tot += (double) (cg*vs);
                     vsumL += (double) (cf*vl); vsumS += (double) (cf*vs);
                     m_tot++;
-                }
-                            }
                 }
             }
             __syncwarp();
