@@ -52,12 +52,12 @@ struct TreeStore {
 
 // a node's two Gaussians (enlarged / vdW radii) in the root's frame: positions are relative to the root atom
 struct __align__(16) NodeGauss {
-    double aL, vL, xL, yL, zL;
-    double aS, vS, xS, yS, zS;
-    float4 f0;               // (aL, vL, xL, yL) rounded to float: all the FP32 screen reads
-    float4 f1;               // (zL rounded to float, gamma_1..n, -, -)
+    double aL, vL, xL, yL, zL;   // the FP32 screen reads these five and rounds them itself: float copies would make the
+    double aS, vS, xS, yS, zS;   // record 112 bytes, and the staged bytes per node are what the kernel pays for
+    float gam;                   // gamma_1..n
+    float pad[3];
 };
-static_assert(sizeof(NodeGauss) == 112, "NodeGauss layout");
+static_assert(sizeof(NodeGauss) == 96, "NodeGauss layout");
 
 constexpr int BLIST_MAX = 64;       // neighbor blocks listed per heavy block (more: the root scans all blocks)
 
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             NodeGauss g;
             g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
             g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
-            g.f0 = make_float4((float) g.aL, (float) g.vL, 0.f, 0.f); g.f1 = make_float4(0.f, gam_r, 0.f, 0.f);
+            g.gam = gam_r; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
             G[0] = g;
             const float own = part == 0 ? 1.f : 0.f;              // the root's own terms belong to part 0
             swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
@@ -477,14 +477,15 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                         kn = (int) W.nbr[ls + W.perm[u]] - 1;
                     }
                     kn = valid ? kn : 0;
-                    const float4 f0 = G[p].f0;                            // aL, vL, xL, yL rounded to float
-                    const float z1 = G[p].f1.x;
+                    const NodeGauss* gq = G+p;
+                    const float a1f = (float) gq->aL, v1f = (float) gq->vL;
+                    const float x1f = (float) gq->xL, y1f = (float) gq->yL, z1f = (float) gq->zL;
                     const float a2 = W.nba[kn], v2 = W.nbv[kn];
-                    const float dx = (W.nbx[kn]-pr.x)-f0.z, dy = (W.nby[kn]-pr.y)-f0.w, dz = (W.nbz[kn]-pr.z)-z1;
+                    const float dx = (W.nbx[kn]-pr.x)-x1f, dy = (W.nby[kn]-pr.y)-y1f, dz = (W.nbz[kn]-pr.z)-z1f;
                     const float d2 = dx*dx + dy*dy + dz*dz;
-                    const float df = __fdividef(f0.x*a2, f0.x+a2);
+                    const float df = __fdividef(a1f*a2, a1f+a2);
                     const float u = df*0.318309886f;
-                    const float est = f0.y*v2*(u*sqrtf(u))*__expf(-df*d2);
+                    const float est = v1f*v2*(u*sqrtf(u))*__expf(-df*d2);
                     mb[q4] = valid && est > A.screen;
                     pkv[q4] = p | (kn << 16);
                 }
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                     // round trip instead of two
                     b1 = gp->aS; w1 = gp->vS; u1 = gp->xS; q1 = gp->yS; r1 = gp->zS;
                     b2 = A.aS[j]; w2 = A.vS[j];
-                    gam = gp->f1.y + A.gamma[j];                          // gaussvol.cpp:244
+                    gam = gp->gam + A.gamma[j];                          // gaussvol.cpp:244
                     x2 = (double) W.nbx[kn] - (double) pr.x;              // exact in double
                     y2 = (double) W.nby[kn] - (double) pr.y;
                     z2 = (double) W.nbz[kn] - (double) pr.z;
@@ -554,8 +555,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                         pol_switch(gS, A.volmina, A.volminb, A.swd, sS, spS);
                         g.aS = b1+b2; g.vS = gS;
                         g.xS = (u1*b1 + x2*b2)*dS; g.yS = (q1*b1 + y2*b2)*dS; g.zS = (r1*b1 + z2*b2)*dS;
-                        g.f0 = make_float4((float) g.aL, (float) g.vL, (float) g.xL, (float) g.yL);
-                        g.f1 = make_float4((float) g.zL, gam, 0.f, 0.f);
+                        g.gam = gam; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
                         G[slot] = g;
                         const double mS = 2.0*dfS*gS;
                         const float vs = (float) (sS*gS);
@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
             NodeGauss g;
             g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
             g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
-            g.f0 = make_float4((float) g.aL, (float) g.vL, 0.f, 0.f); g.f1 = make_float4(0.f, gam_r, 0.f, 0.f);
+            g.gam = gam_r; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
             G[0] = g;
             const float own = part == 0 ? 1.f : 0.f;
             swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
                 const double a1 = gp->aL, v1 = gp->vL, x1 = gp->xL, y1 = gp->yL, z1 = gp->zL;
                 const double b1 = gp->aS, w1 = gp->vS, u1 = gp->xS, q1 = gp->yS, r1 = gp->zS;
                 const double a2 = A.aL[j], v2 = A.vL[j], b2 = A.aS[j], w2 = A.vS[j];
-                const float gam = gp->f1.y + A.gamma[j];                          // gaussvol.cpp:244
+                const float gam = gp->gam + A.gamma[j];                          // gaussvol.cpp:244
                 const float4 pj = A.posq[j];
                 const double x2 = (double) pj.x - (double) pr.x, y2 = (double) pj.y - (double) pr.y, z2 = (double) pj.z - (double) pr.z;
                 const double dx = x2-x1, dy = y2-y1, dz = z2-z1;
@@ -796,8 +796,7 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
                 pol_switch(gS, A.volmina, A.volminb, A.swd, sS, spS);
                 g.aS = b1+b2; g.vS = gS;
                 g.xS = (u1*b1 + x2*b2)*dS; g.yS = (q1*b1 + y2*b2)*dS; g.zS = (r1*b1 + z2*b2)*dS;
-                g.f0 = make_float4((float) g.aL, (float) g.vL, (float) g.xL, (float) g.yL);
-                g.f1 = make_float4((float) g.zL, gam, 0.f, 0.f);
+                g.gam = gam; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
                 G[sl] = g;
                 const double mS = 2.0*dfS*gS;
                 float vs = (float) (sS*gS), sfs = (float) (spS*gS + sS);
