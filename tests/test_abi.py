@@ -45,6 +45,18 @@ def test_default_config_matches_reference_defaults():
     # AGBNPForce.cpp:15
     assert (cfg.version, cfg.nonbonded_method, cfg.cutoff) == (1, _lib.NOCUTOFF, 1.0)
     assert (cfg.shard_rank, cfg.shard_count) == (0, 1)
+    assert cfg.tree_reuse_interval == 0          # the opt-in tree reuse is off: the reference rebuilds every evaluation
+
+
+def test_config_struct_matches_the_header():
+    """agbnp_b200_config is passed by pointer: the ctypes mirror must list the header's fields in the header's order."""
+    import re
+    text = open(_lib.HEADER_PATH).read()
+    body = text[text.index("typedef struct {"):text.index("} agbnp_b200_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(int|double)\s+(\w+)\s*;", body)
+    ctype = {"int": C.c_int, "double": C.c_double}
+    assert [(n, ctype[t]) for t, n in fields] == list(_lib.Config._fields_)
 
 
 def _create(cfg_mod, s):
