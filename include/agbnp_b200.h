@@ -105,8 +105,12 @@ int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, v
  * and by agbnp_b200_synchronize: capacities are grown ahead of need from the high-water marks every evaluation reports
  * (a capacity grows as soon as a high-water mark passes 90% of it, so an overflow needs a >11% jump in local packing
  * between two evaluations); if one happens anyway the call that
- * notices it returns ERR_CAPACITY naming the evaluation, which must be re-issued.  With h_energy != NULL (and in
- * agbnp_b200_execute_host) the call is synchronous and re-runs an overflowed evaluation itself.
+ * notices it returns ERR_CAPACITY naming the evaluation, which must be re-issued.  The call that reports a fault has
+ * itself enqueued ITS evaluation as usual (an error code never means "this call did nothing"); evaluations that were
+ * already in flight when the fault happened ran with the old capacities and are reported by the calls that retire them;
+ * the capacities grow once per fault.  With h_energy != NULL (and in agbnp_b200_execute_host) the call is synchronous and
+ * re-runs an overflowed evaluation itself; a pending fault of an earlier asynchronous evaluation is reported by it AFTER
+ * its own evaluation has completed (energy and forces of the synchronous evaluation are valid).
  * agbnp_b200_synchronize waits for the stream and retires every pending status. */
 int agbnp_b200_synchronize(agbnp_b200* h, void* stream);
 
@@ -141,7 +145,10 @@ typedef enum {
     AGBNP_B200_GET_DERIV_WU = 9,          /* double[N]  (W_i + U_i) before division by the atomic volume */
     AGBNP_B200_GET_NEIGHBOR_PAIRS = 10,   /* int[2*P]   (i<j) with r2 < cutoff2 as used by the GB pass (cutoff mode) */
     AGBNP_B200_GET_NEIGHBOR_COUNT = 11,   /* long long[1] P */
-    AGBNP_B200_GET_WORK_COUNTERS = 12     /* double[8]  P_gb, P_q(directed, evaluated), C2, C3+, M, tiles_gb, tiles_q, - */
+    AGBNP_B200_GET_WORK_COUNTERS = 12,    /* double[8]  P_gb, P_q(directed, evaluated), C2, C3+, M, tiles_gb, tiles_q, - */
+    AGBNP_B200_GET_STATS = 13             /* double[8]  since creation: capacity growths, spatial re-sorts, CUDA-graph instantiations,
+                                                         asynchronous evaluations found overflowed; now: nodes-per-root capacity,
+                                                         nodes-per-level capacity, level-2 neighbor capacity, 1 if a growth is pending */
 } agbnp_b200_get_what;
 
 int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);
@@ -169,8 +176,11 @@ typedef enum {
     AGBNP_B200_BUF_BSUM = 5      /* float[np]     partial Born-radius pair sums */
 } agbnp_b200_buffer;
 int agbnp_b200_shard_buffer(agbnp_b200* h, int which, void** d_ptr, size_t* bytes);
-/* h_energy == NULL: asynchronous.  Otherwise synchronises and returns ERR_CAPACITY if THIS shard overflowed (the caller
- * must agree on the outcome across ranks before re-running; sharding.py all-reduces the return code). */
+/* h_energy == NULL: asynchronous, with the deferred validation of agbnp_b200_execute_device (the status words are part of
+ * the ENERGY exchange, so a fault is seen by every shard, at the same call).  Otherwise synchronises and returns
+ * ERR_CAPACITY if ANY shard overflowed: the last kernel of phase 4 folds the shard's status word into the ENERGY buffer, the
+ * exchange sums it, and the finish kernel of every shard then withholds the delivery (sharding.py still all-reduces the
+ * return code before re-running, which covers callers whose exchange is not the library's). */
 int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int force_layout, int padded_n,
                             double* d_energy, double* h_energy);
 
@@ -184,15 +194,23 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
  * (any host-side all-gather) and hands them to every shard. */
 int agbnp_b200_peer_export(agbnp_b200* h, void* ipc_handle_64_bytes);
 int agbnp_b200_peer_import(agbnp_b200* h, const void* ipc_handles /* [shard_count][64] */, int shard_count);
+/* The same wiring when all shards live in ONE process (one host thread driving several GPUs, or several shards on one GPU):
+ * CUDA IPC handles cannot be opened by the process that exported them, so the mailboxes are linked directly (with
+ * cudaDeviceEnablePeerAccess between different devices).  shards[p] = handle of shard p; call it on every handle.  With a
+ * single host thread, issue the shards' calls of one evaluation on DIFFERENT streams and start with the position owner. */
+int agbnp_b200_peer_import_local(agbnp_b200* h, agbnp_b200* const* shards, int shard_count);
+/* The waits are bounded: a peer whose flag does not arrive within ~4 s (a dead process, shards driven out of step) makes the
+ * exchange give up; from then on the handle delivers nothing and reports ERR_CAPACITY with status bit 128 (peer timeout)
+ * instead of hanging the GPU. */
 int agbnp_b200_peer_exchange(agbnp_b200* h, int which /* agbnp_b200_buffer */, void* stream);
 /* positions (device float4[N], caller's order) from shard `owner` to every shard's own d_posq, same mechanism */
 int agbnp_b200_peer_broadcast(agbnp_b200* h, void* d_posq, int owner, void* stream);
 /* One whole sharded evaluation, asynchronous, in one call: position broadcast from `owner`, then the five phases with their
  * peer-memory exchanges and the finish kernel, enqueued back to back (the exchange kernels keep their epochs in device
  * memory, so no launch argument changes between evaluations).  Every shard must call it the same number of times.
- * A capacity overflow suppresses the delivery on the shard that overflowed only; use the phase-by-phase entry points
- * with agbnp_b200_shard_finish(h_energy != NULL) when the outcome must be agreed on (sharding.py does, once per context
- * and whenever it wants the energy on the host). */
+ * A capacity overflow on ANY shard suppresses the delivery on EVERY shard (the status words travel with the ENERGY exchange)
+ * and is reported, by every shard, by the call issued ASYNC_DEPTH-1 evaluations later -- after that call has enqueued its
+ * own full collective sequence, so the shards never fall out of step. */
 int agbnp_b200_shard_evaluate(agbnp_b200* h, void* d_posq, int owner, void* stream, void* d_force, int force_layout,
                               int padded_n, double* d_energy);
 

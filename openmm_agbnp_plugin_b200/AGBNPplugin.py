@@ -164,7 +164,7 @@ class CalcAGBNPForceKernel:
     def get(self, what):
         L = _lib.lib()
         sel = _lib.GET[what]
-        if what in ("SCALARS", "WORK_COUNTERS"):
+        if what in ("SCALARS", "WORK_COUNTERS", "STATS"):
             out = np.zeros(8)
         elif what in ("TREE_SIZE", "NEIGHBOR_COUNT"):
             out = np.zeros(1, dtype=np.int64)

@@ -37,7 +37,20 @@ struct PeerBox {
     int* counter;                       // local: [0] CTAs of the running kernel that have pushed, [1] that have finished
     int* epochs;                        // local: [PEER_KINDS] exchanges of each kind completed so far (device-side, so that the
                                         // launches carry no changing argument and a whole sharded evaluation is one CUDA graph)
+    int* status;                        // local, sticky: ST_PEER_TIMEOUT once a wait has given up (k_finish then delivers nothing)
 };
+
+// Wait until a peer's flag reaches `epoch`.  Bounded: a peer that never arrives (its process died, or the shards were driven
+// out of step) must not hang this GPU for ever -- after ~4 s of spinning the wait gives up, raises ST_PEER_TIMEOUT in the
+// status word (the evaluation then delivers nothing and the host reports it) and the kernel runs to completion.
+__device__ __forceinline__ void peer_wait(const volatile int* flag, int epoch, int* status) {
+    if (*flag >= epoch) return;
+    const long long t0 = clock64();
+    while (*flag < epoch) {
+        if (clock64() - t0 > 8000000000ll) { atomicOr(status, ST_PEER_TIMEOUT); break; }
+        __nanosleep(64);
+    }
+}
 
 template <class T> __device__ __forceinline__ T peer_add(T a, T b) { return a+b; }
 template <> __device__ __forceinline__ float4 peer_add<float4>(float4 a, float4 b) { return make_float4(a.x+b.x, a.y+b.y, a.z+b.z, a.w+b.w); }
@@ -65,7 +78,7 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(T* buf, size_t n, PeerBo
         }
         const volatile int* flags = (const volatile int*) (pb.mail[pb.rank] + pb.flag_off) + kind*PEER_MAX;
         for (int q = 0; q < pb.count; q++)
-            if (q != pb.rank) while (flags[q] < epoch) { }
+            if (q != pb.rank) peer_wait(flags+q, epoch, pb.status);
         __threadfence_system();
     }
     __syncthreads();
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__(256) k_peer_broadcast(float4* buf, size_t n, P
     } else {
         if (threadIdx.x == 0) {
             const volatile int* flags = (const volatile int*) (pb.mail[pb.rank] + pb.flag_off) + kind*PEER_MAX;
-            while (flags[owner] < epoch) { }
+            peer_wait(flags+owner, epoch, pb.status);
             __threadfence_system();
         }
         __syncthreads();
@@ -240,6 +253,8 @@ struct agbnp_b200 {
     bool async_pending[ASYNC_DEPTH] = {};
     long long async_issued = 0;
     bool async_fault = false;
+    int deferred_rc = 0;                    // outcome of an earlier asynchronous evaluation, reported by the next call that returns one
+    long long n_grow = 0, n_resort = 0, n_graph_inst = 0, n_async_fault = 0;    // AGBNP_B200_GET_STATS
     int ahead[16] = {};                     // capacities to grow before the next evaluation (grow_ahead)
     bool ahead_pending = false;
     // CUDA graphs of the whole kernel sequence, keyed by everything the launches bake in: `launch_gen` (bumped whenever
@@ -306,6 +321,14 @@ void alloc_tree_scratch(agbnp_b200* h) {
     static size_t tree_smem_max[64] = {};
     size_t& tmax = tree_smem_max[h->cfg.device & 63];
     if (smem > tmax) { tmax = smem; CK(cudaFuncSetAttribute(k_tree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024))); }
+    // k_tree_rescan (opt-in tree reuse) keeps parent / atom / flag per node in shared memory: 2 warps x (8 cap + 48) bytes
+    // passes 48 KB at cap ~3070, while k_tree is still in shared-memory mode up to cap ~5800
+    {
+        static size_t rescan_smem_max[64] = {};
+        size_t& rmax = rescan_smem_max[h->cfg.device & 63];
+        const size_t rs = h->tree_work_global ? 0 : h->tree_warps*rescan_work_bytes(h->tree_cap);
+        if (rs > rmax) { rmax = rs; CK(cudaFuncSetAttribute(k_tree_rescan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(rs, 1024))); }
+    }
     // k_tree_gamma: per-warp gamma_1..n and children sums, in shared memory while they fit
     {
         const size_t pw = gamma_work_bytes(h->tree_cap);
@@ -336,6 +359,7 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
     for (int i = 0; i < h->nh; i++) h->orig[i] = hv[i];
     for (int i = 0; i < h->nhy; i++) h->orig[h->nhp+i] = hy[i];
     h->order_valid = true;
+    h->n_resort++;
     h->tree_built = false;                  // the stored tree is indexed by the old order
     h->params_dirty = true;
     h->evals_since_sort = 0;
@@ -745,11 +769,19 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         else launch(h, k_tree_gamma<true>, h->gamma_grid, 32*h->gamma_warps, h->gamma_warps*gm.scratch_stride, s, gm);
         end(K_GAMMA);
     }
+    if ((phase_mask & PH_GAMMA) && h->cfg.shard_count > 1) {
+        // the status word joins the energy scalars, so that the ENERGY exchange tells every shard whether ANY shard overflowed
+        StatusFoldArgs sf{h->d_ctrl+CW_STATUS, h->d_scalars};
+        launch(h, k_status_fold, 1, 32, 0, s, sf);
+        h->launches++;
+    }
     if (phase_mask & PH_FINISH) {
         FinishArgs fa{};
         fa.np = h->np; fa.n = h->n; fa.orig = h->d_orig.p; fa.accL = h->d_accL; fa.accS = h->d_accS; fa.scalars = h->d_scalars;
         fa.inv_roffset = (float) (1.0/h->k.roffset);
         fa.status = h->d_ctrl+CW_STATUS;
+        fa.sharded = h->cfg.shard_count > 1;
+        fa.peer_fault = h->peer_ready ? h->peer.status : nullptr;
         fa.tree_ok_out = h->cur_eval_rescan ? nullptr : h->d_tree_ok.p;     // a build evaluation (in)validates the stored tree
         if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; fa.gb_scale = -2.0*h->k.dielectric_factor; }
         fa.padded_n = sink ? sink->padded_n : 0;
@@ -829,6 +861,7 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
         agbnp_b200::GraphEntry e{h->launch_gen, d_posq_in, sink->ptr, sink->layout, sink->padded_n, sink->d_energy, sharded, h->cur_eval_rescan, nullptr,
                                  (int) (h->launches-before), 0};
         h->launches = before;
+        h->n_graph_inst++;
         const cudaError_t ce = cudaGraphInstantiate(&e.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) throw CudaFail{std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)};
@@ -849,19 +882,31 @@ int fetch_status(agbnp_b200* h, cudaStream_t s) {
 }
 
 // grow whatever overflowed; returns false if a limit was hit.  ctrl = the evaluation's control words (host copy).
+// A real overflow reports a high-water mark above the capacity it was enqueued with; if the capacity has been grown past
+// that mark since (asynchronous evaluations that were already in flight when an earlier one faulted), nothing is grown
+// again: one fault, one growth.
 bool grow(agbnp_b200* h, const int* ctrl, bool ahead = false) {
     const int status = ctrl[CW_STATUS];
+    if (status & ST_PEER_TIMEOUT) return false;        // not a capacity problem: a peer never arrived (sticky)
+    const bool g_nbr = (status & ST_NBR_OVERFLOW) && (ahead || ctrl[CW_MAX_NBR] > h->nbrmax);
+    const bool g_node = (status & ST_NODE_OVERFLOW) && (ahead || ctrl[CW_MAX_NODES] > h->tree_cap);
+    const bool g_level = (status & ST_LEVEL_OVERFLOW) && (ahead || ctrl[CW_MAX_WIDTH] > h->tree_wcap);
+    const bool g_store = (status & ST_TREE_OVERFLOW) && (ahead || ctrl[CW_TREE_CURSOR] > h->st.cap);
+    if (!(g_nbr || g_node || g_level || g_store)) return true;
+    if (g_nbr && h->nbrmax >= 1024) return false;
+    if (g_node && h->tree_cap >= 16384) return false;
+    if (g_level && h->tree_wcap >= 16384) return false;
     CK(cudaDeviceSynchronize());                       // buffers below may still be in use by queued evaluations
-    bool tree = false;
+    h->n_grow++;
     // a real overflow doubles (its high-water mark is only a lower bound); growing ahead of need takes small steps so that
     // the work arrays keep fitting in shared memory
     auto bump = [ahead](int v, int seen) { return (std::max(ahead ? v + v/8 : 2*v, seen + seen/8) + 31)/32*32; };
-    if (status & ST_NBR_OVERFLOW) { if (h->nbrmax >= 1024) return false; h->nbrmax = std::min(1024, bump(h->nbrmax, ctrl[CW_MAX_NBR])); tree = true; }
-    if (status & ST_NODE_OVERFLOW) { if (h->tree_cap >= 16384) return false; h->tree_cap = std::min(16384, bump(h->tree_cap, ctrl[CW_MAX_NODES])); tree = true; }
-    if (status & ST_LEVEL_OVERFLOW) { if (h->tree_wcap >= 16384) return false; h->tree_wcap = std::min(16384, bump(h->tree_wcap, ctrl[CW_MAX_WIDTH])); tree = true; }
+    if (g_nbr) h->nbrmax = std::min(1024, bump(h->nbrmax, ctrl[CW_MAX_NBR]));
+    if (g_node) h->tree_cap = std::min(16384, bump(h->tree_cap, ctrl[CW_MAX_NODES]));
+    if (g_level) h->tree_wcap = std::min(16384, bump(h->tree_wcap, ctrl[CW_MAX_WIDTH]));
     h->tree_wcap = std::min(h->tree_wcap, h->tree_cap);
-    if (tree) alloc_tree_scratch(h);
-    if (status & ST_TREE_OVERFLOW) {
+    if (g_nbr || g_node || g_level) alloc_tree_scratch(h);
+    if (g_store) {
         const int need = ctrl[CW_TREE_CURSOR];
         alloc_store(h, std::max(need + need/4 + 4096, h->st.cap*2));
     }
@@ -920,7 +965,11 @@ int run_checked(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
             return AGBNP_B200_OK;
         }
         h->tree_built = false;
-        if (!grow(h, h->h_ctrl)) { h->err = "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")"; return AGBNP_B200_ERR_CAPACITY; }
+        if (!grow(h, h->h_ctrl)) {
+            h->err = (status & ST_PEER_TIMEOUT) ? "agbnp_b200: a peer-memory exchange timed out waiting for another shard; this handle no longer delivers results"
+                                                : "agbnp_b200: internal capacity limit exceeded (status " + std::to_string(status) + ")";
+            return AGBNP_B200_ERR_CAPACITY;
+        }
     }
     h->err = "agbnp_b200: capacity growth did not converge";
     return AGBNP_B200_ERR_CAPACITY;
@@ -937,30 +986,48 @@ int async_retire(agbnp_b200* h, long long k) {
         h->tree_built = false;
         const bool ok = grow(h, ctrl);
         h->async_fault = true;
-        h->err = std::string("agbnp_b200: asynchronous evaluation ") + std::to_string(k) + " overflowed an internal capacity (status "
-               + std::to_string(ctrl[CW_STATUS]) + "); its forces and energy were NOT delivered" + (ok ? "; capacities grown, re-issue it" : "");
+        h->n_async_fault++;
+        const bool peer_only = (ctrl[CW_STATUS] & ~ST_PEER_OVERFLOW) == 0;
+        h->err = std::string("agbnp_b200: asynchronous evaluation ") + std::to_string(k) + (peer_only ? " overflowed an internal capacity on another shard" :
+               " overflowed an internal capacity") + " (status " + std::to_string(ctrl[CW_STATUS]) + "); its forces and energy were NOT delivered"
+               + (h->cfg.shard_count > 1 ? " on any shard" : "") + (ok ? "; capacities grown, re-issue it" : "; a capacity limit was reached")
+               + ".  Evaluations enqueued since (including the one issued by the call that returned this) ran with the old capacities and are reported separately";
         return AGBNP_B200_ERR_CAPACITY;
     }
     grow_ahead(h, ctrl);
     return AGBNP_B200_OK;
 }
 
-// asynchronous evaluation: returns after enqueueing.  The status words travel to pinned memory behind the kernels and
-// are checked ASYNC_DEPTH-1 evaluations later (or by agbnp_b200_synchronize).
-int run_async(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
+// Book-keeping of an asynchronous evaluation, called right AFTER it has been enqueued on `s`: its status words follow it to
+// pinned memory (ring slot k % ASYNC_DEPTH), then the evaluation issued ASYNC_DEPTH-1 calls ago is retired and ITS outcome
+// is what the call returns.  Enqueue-then-check matters for sharded evaluations: every shard has enqueued the full
+// collective sequence of evaluation k before it looks at anything, so a fault on one shard can neither leave the peers'
+// exchange kernels waiting for flags that never come nor let the shards' evaluation counters (epochs, re-sort schedule)
+// drift apart; and since the status words are exchanged (SC_FAULT), all shards see the same fault at the same call.
+int async_post(agbnp_b200* h, cudaStream_t s) {
     const long long k = h->async_issued;
-    if (k >= agbnp_b200::ASYNC_DEPTH-1) {
-        const int rc = async_retire(h, k-(agbnp_b200::ASYNC_DEPTH-1));
-        if (rc != AGBNP_B200_OK) return rc;
-    }
-    launch_all(h, d_posq_in, s, sink);
     const int slot = (int) (k % agbnp_b200::ASYNC_DEPTH);
+    if (h->async_pending[slot]) {                    // cannot happen in steady state (retired by the previous call)
+        const int rc = async_retire(h, k-agbnp_b200::ASYNC_DEPTH);
+        if (rc != AGBNP_B200_OK) h->deferred_rc = rc;
+    }
     CK(cudaMemcpyAsync(h->h_async + slot*CW_COUNT, h->d_ctrl, sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(h->async_ev[slot], s));
     h->async_pending[slot] = true;
     h->async_issued++;
     h->evals_since_sort++; h->total_evals++;
-    return AGBNP_B200_OK;
+    int rc = AGBNP_B200_OK;
+    if (k >= agbnp_b200::ASYNC_DEPTH-1) rc = async_retire(h, k-(agbnp_b200::ASYNC_DEPTH-1));
+    if (rc == AGBNP_B200_OK && h->deferred_rc != AGBNP_B200_OK) { rc = h->deferred_rc; }
+    h->deferred_rc = AGBNP_B200_OK;
+    return rc;
+}
+
+// asynchronous evaluation: returns after enqueueing.  The status words travel to pinned memory behind the kernels and
+// are checked ASYNC_DEPTH-1 evaluations later (or by agbnp_b200_synchronize).
+int run_async(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const ForceSink* sink) {
+    launch_all(h, d_posq_in, s, sink);
+    return async_post(h, s);
 }
 
 int async_drain(agbnp_b200* h) {
@@ -1054,6 +1121,12 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         CK(cudaFuncSetAttribute(k_deriv<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, deriv_smem));
         CK(cudaFuncSetAttribute(k_deriv<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, deriv_smem));
         CK(cudaFuncSetAttribute(k_deriv<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, deriv_smem));
+        if (const char* ic = std::getenv("AGBNP_B200_INIT_CAPS")) {     // tests: start from small capacities to exercise the growth paths
+            int a = 0, b = 0, c = 0;
+            if (std::sscanf(ic, "%d,%d,%d", &a, &b, &c) == 3 && a >= 32 && b >= 32 && c >= 8) {
+                h->tree_cap = a; h->tree_wcap = std::min(a, b); h->nbrmax = c;
+            }
+        }
         alloc_tree_scratch(h);
         CK(cudaMallocHost((void**) &h->h_posq, sizeof(float4)*n));
         CK(cudaMallocHost((void**) &h->h_force, sizeof(float)*3*n));
@@ -1096,7 +1169,8 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         static long ncall = 0;
         auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = timing ? now() : 0;
-        if (async_drain(h) != AGBNP_B200_OK) return AGBNP_B200_ERR_CAPACITY;
+        const int rc_deferred = async_drain(h);      // a fault of an earlier asynchronous evaluation is reported by this call
+        std::string deferred_msg = h->err;
         pack_positions(pos, (float*) h->h_posq, h->n);
         CK(cudaMemcpyAsync(h->d_posq_in.p, h->h_posq, sizeof(float4)*h->n, cudaMemcpyHostToDevice, s));
         const double t1 = timing ? now() : 0;
@@ -1121,7 +1195,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         grow_ahead(h, h->h_ctrl);
         const double t4 = timing ? now() : 0;
         if (include_forces && forces) add_forces(h->h_force, forces, 3*h->n);
-        if (energy) *energy = include_energy ? h->h_scal[SC_SPARE0] : 0.0;
+        if (energy) *energy = include_energy ? h->h_scal[SC_TOTAL] : 0.0;
         if (timing) {
             const double t5 = now();
             acc[0] += t1-t0; acc[1] += t2-t1; acc[2] += t3-t2; acc[3] += t4-t3; acc[4] += t5-t4;
@@ -1131,6 +1205,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
                 for (double& a : acc) a = 0;
             }
         }
+        if (rc_deferred != AGBNP_B200_OK) { h->err = deferred_msg; return rc_deferred; }
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
@@ -1145,10 +1220,12 @@ int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, v
         prepare(h, nullptr, 0, d_posq, s);
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
         if (!h_energy) return run_async(h, (const float4*) d_posq, s, &sink);
-        if (async_drain(h) != AGBNP_B200_OK) return AGBNP_B200_ERR_CAPACITY;
+        const int rc_deferred = async_drain(h);      // a fault of an earlier asynchronous evaluation is reported by this call
+        const std::string deferred_msg = h->err;
         const int rc = run_checked(h, (const float4*) d_posq, s, &sink);
         if (rc != AGBNP_B200_OK) return rc;
-        *h_energy = h->h_scal[SC_SPARE0];
+        *h_energy = h->h_scal[SC_TOTAL];
+        if (rc_deferred != AGBNP_B200_OK) { h->err = deferred_msg; return rc_deferred; }
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
@@ -1260,7 +1337,7 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             CK(cudaMemcpy(&cm, h->d_counters+CT_M, sizeof(cm), cudaMemcpyDeviceToHost));
             const double ir = (double) (float) (1.0/h->k.roffset);          // the factor k_finish applies
             od[0] = sc[SC_EVOL_L]*ir; od[1] = -sc[SC_EVOL_S]*ir; od[2] = sc[SC_EGB]; od[3] = sc[SC_EVDW];
-            od[4] = sc[SC_VOL_L]; od[5] = sc[SC_VOL_S]; od[6] = sc[SC_SPARE0]; od[7] = (double) cm;
+            od[4] = sc[SC_VOL_L]; od[5] = sc[SC_VOL_S]; od[6] = sc[SC_TOTAL]; od[7] = (double) cm;
             break;
         }
         case AGBNP_B200_GET_WORK_COUNTERS: {
@@ -1268,6 +1345,12 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             unsigned long long c[CT_COUNT];
             CK(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
             for (int i = 0; i < 8; i++) od[i] = (double) c[i];
+            break;
+        }
+        case AGBNP_B200_GET_STATS: {
+            need(sizeof(double)*8);
+            od[0] = (double) h->n_grow; od[1] = (double) h->n_resort; od[2] = (double) h->n_graph_inst; od[3] = (double) h->n_async_fault;
+            od[4] = h->tree_cap; od[5] = h->tree_wcap; od[6] = h->nbrmax; od[7] = h->ahead_pending ? 1.0 : 0.0;
             break;
         }
         case AGBNP_B200_GET_TREE_SIZE: {
@@ -1390,8 +1473,12 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
         cudaStream_t s = (cudaStream_t) stream;
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
         enqueue(h, nullptr, s, PH_FINISH, &sink);
+        // asynchronous: the status words follow the evaluation through the same ring as agbnp_b200_execute_device's; the
+        // call returns the outcome of the evaluation issued ASYNC_DEPTH-1 calls ago (identical on every shard: SC_FAULT)
+        if (!h_energy) return async_post(h, s);
         h->evals_since_sort++; h->total_evals++;
-        if (!h_energy) return AGBNP_B200_OK;        // asynchronous: status is checked by the next synchronous finish
+        const int rc_deferred = async_drain(h);
+        const std::string deferred_msg = h->err;
         const int status = fetch_status(h, s);
         if (status != 0) {
             h->tree_built = false;
@@ -1400,7 +1487,8 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
             return AGBNP_B200_ERR_CAPACITY;
         }
         grow_ahead(h, h->h_ctrl);
-        *h_energy = h->h_scal[SC_SPARE0];
+        *h_energy = h->h_scal[SC_TOTAL];
+        if (rc_deferred != AGBNP_B200_OK) { h->err = deferred_msg; return rc_deferred; }
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
@@ -1424,19 +1512,53 @@ void peer_layout(agbnp_b200* h) {
 }
 }
 
+namespace {
+void ensure_mailbox(agbnp_b200* h) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->d_mailbox) return;
+    peer_layout(h);
+    CK(cudaMalloc((void**) &h->d_mailbox, h->mailbox_bytes));
+    CK(cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
+    CK(cudaMalloc((void**) &h->d_peer_counter, sizeof(int)*(3+PEER_KINDS)));
+    CK(cudaMemset(h->d_peer_counter, 0, sizeof(int)*(3+PEER_KINDS)));
+    CK(cudaDeviceSynchronize());
+}
+void peer_bind(agbnp_b200* h, int shard_count) {
+    h->peer.rank = h->cfg.shard_rank; h->peer.count = shard_count; h->peer.counter = h->d_peer_counter; h->peer.epochs = h->d_peer_counter+2;
+    h->peer.status = h->d_peer_counter+2+PEER_KINDS;
+}
+}
+
+int agbnp_b200_peer_import_local(agbnp_b200* h, agbnp_b200* const* shards, int shard_count) {
+    if (!h || !shards || shard_count != h->cfg.shard_count || shard_count > PEER_MAX) return AGBNP_B200_ERR_ARG;
+    try {
+        for (int p = 0; p < shard_count; p++) {
+            agbnp_b200* q = shards[p];
+            if (!q || q->cfg.shard_count != shard_count || q->cfg.shard_rank != p || q->n != h->n) {
+                h->err = "agbnp_b200_peer_import_local: shards[p] must be the handle of shard p of the same system"; return AGBNP_B200_ERR_ARG;
+            }
+            ensure_mailbox(q);
+        }
+        CK(cudaSetDevice(h->cfg.device));
+        peer_bind(h, shard_count);
+        for (int p = 0; p < shard_count; p++) {
+            if (shards[p]->cfg.device != h->cfg.device) {
+                const cudaError_t ce = cudaDeviceEnablePeerAccess(shards[p]->cfg.device, 0);
+                if (ce == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (ce != cudaSuccess) throw CudaFail{std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(ce)};
+            }
+            h->peer.mail[p] = shards[p]->d_mailbox;
+        }
+        h->peer_ready = true;
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
 int agbnp_b200_peer_export(agbnp_b200* h, void* ipc_handle) {
     if (!h || !ipc_handle) return AGBNP_B200_ERR_ARG;
     if (h->cfg.shard_count > PEER_MAX) { h->err = "agbnp_b200_peer_export: at most 8 shards"; return AGBNP_B200_ERR_ARG; }
     try {
-        CK(cudaSetDevice(h->cfg.device));
-        if (!h->d_mailbox) {
-            peer_layout(h);
-            CK(cudaMalloc((void**) &h->d_mailbox, h->mailbox_bytes));
-            CK(cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
-            CK(cudaMalloc((void**) &h->d_peer_counter, sizeof(int)*(2+PEER_KINDS)));
-            CK(cudaMemset(h->d_peer_counter, 0, sizeof(int)*(2+PEER_KINDS)));
-            CK(cudaDeviceSynchronize());
-        }
+        ensure_mailbox(h);
         cudaIpcMemHandle_t hd;
         CK(cudaIpcGetMemHandle(&hd, h->d_mailbox));
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1449,7 +1571,7 @@ int agbnp_b200_peer_import(agbnp_b200* h, const void* ipc_handles, int shard_cou
     if (!h || !ipc_handles || shard_count != h->cfg.shard_count || !h->d_mailbox) return AGBNP_B200_ERR_ARG;
     try {
         CK(cudaSetDevice(h->cfg.device));
-        h->peer.rank = h->cfg.shard_rank; h->peer.count = shard_count; h->peer.counter = h->d_peer_counter; h->peer.epochs = h->d_peer_counter+2;
+        peer_bind(h, shard_count);
         for (int p = 0; p < shard_count; p++) {
             if (p == h->cfg.shard_rank) { h->peer.mail[p] = h->d_mailbox; continue; }
             cudaIpcMemHandle_t hd;
@@ -1498,20 +1620,9 @@ int agbnp_b200_shard_evaluate(agbnp_b200* h, void* d_posq, int owner, void* stre
         h->launches += 1;
         prepare(h, nullptr, 0, d_posq, s);                  // (re)sorting reads the broadcast positions; same evaluation count on every shard
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
-        // deferred validation, as in the asynchronous single-GPU path: the status words of this evaluation follow it to
-        // pinned memory and are examined ASYNC_DEPTH-1 calls later (capacities grow ahead of need from the high-water marks)
-        const long long k = h->async_issued;
-        if (k >= agbnp_b200::ASYNC_DEPTH-1) {
-            const int rc = async_retire(h, k-(agbnp_b200::ASYNC_DEPTH-1));
-            if (rc != AGBNP_B200_OK) return rc;
-        }
         launch_all(h, (const float4*) d_posq, s, &sink, true);
-        const int slot = (int) (k % agbnp_b200::ASYNC_DEPTH);
-        CK(cudaMemcpyAsync(h->h_async + slot*CW_COUNT, h->d_ctrl, sizeof(int)*CW_COUNT, cudaMemcpyDeviceToHost, s));
-        CK(cudaEventRecord(h->async_ev[slot], s));
-        h->async_pending[slot] = true;
-        h->async_issued++;
-        h->evals_since_sort++; h->total_evals++;
+        // deferred validation, as in the asynchronous single-GPU path -- AFTER the whole collective sequence is enqueued
+        return async_post(h, s);
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }

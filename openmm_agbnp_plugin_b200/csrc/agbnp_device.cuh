@@ -20,10 +20,12 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // status bits written by kernels when a capacity is exceeded (host grows the buffer and re-runs the evaluation)
 enum StatusBits { ST_NBR_OVERFLOW = 1, ST_NODE_OVERFLOW = 2, ST_LEVEL_OVERFLOW = 4, ST_TREE_OVERFLOW = 8, ST_PAIRLIST_OVERFLOW = 16,
-                  ST_TREE_STALE = 32 /* a rescan found no valid stored tree (its build evaluation overflowed): rebuild */ };
+                  ST_TREE_STALE = 32 /* a rescan found no valid stored tree (its build evaluation overflowed): rebuild */,
+                  ST_PEER_OVERFLOW = 64 /* sharded evaluation: another shard overflowed, nothing was delivered here either */,
+                  ST_PEER_TIMEOUT = 128 /* peer-memory exchange: a peer's flag did not arrive within the spin limit */ };
 
 // energy / diagnostic scalar slots (double)
-enum ScalarSlot { SC_EVOL_L = 0, SC_EVOL_S = 1, SC_EGB = 2, SC_EVDW = 3, SC_VOL_L = 4, SC_VOL_S = 5, SC_SPARE0 = 6, SC_SPARE1 = 7, SC_COUNT = 8 };
+enum ScalarSlot { SC_EVOL_L = 0, SC_EVOL_S = 1, SC_EGB = 2, SC_EVDW = 3, SC_VOL_L = 4, SC_VOL_S = 5, SC_TOTAL = 6, SC_FAULT = 7, SC_COUNT = 8 };
 // work counters (unsigned long long)
 enum CounterSlot { CT_PGB = 0, CT_PQ = 1, CT_C2 = 2, CT_C3 = 3, CT_M = 4, CT_TILES_GB = 5, CT_TILES_Q = 6, CT_SPARE = 7, CT_COUNT = 8 };
 

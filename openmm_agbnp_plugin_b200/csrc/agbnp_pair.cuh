@@ -761,23 +761,42 @@ struct FinishArgs {
     float* out_set;                     // internal: float[3n] interleaved, = (host path)
     int padded_n;
     double* scalars;                    // SC_* terms
-    const int* status;                  // capacity-overflow bits of this evaluation: nothing is delivered unless 0
+    int* status;                        // capacity-overflow bits of this evaluation: nothing is delivered unless 0
+    int sharded;                        // scalars[SC_FAULT] holds the number of shards whose status word is non-zero (k_status_fold + ENERGY exchange)
+    const int* peer_fault;              // peer-memory exchange: non-zero once a wait for a peer has timed out (sticky), or null
     int* tree_ok_out;                   // build evaluations: 1 if the tree was built without overflow (read by k_tree_rescan)
     double* energy_accum;               // optional device accumulator (+=)
     double* energy_out;                 // optional device/pinned-mapped slot (=)
 };
 
+// sharded evaluations: this shard's status word, as 0/1, into the energy scalars, which the ENERGY exchange sums over the shards
+struct StatusFoldArgs { const int* status; double* scalars; };
+__global__ void k_status_fold(StatusFoldArgs A) {
+    pdl_release();
+    pdl_acquire();
+    if (threadIdx.x == 0) A.scalars[SC_FAULT] = *A.status != 0 ? 1.0 : 0.0;
+}
+
 __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     pdl_release();
     pdl_acquire();
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
-    const bool bad = A.status && *A.status != 0;
+    // sharded: every shard withholds the delivery when ANY shard overflowed (the shards' status words were summed into
+    // SC_FAULT by the ENERGY exchange), and the host of a shard that did not overflow itself learns it from ST_PEER_OVERFLOW
+    const bool mine = A.status && *A.status != 0;
+    const bool peers = A.sharded && A.scalars[SC_FAULT] != 0.0;
+    const bool dead = A.peer_fault && *A.peer_fault != 0;
+    const bool bad = mine || peers || dead;
     if (k == 0 && A.tree_ok_out) *A.tree_ok_out = bad ? 0 : 1;
-    if (bad) return;
+    if (bad) {
+        __syncthreads();                // every thread of CTA 0 has read the status word before thread 0 changes it
+        if (k == 0 && !mine) atomicOr(A.status, dead ? ST_PEER_TIMEOUT : ST_PEER_OVERFLOW);
+        return;
+    }
     if (k == 0) {
         // E1 + E2 (ReferenceAGBNPKernels.cpp:188,233,266) + GB + vdW
         const double e = (A.scalars[SC_EVOL_L] - A.scalars[SC_EVOL_S])*(double) A.inv_roffset + A.scalars[SC_EGB] + A.scalars[SC_EVDW];
-        A.scalars[SC_SPARE0] = e;
+        A.scalars[SC_TOTAL] = e;
         if (A.energy_out) *A.energy_out = e;
         if (A.energy_accum) atomicAdd(A.energy_accum, e);
     }

@@ -91,6 +91,16 @@ class CudaShardKernel:
         self.peer = all(flags)
         return self.peer
 
+    @staticmethod
+    def setup_peer_local(kernels):
+        """All shards in THIS process (one host thread driving several GPUs, or several shards on one GPU in the tests):
+        link the mailboxes directly (agbnp_b200_peer_import_local)."""
+        L = _lib.lib()
+        arr = (C.c_void_p * len(kernels))(*[k.handle for k in kernels])
+        for k in kernels:
+            k._check(L.agbnp_b200_peer_import_local(k.handle, arr, len(kernels)))
+            k.peer = True
+
     def broadcast(self, d_posq, owner, stream):
         self._check(_lib.lib().agbnp_b200_peer_broadcast(self.handle, C.c_void_p(d_posq.data_ptr()), owner, C.c_void_p(stream)))
 

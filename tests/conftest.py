@@ -67,3 +67,15 @@ def golden():
 @pytest.fixture(scope="session")
 def ref_outputs():
     return np.load(os.path.join(GOLDEN, "ref_outputs.npz"))
+
+
+@pytest.fixture(scope="session")
+def ref_large():
+    """Outputs of the compiled, unmodified reference on 1dwc, 2clr and the full-size HIV-RT stand-in (tools/make_golden.py)."""
+    return np.load(os.path.join(GOLDEN, "ref_outputs_large.npz"))
+
+
+def pair_keys(pairs, n):
+    """(i<j) pair list -> sorted int64 keys, for set comparison of million-pair lists without Python sets"""
+    p = np.asarray(pairs, dtype=np.int64)
+    return np.sort(p[:, 0] * n + p[:, 1])

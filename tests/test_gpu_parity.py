@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import load_system, sys_args, relrms, gpu_topology
+from conftest import load_system, sys_args, relrms, gpu_topology, pair_keys
 import openmm_agbnp_plugin_b200 as plug
 from openmm_agbnp_plugin_b200 import systems, _lib
 from oracle import portlib
@@ -109,6 +109,69 @@ def test_2clr_full_size():
     assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
     assert abs(e - e_ref) <= E_TOL * abs(e_ref)
     assert relrms(f, f_ref) <= F_TOL
+
+
+@pytest.mark.parametrize("name", ["1dwc", "2clr"])
+def test_baseline_md_systems_nocutoff_against_the_compiled_reference(name, ref_large):
+    """BASELINE configs 2 and 3 (1dwc: 4152 atoms, 2clr: 5983 atoms), NoCutoff, against the committed outputs of the
+    reference's own Reference platform compiled unmodified (ReferenceAGBNPKernels.cpp:274-795; tools/make_golden.py), and
+    node for node against the restatement's tree."""
+    s = load_system(name)
+    pos = systems.float_rounded(s["pos"])
+    ctx, e, f = _gpu(s, pos, 1)
+    k = ctx.kernel
+    e_ref, f_ref = float(ref_large[name + "_v1_energy"]), ref_large[name + "_v1_forces"]
+    assert int(k.get("TREE_SIZE")[0]) == int(ref_large[name + "_v1_tree_size"]) - 1 - len(pos)
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+    assert relrms(k.get("SELF_VOLUME_VDW"), ref_large[name + "_self_volume"]) <= 1e-5
+    assert np.abs(k.get("BORN_RADIUS") / ref_large[name + "_born_radius"] - 1).max() <= 1e-5
+    o = portlib.OracleKernel(1, *sys_args(s))
+    o.execute(pos)
+    assert gpu_topology(k.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
+
+
+@pytest.mark.parametrize("name,cutoff", [("1dwc", 1.2), ("2clr", 1.2)])
+def test_baseline_md_systems_cutoff(name, cutoff):
+    """BASELINE configs 2 and 3 as benchmarked: CutoffNonPeriodic 1.2 nm.  The Reference platform has no cutoff; the
+    convention is the OpenCL platform's (pairs with r2 < rc2, no switching: AGBNPGBEnergy.cl:313, AGBNPBornRadii.cl:430),
+    restated in the oracle ("parity unpinned" by any reference test): neighbor membership must be identical pair for
+    pair, the overlap tree (which the cutoff does not touch) node for node."""
+    s = load_system(name)
+    pos = systems.float_rounded(s["pos"])
+    n = len(pos)
+    o = portlib.OracleKernel(1, *sys_args(s), nonbonded_method=portlib.CutoffNonPeriodic, cutoff=cutoff)
+    e_ref, f_ref = o.execute(pos)
+    ctx, e, f = _gpu(s, pos, 1, plug.AGBNPForce.CutoffNonPeriodic, cutoff)
+    pg = ctx.kernel.get("NEIGHBOR_PAIRS")
+    pr = portlib.neighbor_pairs(pos.astype(np.float32), cutoff)
+    assert len(pg) == len(pr)
+    assert np.array_equal(pair_keys(pg, n), pair_keys(pr, n))
+    assert int(ctx.kernel.get("WORK_COUNTERS")[0]) == len(pr)
+    assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+
+
+def test_hivrt_standin_full_size_against_the_compiled_reference(ref_large):
+    """The headline workload at full size (2clr x 3 stand-in, N = 17 949, 0.98 M overlaps) against the committed outputs of
+    the compiled, unmodified Reference platform, plus the whole overlap tree node for node against the restatement (which is
+    bit-identical to the compiled reference, tests/test_oracle.py) -- the parity that bench.py used to check privately."""
+    s = systems.hivrt()
+    if not s["name"].startswith("hivrt-standin"):
+        pytest.skip("the real hivrt_agbnp1.dms is present; the committed golden outputs are those of the stand-in")
+    pos = systems.float_rounded(s["pos"])
+    ctx, e, f = _gpu(s, pos, 1)
+    k = ctx.kernel
+    e_ref, f_ref = float(ref_large["hivrt_standin_v1_energy"]), ref_large["hivrt_standin_v1_forces"]
+    assert int(k.get("TREE_SIZE")[0]) == int(ref_large["hivrt_standin_v1_tree_size"]) - 1 - len(pos)
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+    assert relrms(k.get("SELF_VOLUME_VDW"), ref_large["hivrt_standin_self_volume"]) <= 1e-5
+    assert np.abs(k.get("BORN_RADIUS") / ref_large["hivrt_standin_born_radius"] - 1).max() <= 1e-5
+    o = portlib.OracleKernel(1, *sys_args(s))
+    o.execute(pos)
+    assert gpu_topology(k.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree())
 
 
 def test_hivrt_size_properties():

@@ -198,3 +198,145 @@ def test_two_shards_with_tree_reuse(monkeypatch):
             assert relrms(d_f.cpu().numpy().astype(np.float64), f_ref) <= 1e-4
     for k in ks:
         k.close()
+
+
+def _shard_pair_on_one_gpu(force, monkeypatch=None, caps_for_shard1=None):
+    """Two shard handles in this process, both on GPU 0, wired through the library's peer-memory exchange."""
+    ks = []
+    for r in range(2):
+        if r == 1 and caps_for_shard1:
+            monkeypatch.setenv("AGBNP_B200_INIT_CAPS", caps_for_shard1)
+        ks.append(sharding.CudaShardKernel(force, 0, r, 2))
+        if r == 1 and caps_for_shard1:
+            monkeypatch.delenv("AGBNP_B200_INIT_CAPS")
+    sharding.CudaShardKernel.setup_peer_local(ks)
+    return ks
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300, method="thread")
+@pytest.mark.parametrize("method,cutoff", [(0, 1.0), (1, 1.2)])
+def test_peer_memory_exchange_two_shards_one_gpu(method, cutoff):
+    """The multi-GPU path that bench.py --gpus N actually runs -- k_peer_broadcast, k_peer_allreduce and
+    agbnp_b200_shard_evaluate -- driven on ONE GPU: two shard handles on two streams exchange through each other's
+    mailboxes (linked with agbnp_b200_peer_import_local; between processes the same mailboxes are opened through CUDA IPC).
+    Every shard must end with the unsharded result."""
+    import openmm_agbnp_plugin_b200 as plug
+    from openmm_agbnp_plugin_b200 import systems, _lib
+    from conftest import load_system, relrms
+    import ctypes as C
+    s = load_system("1li2")
+    pos = systems.float_rounded(s["pos"])
+    n = len(pos)
+    force = systems.make_force(s, 1, method, cutoff)
+    ctx = plug.Context(force)
+    ctx.setPositions(pos)
+    e_ref = ctx.calcForcesAndEnergy()
+    f_ref = ctx.getForces().copy()
+    ks = _shard_pair_on_one_gpu(force)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    sp = [st.cuda_stream for st in streams]
+    posq = torch.zeros((n, 4), dtype=torch.float32)
+    posq[:, :3] = torch.from_numpy(pos.astype(np.float32))
+    d_posq = [posq.cuda(), torch.zeros((n, 4), dtype=torch.float32, device="cuda")]      # only the owner (shard 0) has positions
+    torch.cuda.synchronize()
+
+    # (a) phase by phase with explicit exchanges, synchronous finish: settles the capacities
+    for attempt in range(4):
+        for r in (0, 1):
+            ks[r].broadcast(d_posq[r], 0, sp[r])
+        for ph in range(sharding.N_PHASES):
+            for r in (0, 1):
+                ks[r].phase(ph, d_posq[r] if ph == 0 else None, sp[r])
+            for name in sharding.EXCHANGES[ph]:
+                for r in (0, 1):
+                    ks[r].exchange(name, sp[r])
+        outs = []
+        for r in (0, 1):
+            d_f = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+            rc, e = ks[r].finish(sp[r], d_f, 0, n, None, True)
+            outs.append((rc, e, d_f))
+        if all(rc == 0 for rc, _, _ in outs):
+            break
+        assert all(rc != 0 for rc, _, _ in outs)          # a fault is seen by BOTH shards
+    assert torch.equal(d_posq[0], d_posq[1])              # the broadcast delivered the owner's positions
+    for rc, e, d_f in outs:
+        assert rc == 0
+        assert abs(e - e_ref) <= 2e-6*abs(e_ref)
+        assert relrms(d_f.cpu().numpy().astype(np.float64), f_ref) <= 1e-5
+
+    # (b) the one-call asynchronous evaluation, several in flight
+    L = _lib.lib()
+    d_e = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in (0, 1)]
+    d_f = [torch.zeros((n, 3), dtype=torch.float32, device="cuda") for _ in (0, 1)]
+    torch.cuda.synchronize()
+    nev = 6
+    for it in range(nev):
+        for r in (0, 1):                                  # the position owner first (single host thread)
+            ks[r].evaluate_graph(d_posq[r], 0, sp[r], d_f[r], 0, n, d_e[r])
+    for r in (0, 1):
+        assert L.agbnp_b200_synchronize(ks[r].handle, C.c_void_p(sp[r])) == 0
+    for r in (0, 1):
+        assert abs(d_e[r].item()/nev - e_ref) <= 2e-6*abs(e_ref)
+        assert relrms(d_f[r].cpu().numpy().astype(np.float64)/nev, f_ref) <= 1e-5
+    for k in ks:
+        k.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300, method="thread")
+def test_overflow_on_one_shard_withholds_delivery_on_all(monkeypatch):
+    """A capacity overflow on ONE shard of an asynchronous sharded evaluation: no shard may deliver forces that lack the
+    other's partial sums, every shard must report the fault for the same evaluation, nobody may hang, and the shards must
+    stay in step (the evaluations after the growth are complete and correct)."""
+    import openmm_agbnp_plugin_b200 as plug
+    from openmm_agbnp_plugin_b200 import systems, _lib
+    from conftest import load_system, relrms
+    import ctypes as C
+    s = load_system("1li2")
+    pos = systems.float_rounded(s["pos"])
+    n = len(pos)
+    force = systems.make_force(s, 1, 0, 1.0)
+    ctx = plug.Context(force)
+    ctx.setPositions(pos)
+    e_ref = ctx.calcForcesAndEnergy()
+    f_ref = ctx.getForces().copy()
+    ks = _shard_pair_on_one_gpu(force, monkeypatch, caps_for_shard1="64,32,16")     # shard 1 cannot hold its subtrees
+    L = _lib.lib()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    sp = [st.cuda_stream for st in streams]
+    posq = torch.zeros((n, 4), dtype=torch.float32)
+    posq[:, :3] = torch.from_numpy(pos.astype(np.float32))
+    d_posq = [posq.cuda(), torch.zeros((n, 4), dtype=torch.float32, device="cuda")]
+    torch.cuda.synchronize()
+
+    def run(count):
+        d_f = [torch.zeros((n, 3), dtype=torch.float32, device="cuda") for _ in (0, 1)]
+        d_e = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in (0, 1)]
+        torch.cuda.synchronize()
+        rcs = [[], []]
+        for it in range(count):
+            for r in (0, 1):
+                rcs[r].append(L.agbnp_b200_shard_evaluate(ks[r].handle, C.c_void_p(d_posq[r].data_ptr()), 0, C.c_void_p(sp[r]),
+                                                          C.c_void_p(d_f[r].data_ptr()), 0, n, C.c_void_p(d_e[r].data_ptr())))
+        for r in (0, 1):
+            rcs[r].append(L.agbnp_b200_synchronize(ks[r].handle, C.c_void_p(sp[r])))
+        return rcs, d_f, d_e
+
+    rcs, d_f, d_e = run(1)
+    assert rcs[0] == rcs[1] == [0, _lib.ERR_CAPACITY]        # reported by BOTH shards, by the same call
+    for r in (0, 1):
+        assert float(d_f[r].abs().max().item()) == 0.0 and d_e[r].item() == 0.0      # nothing was delivered anywhere
+        assert b"NOT delivered" in L.agbnp_b200_last_error(ks[r].handle)
+    # growth may take more than one round (each fault doubles what overflowed); afterwards everything is delivered
+    for attempt in range(8):
+        rcs, d_f, d_e = run(5)
+        assert rcs[0] == rcs[1]
+        if all(rc == 0 for rc in rcs[0]):
+            break
+    assert all(rc == 0 for rc in rcs[0])
+    for r in (0, 1):
+        assert abs(d_e[r].item()/5 - e_ref) <= 2e-6*abs(e_ref)
+        assert relrms(d_f[r].cpu().numpy().astype(np.float64)/5, f_ref) <= 1e-5
+    for k in ks:
+        k.close()

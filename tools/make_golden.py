@@ -6,6 +6,8 @@
   golden.json      the numbers printed in platforms/reference/tests/{v0,v1}.reference (the reference's golden outputs)
   ref_outputs.npz  full-precision outputs of the compiled, unmodified reference (oracle/_ref) on gaussvol, trpcage and
                    rnaseh with float-rounded positions: energies, forces, self-volumes, Born radii, tree sizes
+  ref_outputs_large.npz  the same for the BASELINE systems 1dwc and 2clr and for the full-size HIV-RT stand-in "2clr x 3"
+                   (N = 17 949; systems.hivrt()), AGBNP1 only (ReferenceAGBNPKernels.cpp:274-795): ~15 s of CPU
 """
 import json
 import os
@@ -82,6 +84,22 @@ def main():
             print(name, v, "%.10g" % e, k.tree_size())
             k.close()
     np.savez_compressed(os.path.join(OUT, "ref_outputs.npz"), **out)
+
+    from openmm_agbnp_plugin_b200 import systems as psys
+    big = {}
+    for name in ("1dwc", "2clr", "hivrt_standin"):
+        s = psys.load(name)
+        pos = psys.float_rounded(s["pos"])
+        k = reflib.ReferenceKernel(1, s["radius"], s["gamma"], s["alpha"], s["charge"], s["ishydrogen"])
+        e, f = k.execute(pos)
+        big["%s_v1_energy" % name] = np.array(e)
+        big["%s_v1_forces" % name] = f
+        big["%s_v1_tree_size" % name] = np.array(k.tree_size())
+        big["%s_self_volume" % name] = k.get("self_volume")
+        big["%s_born_radius" % name] = k.get("born_radius")
+        print(name, 1, "%.10g" % e, k.tree_size())
+        k.close()
+    np.savez_compressed(os.path.join(OUT, "ref_outputs_large.npz"), **big)
 
 
 if __name__ == "__main__":
