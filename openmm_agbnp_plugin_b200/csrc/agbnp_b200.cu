@@ -135,6 +135,17 @@ struct CudaFail { std::string msg; };
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     throw CudaFail{std::string(#call) + ": " + cudaGetErrorString(e_)}; } } while (0)
 
+// Buffers replaced while a handle is in use (capacity growth, re-sort) are not cudaFree'd on the spot: cudaFree waits for ALL
+// work on the device, including kernels of OTHER handles -- and a peer shard's exchange kernel may be spinning for this very
+// handle's next launch (several shards on one GPU).  Inside a TrashScope they are parked in the handle's trash list instead
+// and freed when the handle is destroyed (growth is geometric and rare: the parked memory is less than what is in use).
+thread_local std::vector<void*>* g_trash = nullptr;
+struct TrashScope {
+    std::vector<void*>* prev;
+    explicit TrashScope(std::vector<void*>* t) : prev(g_trash) { g_trash = t; }
+    ~TrashScope() { g_trash = prev; }
+};
+
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0, cap = 0;
@@ -146,7 +157,7 @@ template <class T> struct DevBuf {
         n = cap = count;
         if (count) CK(cudaMalloc((void**) &p, count*sizeof(T)));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
+    void release() { if (p) { if (g_trash) g_trash->push_back(p); else cudaFree(p); } p = nullptr; n = cap = 0; }
     void upload(const std::vector<T>& h, cudaStream_t s) {
         if (h.size() > n) alloc(h.size());
         if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size()*sizeof(T), cudaMemcpyHostToDevice, s));
@@ -238,6 +249,9 @@ struct agbnp_b200 {
     DevBuf<int2> d_pairs;
     cudaEvent_t ev[2] = {};
     bool have_events = false;
+    cudaEvent_t tail_ev = nullptr;          // recorded behind everything this handle enqueues: "my own work is done"
+    bool tail_valid = false;
+    std::vector<void*> trash;               // device buffers replaced while in use, freed at destruction (TrashScope)
     long long launches = 0;                 // kernels launched by this handle (bench.py's gpu_launches)
     // per-kernel CUDA-event brackets (agbnp_b200_profile): events come from a pool so that a whole timed region can be
     // bracketed launch by launch and summed afterwards
@@ -276,7 +290,8 @@ struct agbnp_b200 {
         if (h_posq) cudaFreeHost(h_posq);
         if (h_force) cudaFreeHost(h_force);
         if (h_tail) cudaFreeHost(h_tail);
-        if (have_events) { for (auto& e : ev) cudaEventDestroy(e); for (auto& e : async_ev) cudaEventDestroy(e); }
+        if (have_events) { for (auto& e : ev) cudaEventDestroy(e); for (auto& e : async_ev) cudaEventDestroy(e); cudaEventDestroy(tail_ev); }
+        for (void* q : trash) cudaFree(q);
         for (auto& e : prof_pool) cudaEventDestroy(e);
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
         for (void* p : peer_opened) cudaIpcCloseMemHandle(p);
@@ -288,6 +303,15 @@ struct agbnp_b200 {
 };
 
 namespace {
+
+// wait for the work THIS handle has enqueued (never cudaDeviceSynchronize: see TrashScope)
+void wait_own_work(agbnp_b200* h) {
+    if (h->tail_valid) CK(cudaEventSynchronize(h->tail_ev));
+}
+void mark_tail(agbnp_b200* h, cudaStream_t s) {
+    CK(cudaEventRecord(h->tail_ev, s));
+    h->tail_valid = true;
+}
 
 void alloc_store(agbnp_b200* h, int cap) {
     h->launch_gen++;
@@ -834,6 +858,7 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
     // graph of it is no faster than the plain launches (490 vs 466 us, 372 vs 367 us), so it is launched directly
     if (!h->use_graph || h->prof_mask || sharded) {
         if (sharded) enqueue_sharded(h, d_posq_in, s, sink); else enqueue(h, d_posq_in, s, PH_ALL, sink);
+        mark_tail(h, s);
         return;
     }
     agbnp_b200::GraphEntry* hit = nullptr;
@@ -871,6 +896,7 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
     hit->last_use = ++h->graph_clock;
     CK(cudaGraphLaunch(hit->exec, s));
     h->launches += hit->kernels;
+    mark_tail(h, s);
 }
 
 // read back status + scalars (synchronises the stream); returns the status bits
@@ -896,7 +922,8 @@ bool grow(agbnp_b200* h, const int* ctrl, bool ahead = false) {
     if (g_nbr && h->nbrmax >= 1024) return false;
     if (g_node && h->tree_cap >= 16384) return false;
     if (g_level && h->tree_wcap >= 16384) return false;
-    CK(cudaDeviceSynchronize());                       // buffers below may still be in use by queued evaluations
+    wait_own_work(h);                                  // buffers below may still be in use by queued evaluations
+    TrashScope ts(&h->trash);
     h->n_grow++;
     // a real overflow doubles (its high-water mark is only a lower bound); growing ahead of need takes small steps so that
     // the work arrays keep fitting in shared memory
@@ -942,11 +969,13 @@ void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_pos
             CK(cudaStreamSynchronize(s));
             host_xyz = tmp.data(); stride = 4;
         }
-        CK(cudaDeviceSynchronize());                   // queued evaluations still read the arrays about to be replaced
+        wait_own_work(h);                              // queued evaluations still read the arrays about to be replaced
         build_order(h, host_xyz, stride, s);
         if (timing) tp1 = now();
     }
     if (h->params_dirty) {
+        wait_own_work(h);
+        TrashScope ts(&h->trash);
         upload_static(h, s);
         if (timing) std::fprintf(stderr, "prepare: build_order %.2f ms, upload_static %.2f ms\n", tp1-tp0, now()-tp1);
     }
@@ -1099,6 +1128,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         { const char* ng = std::getenv("AGBNP_B200_NO_PDL"); h->use_pdl = !(ng && ng[0] == '1'); }
         for (auto& e2 : h->ev) CK(cudaEventCreate(&e2));
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->tail_ev, cudaEventDisableTiming));
         h->have_events = true;
         CK(cudaMallocHost((void**) &h->h_async, sizeof(int)*CW_COUNT*agbnp_b200::ASYNC_DEPTH));
         h->d_tree_ok.alloc(1);
@@ -1446,6 +1476,7 @@ int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* s
             begin_eval(h);
         }
         enqueue(h, (const float4*) d_posq, s, masks[phase], nullptr);
+        mark_tail(h, s);
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
@@ -1473,6 +1504,7 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
         cudaStream_t s = (cudaStream_t) stream;
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
         enqueue(h, nullptr, s, PH_FINISH, &sink);
+        mark_tail(h, s);
         // asynchronous: the status words follow the evaluation through the same ring as agbnp_b200_execute_device's; the
         // call returns the outcome of the evaluation issued ASYNC_DEPTH-1 calls ago (identical on every shard: SC_FAULT)
         if (!h_energy) return async_post(h, s);
@@ -1604,6 +1636,7 @@ int agbnp_b200_peer_exchange(agbnp_b200* h, int which, void* stream) {
     try {
         CK(cudaSetDevice(h->cfg.device));
         peer_enqueue(h, which, (cudaStream_t) stream);
+        mark_tail(h, (cudaStream_t) stream);
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }

@@ -130,12 +130,14 @@ struct TreeArgs {
 };
 
 __host__ __device__ inline size_t tree_work_bytes(int nbrmax, int cap, int wcap) {
-    size_t b = (size_t) wcap*sizeof(double)                   // key
-             + (size_t) (wcap+2)*sizeof(int)                  // pref
+    size_t b = (size_t) wcap*sizeof(float4)                   // sc4
+             + (size_t) (wcap+2)*sizeof(double)               // key / pl (aliased: never live at the same time)
+             + (size_t) wcap*sizeof(float)                    // scv
              + (size_t) wcap*sizeof(int)                      // cand
              + (size_t) nbrmax*6*sizeof(float)                // nbx, nby, nbz, nba, nbv, nbi
              + (size_t) (MAX_LEVELS+2)*sizeof(int)            // lvs
-             + (size_t) (4*cap + 2*wcap)*sizeof(short);       // parent, nbr, cstart, ccount, perm, gend
+             + (size_t) ((cap+31)/32)*sizeof(unsigned)        // hc
+             + (size_t) (2*cap + 4*wcap)*sizeof(short);       // parent, nbr | cstart, ccount, perm, gend
     return (b + 15) & ~(size_t) 15;
 }
 __host__ __device__ inline size_t tree_stage_bytes(int cap) {
@@ -168,24 +170,34 @@ __device__ __forceinline__ double overlap_volume(double a1, double v1, double a2
 
 // per-warp work arrays (shared memory, or global scratch for oversize capacities)
 struct TreeWork {
-    double* key;             // [wcap] sort key (switched volume) of the level being created
-    int* pref;               // [wcap+1] exclusive prefix of candidate counts of the level being expanded
+    float4* sc4;             // [wcap] FP32 copy (x, y, z, a) of the enlarged-radius Gaussian of every node of the level being
+    float* scv;              //        expanded, and its volume: all the FP32 screen reads of a parent (written at node creation:
+                             //        the screen of a level is complete before the exact phase creates the next one, in place)
+    double* key;             // [wcap] sort key (switched volume) of the level being created (exact phase + sort)
+    int2* pl;                // [wcap+1] ALIASES key (screen only): the expanding parents of the level, compacted:
+                             //        (sorted position, first candidate index); pl[np] = (-, number of candidates)
     int* cand;               // [wcap] candidates that passed the FP32 screen: parent slot | neighbor index << 16
     float *nbx, *nby, *nbz;  // [nbrmax] level-2 candidate positions (absolute, float as given)
     float *nba, *nbv;        // [nbrmax] their enlarged-radius Gaussian exponent / volume rounded to float (screen only)
     int* nbi;                // [nbrmax] their sorted atom indices
     int* lvs;                // [MAX_LEVELS+2] first slot of each level
-    short *parent, *nbr, *cstart, *ccount;   // [cap]
+    unsigned* hc;            // [cap/32] bit per slot: the node has children
+    short *parent, *nbr;     // [cap] parent slot, level-2 neighbor index + 1 of the node's last atom
+    short *cstart, *ccount;  // [wcap] first child slot / number of children of the nodes of the level being expanded (by slot - ls);
+                             //        k_tree_rescan: ccount is [cap], 1 if the node has children
     short *perm, *gend;      // [wcap] sorted position -> slot, end of the sibling group (both relative to the level start)
     __device__ void bind(unsigned char* base, int nbrmax, int cap, int wcap) {
-        key = (double*) base;
-        pref = (int*) (key+wcap);
-        cand = pref+wcap+2;
+        sc4 = (float4*) base;
+        key = (double*) (sc4+wcap);
+        pl = (int2*) key;
+        scv = (float*) (key+wcap+2);
+        cand = (int*) (scv+wcap);
         nbx = (float*) (cand+wcap); nby = nbx+nbrmax; nbz = nby+nbrmax; nba = nbz+nbrmax; nbv = nba+nbrmax;
         nbi = (int*) (nbv+nbrmax);
         lvs = nbi+nbrmax;
-        parent = (short*) (lvs+MAX_LEVELS+2); nbr = parent+cap; cstart = nbr+cap; ccount = cstart+cap;
-        perm = ccount+cap; gend = perm+wcap;
+        hc = (unsigned*) (lvs+MAX_LEVELS+2);
+        parent = (short*) (hc+(cap+31)/32); nbr = parent+cap; cstart = nbr+cap; ccount = cstart+wcap;
+        perm = ccount+wcap; gend = perm+wcap;
     }
 };
 
@@ -244,14 +256,15 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
             if (valid) {
                 const float4 l0 = swL[2*sl], l1 = swL[2*sl+1], s0v = swS[2*sl], s1v = swS[2*sl+1];
                 float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, h2 = h0;
-                if (W.ccount[sl] > 0) { h0 = hu[4*sl]; h1 = hu[4*sl+1]; h2 = hu[4*sl+2]; }
+                const bool has_kids = STORED ? W.ccount[sl] > 0 : ((W.hc[sl >> 5] >> (sl & 31)) & 1u) != 0;
+                if (has_kids) { h0 = hu[4*sl]; h1 = hu[4*sl+1]; h2 = hu[4*sl+2]; }
                 int ja;
                 if (STORED) ja = ja_arr[sl];
                 else { const int ia = W.nbr[sl]; ja = ia == 0 ? r : W.nbi[ia-1]; }
                 key = W.parent[sl];
                 if (!STORED && rec_out) {
                     // persist what the gamma sweep needs (TreeStore) while the records are in registers anyway
-                    const int pk = (key & 0xffff) | (W.ccount[sl] > 0 ? 0x10000 : 0);
+                    const int pk = (key & 0xffff) | (has_kids ? 0x10000 : 0);
                     rec_out[2*sl] = make_float4(coefp*s0v.y, s0v.z, s0v.w, __int_as_float(ja));
                     rec_out[2*sl+1] = make_float4(s1v.x, s1v.y, s1v.z, __int_as_float(pk));
                     rank_out[sl] = rk[sl];
@@ -406,6 +419,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
 
         // ---- slot 0: the root atom (gaussvol.cpp:130-148) ----
         const float gam_r = A.gamma[r];
+        for (int w = lane; w < (cap+31)/32; w += 32) W.hc[w] = 0u;
         if (lane == 0) {
             NodeGauss g;
             g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
@@ -416,8 +430,9 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
             swS[0] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
             rk[0] = 0;
-            W.parent[0] = -1; W.nbr[0] = 0; W.cstart[0] = 1; W.ccount[0] = 0; W.perm[0] = 0; W.gend[0] = 1;
+            W.parent[0] = -1; W.nbr[0] = 0; W.perm[0] = 0; W.gend[0] = 1;
             W.lvs[1] = 0;
+            W.sc4[0] = make_float4(0.f, 0.f, 0.f, (float) g.aL); W.scv[0] = (float) g.vL;
             eL_tot += (double) (own*gam_r*(float) g.vL); eS_tot += (double) (own*gam_r*(float) g.vS);
             vsumL += (double) (own*(float) g.vL); vsumS += (double) (own*(float) g.vS);
         }
@@ -427,24 +442,26 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
         int nslots = 1, ls = 0, le = 1, level = 1;
         bool failed = false;
         while (level < A.max_order) {           // a node at level >= MAX_ORDER gets no children (gaussvol.cpp:211)
-            int T;
+            int T, npar = 0;
             const int width = le-ls;
             if (level == 1) {
                 T = nn;
             } else {
-                // candidates of the node at sorted position t: its younger siblings t+1 .. gend[t]-1 (gaussvol.cpp:221)
-                int carry = 0;
+                // candidates of the node at sorted position t: its younger siblings t+1 .. gend[t]-1 (gaussvol.cpp:221).
+                // The parents that have any are compacted into pl[] with the index of their first candidate, parent-major.
+                T = 0;
                 for (int t0 = 0; t0 < width; t0 += 32) {
                     const int t = t0+lane;
                     int c = 0;
                     // level 2 -> 3: only the level-2 nodes this part owns are expanded
                     if (t < width && (level > 2 || t % nparts == part)) c = (int) W.gend[t] - t - 1;
                     const int inc = warp_incl_scan(c);
-                    if (t < width) W.pref[t] = carry + inc - c;
-                    carry += __shfl_sync(FULL, inc, 31);
+                    const unsigned hm = __ballot_sync(FULL, c > 0);
+                    if (c > 0) W.pl[npar + __popc(hm & lanemask_lt())] = make_int2(t, T + inc - c);
+                    npar += __popc(hm);
+                    T += __shfl_sync(FULL, inc, 31);
                 }
-                if (lane == 0) W.pref[width] = carry;
-                T = carry;
+                if (lane == 0) W.pl[npar] = make_int2(0, T);
                 __syncwarp();
             }
             if (level == 1) c2_tot += (lane == 0 && part == 0) ? (unsigned long long) T : 0ull;
@@ -456,48 +473,41 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             // ---- phase A: FP32 screen of all T candidates.  A candidate whose FP32 overlap volume is below VOLMINA by
             // more than the screen's error margin is certainly rejected by the exact test (s = 0 below VOLMINA,
             // gaussvol.cpp:26-29,233); everything else goes, in candidate order, to the exact FP64 phase.
+            // Everything the screen reads is in shared memory.  Candidate -> (parent, sibling): every expanding parent owns
+            // at least one candidate, so the parents that START inside the 32 candidates of a trip are among the next 32 of
+            // pl[]; one redux.or builds the mask of their start positions and a popc gives every lane its parent -- no
+            // per-candidate search.
             int nmaybe = 0;
-            const int nsteps = width > 1 ? 32 - __clz(width-1) : 0;      // binary-search trips (warp-uniform)
-            for (int k0 = 0; k0 < T; k0 += 32*SCREEN_UNROLL) {           // several candidates per lane in flight: the loads overlap
-                bool mb[SCREEN_UNROLL];
-                int pkv[SCREEN_UNROLL];
-#pragma unroll
-                for (int q4 = 0; q4 < SCREEN_UNROLL; q4++) {
-                    const int k = k0 + 32*q4 + lane;
-                    const bool valid = k < T;
-                    int p = 0, kn = k;
-                    if (level > 1) {
-                        int lo = 0, hi = width-1;
-                        for (int it = 0; it < nsteps; it++) {
-                            const int mid = (lo+hi+1) >> 1;
-                            if (W.pref[mid] <= k) lo = mid; else hi = mid-1;
-                        }
-                        const int u = min(lo + 1 + (k - W.pref[lo]), width-1);
-                        p = ls + W.perm[lo];
-                        kn = (int) W.nbr[ls + W.perm[u]] - 1;
-                    }
-                    kn = valid ? kn : 0;
-                    const NodeGauss* gq = G+p;
-                    const float a1f = (float) gq->aL, v1f = (float) gq->vL;
-                    const float x1f = (float) gq->xL, y1f = (float) gq->yL, z1f = (float) gq->zL;
-                    const float a2 = W.nba[kn], v2 = W.nbv[kn];
-                    const float dx = (W.nbx[kn]-pr.x)-x1f, dy = (W.nby[kn]-pr.y)-y1f, dz = (W.nbz[kn]-pr.z)-z1f;
-                    const float d2 = dx*dx + dy*dy + dz*dz;
-                    const float df = __fdividef(a1f*a2, a1f+a2);
-                    const float u = df*0.318309886f;
-                    const float est = v1f*v2*(u*sqrtf(u))*__expf(-df*d2);
-                    mb[q4] = valid && est > A.screen;
-                    pkv[q4] = p | (kn << 16);
+            int tp = 0;                                                   // pl index of the parent that owns candidate k0
+            for (int k0 = 0; k0 < T; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < T;
+                int p = 0, kn = valid ? k : 0;
+                if (level > 1) {
+                    const int s = W.pl[min(tp+1+lane, npar)].y - k0 - 1;  // start of parent tp+1+lane, relative to k0+1
+                    const unsigned heads = __reduce_or_sync(FULL, (unsigned) s < 32u ? (1u << s) : 0u);
+                    const int2 me = W.pl[min(tp + __popc(heads & lanemask_lt()), npar-1)];
+                    tp += __popc(heads);
+                    const int u = min(me.x + 1 + (k - me.y), width-1);
+                    p = W.perm[me.x];
+                    kn = valid ? (int) W.nbr[ls + W.perm[u]] - 1 : 0;
                 }
-#pragma unroll
-                for (int q4 = 0; q4 < SCREEN_UNROLL; q4++) {
-                    const unsigned mm = __ballot_sync(FULL, mb[q4]);
-                    if (mb[q4]) {
-                        const int q = nmaybe + __popc(mm & lanemask_lt());
-                        if (q < wcap) W.cand[q] = pkv[q4];
-                    }
-                    nmaybe += __popc(mm);
+                const float4 g1 = W.sc4[p];
+                const float v1f = W.scv[p];
+                p += ls;
+                const float a2 = W.nba[kn], v2 = W.nbv[kn];
+                const float dx = (W.nbx[kn]-pr.x)-g1.x, dy = (W.nby[kn]-pr.y)-g1.y, dz = (W.nbz[kn]-pr.z)-g1.z;
+                const float d2 = dx*dx + dy*dy + dz*dz;
+                const float df = __fdividef(g1.w*a2, g1.w+a2);
+                const float u = df*0.318309886f;
+                const float est = v1f*v2*(u*sqrtf(u))*__expf(-df*d2);
+                const bool mb = valid && est > A.screen;
+                const unsigned mm = __ballot_sync(FULL, mb);
+                if (mb) {
+                    const int q = nmaybe + __popc(mm & lanemask_lt());
+                    if (q < wcap) W.cand[q] = p | (kn << 16);
                 }
+                nmaybe += __popc(mm);
             }
             if (nmaybe > wcap) { hw_w = max(hw_w, nmaybe); if (lane == 0) atomicOr(A.status, ST_LEVEL_OVERFLOW); failed = true; break; }
             __syncwarp();
@@ -557,12 +567,13 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                         g.xS = (u1*b1 + x2*b2)*dS; g.yS = (q1*b1 + y2*b2)*dS; g.zS = (r1*b1 + z2*b2)*dS;
                         g.gam = gam; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
                         G[slot] = g;
+                        W.sc4[slot-new_start] = make_float4((float) g.xL, (float) g.yL, (float) g.zL, (float) g.aL);
+                        W.scv[slot-new_start] = (float) gvol;
                         const double mS = 2.0*dfS*gS;
                         const float vs = (float) (sS*gS);
                         swS[2*slot] = make_float4(vs, (float) (spS*gS + sS), (float) (w1 > 0 ? gS/w1 : 0.0), (float) b2/(float) g.aS);
                         swS[2*slot+1] = make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam);
                         W.parent[slot] = (short) p; W.nbr[slot] = (short) (kn+1);
-                        W.cstart[slot] = 0; W.ccount[slot] = 0;
                         // energies and volumes need no tree accumulation (gaussvol.cpp:425-433 summed over the subtree)
                         if (level > 1 || nparts == 1) {                   // level-2 nodes of a split root: after the sort, when ownership is known
                             const float cg = coefp*gam;
@@ -582,13 +593,17 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             // children ranges of the parents (children of one parent are contiguous: candidates are enumerated parent-major)
             for (int s0 = new_start; s0 < nslots; s0 += 32) {
                 const int sl = s0+lane;
-                if (sl < nslots && (sl == new_start || W.parent[sl] != W.parent[sl-1])) W.cstart[W.parent[sl]] = (short) sl;
+                if (sl < nslots && (sl == new_start || W.parent[sl] != W.parent[sl-1])) {
+                    const int p = W.parent[sl];
+                    W.cstart[p-ls] = (short) sl;
+                    atomicOr(&W.hc[p >> 5], 1u << (p & 31));
+                }
             }
             __syncwarp();
             for (int s0 = new_start; s0 < nslots; s0 += 32) {
                 const int sl = s0+lane;
                 if (sl < nslots && (sl == nslots-1 || W.parent[sl+1] != W.parent[sl])) {
-                    const int p = W.parent[sl];
+                    const int p = W.parent[sl] - ls;
                     W.ccount[p] = (short) (sl+1 - W.cstart[p]);
                 }
             }
@@ -598,7 +613,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             for (int s0 = new_start; s0 < nslots; s0 += 32) {
                 const int sl = s0+lane;
                 if (sl < nslots) {
-                    const int p = W.parent[sl];
+                    const int p = W.parent[sl] - ls;
                     const int cs = (int) W.cstart[p] - new_start, ce = cs + W.ccount[p];
                     const int me = sl-new_start;
                     const double kv = W.key[me];
