@@ -199,6 +199,9 @@ struct agbnp_b200 {
     DevBuf<int> d_pq_toff;
     DevBuf<unsigned> d_pq_hits;
     DevBuf<uint2> d_pq_masks;
+    DevBuf<float4> d_posq_ref;              // sorted positions when the pair masks were last built (agbnp_pair.cuh: PairUnits::ctl)
+    DevBuf<int> d_pq_ctl;                   // [4] persistent control words of the pair-mask reuse
+    float pq_skin = 0.05f;                  // nm; AGBNP_B200_PAIR_SKIN overrides, 0 = rebuild the masks in every evaluation
     int nunits = 0, npq_units = 0;
     // per-evaluation arrays
     DevBuf<float4> d_posq, d_bbc, d_bbh, d_posq_in, d_gbj;
@@ -565,6 +568,10 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         h->d_pq_toff.upload(toff, s);
         h->d_pq_hits.alloc(std::max<size_t>(1, pq.size()));
         h->d_pq_masks.alloc((size_t) std::max(1, t)*TILE);
+        // new order, new units: the stored masks are void
+        h->d_posq_ref.alloc(np);
+        h->d_pq_ctl.alloc(4);
+        CK(cudaMemsetAsync(h->d_pq_ctl.p, 0, 4*sizeof(int), s));
     }
     CK(cudaStreamSynchronize(s));      // the host vectors above go out of scope
     // per-evaluation arrays
@@ -668,7 +675,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         const bool rescan = h->cur_eval_rescan;
         // a rescan evaluation keeps root_cnt (the tail of the slab): it says which stored subtrees exist
         PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p,
-                    (float4*) h->d_slab.p, (int) ((rescan ? h->slab_keep_off : h->slab_bytes)/sizeof(float4))};
+                    (float4*) h->d_slab.p, (int) ((rescan ? h->slab_keep_off : h->slab_bytes)/sizeof(float4)),
+                    h->d_posq_ref.p, h->d_pq_ctl.p};
         begin(K_PREP);
         launch(h, k_prep, (h->nb+7)/8, 256, 0, s, pa);
         end(K_PREP);
@@ -718,11 +726,15 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         }
     }
     const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
+    // pair-mask reuse: list range = pass range + skin; rebuild when an atom has moved more than 0.49 skin since the build
+    const float pq_range = cutoff ? (float) std::min(h->k.i4_maxa, h->cfg.cutoff) : (float) h->k.i4_maxa;
+    const float pq_list2 = (pq_range + h->pq_skin)*(pq_range + h->pq_skin);
+    const float pq_move2 = h->pq_skin > 0.f ? (0.49f*h->pq_skin)*(0.49f*h->pq_skin) : -1.f;
     if (v1 && (phase_mask & PH_BORN)) {
         BornArgs ba{};
         ba.c = pc;
         ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_pq_toff.p, h->d_pq_hits.p, h->d_pq_masks.p,
-                         h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, h->cfg.shard_count};
+                         h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, h->cfg.shard_count, h->d_pq_ctl.p, pq_list2, pq_move2};
         ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
         const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
         int bocc = 0;
@@ -759,7 +771,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         DerivArgs da{};
         da.c = pc;
         da.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_pq_toff.p, h->d_pq_hits.p, h->d_pq_masks.p,
-                         h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count};
+                         h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count, h->d_pq_ctl.p, pq_list2, pq_move2};
         da.vsf = h->d_vsf.p; da.gbacc = h->d_gbacc; da.born = h->d_born.p; da.bfp = h->d_bfp.p; da.brw = h->d_brw.p;
         da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
         // launch shape: the warps per CTA (and CTAs per SM) that put the most warps on an SM within 227 KB of shared memory
@@ -807,7 +819,10 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         fa.sharded = h->cfg.shard_count > 1;
         fa.peer_fault = h->peer_ready ? h->peer.status : nullptr;
         fa.tree_ok_out = h->cur_eval_rescan ? nullptr : h->d_tree_ok.p;     // a build evaluation (in)validates the stored tree
-        if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; fa.gb_scale = -2.0*h->k.dielectric_factor; }
+        if (v1) {
+            fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; fa.gb_scale = -2.0*h->k.dielectric_factor;
+            fa.posq = h->d_posq.p; fa.posq_ref = h->d_posq_ref.p; fa.pq_ctl = h->d_pq_ctl.p;
+        }
         fa.padded_n = sink ? sink->padded_n : 0;
         if (sink && sink->ptr) {
             if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;
@@ -1126,6 +1141,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         { const char* ng = std::getenv("AGBNP_B200_NO_GRAPH"); h->use_graph = !(ng && ng[0] == '1'); }
         { const char* ng = std::getenv("AGBNP_B200_NO_PDL"); h->use_pdl = !(ng && ng[0] == '1'); }
+        if (const char* sk = std::getenv("AGBNP_B200_PAIR_SKIN")) h->pq_skin = std::max(0.f, (float) std::atof(sk));
         for (auto& e2 : h->ev) CK(cudaEventCreate(&e2));
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->tail_ev, cudaEventDisableTiming));

@@ -40,6 +40,8 @@ struct PrepArgs {
     float4 *bbc, *bbh;
     float4* slab;               // the per-evaluation accumulators and control words, zeroed here (slab_vec float4)
     int slab_vec;
+    const float4* posq_ref;     // sorted positions at the time the pair masks were built (PairUnits::ctl)
+    int* pq_ctl;                // [1] max over atoms of |x - x_ref|^2 (float bits; reset by k_finish)
 };
 
 __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
@@ -64,6 +66,13 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
         lo[0] = lo[1] = lo[2] = 3.0e38f; hi[0] = hi[1] = hi[2] = -3.0e38f;
     }
     A.posq[k] = p;
+    {
+        // how far has any atom moved since the range-limited pair masks were built?  (k_born rebuilds them beyond skin/2)
+        float d2 = 0.f;
+        if (o >= 0) { const float4 q = A.posq_ref[k]; const float dx = p.x-q.x, dy = p.y-q.y, dz = p.z-q.z; d2 = dx*dx + dy*dy + dz*dz; }
+        d2 = warp_max(d2);
+        if (lane == 0 && d2 > 0.f) atomicMax(A.pq_ctl+1, __float_as_int(d2));     // non-negative floats order like their bit patterns
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) { lo[c] = warp_min(lo[c]); hi[c] = warp_max(hi[c]); }
     if (lane == 0) {
@@ -129,6 +138,14 @@ struct PairUnits {
     uint2* masks;               // [tile slots][32] (row mask, column mask) of every lane
     int* work_counter;
     int shard_rank, shard_count;    // units are dealt round-robin to shards (shard_count 1: all)
+    // Verlet-style reuse of the pair-test cache ACROSS evaluations: the masks are built with the range enlarged by a skin
+    // and stay valid while no atom has moved more than skin/2 since (k_prep measures it, k_born decides, k_finish moves
+    // the reference positions); every walked pair is re-tested against the exact range, so the set of pairs that
+    // contribute -- the membership -- is decided per evaluation exactly as before.
+    int* ctl;                       // persistent: [0] masks valid for the current order, [1] max displacement^2 (float bits),
+                                    // [2] this evaluation rebuilt the masks (written by k_born, read by k_finish)
+    float list2;                    // (range + skin)^2: threshold of the box and atom tests when the masks are built
+    float move2;                    // (0.49 skin)^2: rebuild when an atom has moved further than this since the last build
 };
 
 __device__ __forceinline__ float pq_dist2(bool exact, float dx, float dy, float dz) {
@@ -169,7 +186,7 @@ struct BornSmem { float4 p[TILE]; int tj[TILE]; };     // p = (x, y, z, s_j/(4 p
 // contribution of partner jj (valid = the pair exists; invalid slots run the same instructions on a harmless atom)
 template <bool CUTOFF>
 __device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o, int jj, bool valid, float px, float py, float pz,
-                                           int tbase, float inv_h, unsigned& npair) {
+                                           int tbase, float inv_h, float lim2, unsigned& npair) {
     const int tj = o.tj[jj];
     const float4 c = o.p[jj];
     const float dx = c.x-px, dy = c.y-py, dz = c.z-pz;
@@ -177,7 +194,7 @@ __device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o
     const float d = d2*rsqrtf(fmaxf(d2, 1e-20f));
     const float t = d*inv_h;
     const int k = min((int) t, I4_INTERVALS-1);
-    const bool use = valid && tj >= 0;
+    const bool use = valid && tj >= 0 && d2 < lim2;          // the masks carry a skin: the range itself is tested here
     const float q = spline_value(tabv[tbase + max(tj, 0)*I4_INTERVALS + k], t-(float) k);
     npair += use;
     return use ? c.w*q : 0.f;
@@ -186,7 +203,7 @@ __device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o
 // everything atom "me" receives from the partners in `mask`; two partners per trip for instruction-level parallelism
 template <bool CUTOFF>
 __device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o, unsigned mask, float px, float py, float pz,
-                                           int tbase, float inv_h, unsigned& npair) {
+                                           int tbase, float inv_h, float lim2, unsigned& npair) {
     float s0 = 0.f, s1 = 0.f;
     while (mask) {
         const int j0 = __ffs(mask)-1;
@@ -194,8 +211,8 @@ __device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o
         const bool two = mask != 0;
         const int j1 = two ? __ffs(mask)-1 : j0;
         mask &= mask-1;
-        s0 += born_term<CUTOFF>(tabv, o, j0, true, px, py, pz, tbase, inv_h, npair);
-        s1 += born_term<CUTOFF>(tabv, o, j1, two, px, py, pz, tbase, inv_h, npair);
+        s0 += born_term<CUTOFF>(tabv, o, j0, true, px, py, pz, tbase, inv_h, lim2, npair);
+        s1 += born_term<CUTOFF>(tabv, o, j1, two, px, py, pz, tbase, inv_h, lim2, npair);
     }
     return s0+s1;
 }
@@ -226,16 +243,22 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
     BornSmem& R = sm[2*warp];
     BornSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
+    // rebuild the pair masks (all units, this evaluation) or walk the stored ones?  Nothing below writes ctl[0] / ctl[1].
+    const bool rebuild = A.u.ctl[0] == 0 || __int_as_float(A.u.ctl[1]) > A.u.move2;
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.u.ctl[2] = rebuild ? 1 : 0;
     unsigned npair = 0;
     for (int u = first_unit(); u < A.u.nunits; u = next_unit(A.u.work_counter, lane)) {
         if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
         const int2 un = A.u.units[u];
         const int ra = un.x;
         const int cb0 = un.y & 0xfffff, nc = un.y >> 20;
-        bool hit = false;
-        if (lane < nc) hit = box_box_dist2(A.c.bbc[ra], A.c.bbh[ra], A.c.bbc[cb0+lane], A.c.bbh[cb0+lane]) < lim2;
-        unsigned hits = __ballot_sync(FULL, hit);
-        if (lane == 0) A.u.unit_hits[u] = hits;
+        unsigned hits;
+        if (rebuild) {
+            bool hit = false;
+            if (lane < nc) hit = box_box_dist2(A.c.bbc[ra], A.c.bbh[ra], A.c.bbc[cb0+lane], A.c.bbh[cb0+lane]) < A.u.list2;
+            hits = __ballot_sync(FULL, hit);
+            if (lane == 0) A.u.unit_hits[u] = hits;
+        } else hits = A.u.unit_hits[u];
         if (!hits) continue;
         const int toff = A.u.tile_off[u];
         __syncwarp();
@@ -252,14 +275,19 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
             born_load(A, cb, lane, Cc);
             __syncwarp();
             unsigned rowmask, colmask;
-            pq_masks<CUTOFF>(Cc.p, pa.x, pa.y, pa.z, lim2, diag, lane, rowmask, colmask);
-            A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane] = make_uint2(rowmask, colmask);
-            rsum += born_role<CUTOFF>(tabv, Cc, rowmask, pa.x, pa.y, pa.z, tbase_a, A.c.inv_h, npair);
+            if (rebuild) {
+                pq_masks<CUTOFF>(Cc.p, pa.x, pa.y, pa.z, A.u.list2, diag, lane, rowmask, colmask);
+                A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane] = make_uint2(rowmask, colmask);
+            } else {
+                const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
+                rowmask = mk.x; colmask = mk.y;
+            }
+            rsum += born_role<CUTOFF>(tabv, Cc, rowmask, pa.x, pa.y, pa.z, tbase_a, A.c.inv_h, lim2, npair);
             if (!diag && row_heavy) {
                 const int b = cb*TILE+lane;
                 const int tbase_b = (int) A.c.ts[b]*A.c.ntj*I4_INTERVALS;
                 const float4 pc = Cc.p[lane];
-                const float csum = born_role<CUTOFF>(tabv, R, colmask, pc.x, pc.y, pc.z, tbase_b, A.c.inv_h, npair);
+                const float csum = born_role<CUTOFF>(tabv, R, colmask, pc.x, pc.y, pc.z, tbase_b, A.c.inv_h, lim2, npair);
                 if (csum != 0.f) atomicAdd(&A.bsum[b], csum);
             }
         }
@@ -630,10 +658,12 @@ constexpr size_t DERIV_WARP_SMEM = 2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof
 
 template <bool CUTOFF, int MODE>
 __device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, int jj,
-                                           bool valid, const DerivMe& me, int ntj, float inv_h, float& fx, float& fy, float& fz, float& wu) {
+                                           bool valid, const DerivMe& me, int ntj, float inv_h, float lim2, float& fx, float& fy, float& fz, float& wu) {
     const float4 c = o.p[jj];
     const float dx = c.x-me.px, dy = c.y-me.py, dz = c.z-me.pz;
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
+    valid = valid && d2 < lim2;                             // the masks carry a skin: the range itself is tested here (both roles
+                                                            // of a pair compute the same d2: squares of negated differences)
     const int pk = o.pk[jj];
     const int ts_o = pk & 0xff;
     const float inv_d = rsqrtf(fmaxf(d2, 1e-20f));
@@ -661,7 +691,7 @@ __device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tab
 template <bool CUTOFF, int MODE>
 __device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, unsigned mask,
                                              float px, float py, float pz, float s_me, float bw_me, int ts_me, int tj_me,
-                                             int ntj, float inv_h) {
+                                             int ntj, float inv_h, float lim2) {
     float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
     const DerivMe me{px, py, pz, s_me, bw_me, ts_me*ntj*I4_INTERVALS, tj_me};
     while (mask) {
@@ -670,8 +700,8 @@ __device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* t
         const bool two = mask != 0;
         const int j1 = two ? __ffs(mask)-1 : j0;
         mask &= mask-1;
-        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j0, true, me, ntj, inv_h, fx0, fy0, fz0, wu0);
-        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j1, two, me, ntj, inv_h, fx1, fy1, fz1, wu1);
+        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j0, true, me, ntj, inv_h, lim2, fx0, fy0, fz0, wu0);
+        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j1, two, me, ntj, inv_h, lim2, fx1, fy1, fz1, wu1);
     }
     return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
 }
@@ -727,16 +757,16 @@ __global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
             const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
             const unsigned rowmask = mk.x, colmask = mk.y;
             if (diag) {
-                const float4 r = deriv_role<CUTOFF, 0>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h);
+                const float4 r = deriv_role<CUTOFF, 0>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h, lim2);
                 racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
             } else {
-                const float4 r = deriv_role<CUTOFF, 1>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h);
+                const float4 r = deriv_role<CUTOFF, 1>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h, lim2);
                 racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
                 __syncwarp();                                   // the weights are read by other lanes
                 const int pk = Cc.pk[lane];
                 const float4 pc = Cc.p[lane];
                 const float4 c = deriv_role<CUTOFF, 2>(tabv, tabd, R, wmat, lane, colmask, pc.x, pc.y, pc.z, pc.w, Cc.bw[lane],
-                                                       pk & 0xff, (int) (signed char) ((pk >> 8) & 0xff), A.c.ntj, A.c.inv_h);
+                                                       pk & 0xff, (int) (signed char) ((pk >> 8) & 0xff), A.c.ntj, A.c.inv_h, lim2);
                 if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], c);
             }
         }
@@ -764,6 +794,9 @@ struct FinishArgs {
     int* status;                        // capacity-overflow bits of this evaluation: nothing is delivered unless 0
     int sharded;                        // scalars[SC_FAULT] holds the number of shards whose status word is non-zero (k_status_fold + ENERGY exchange)
     const int* peer_fault;              // peer-memory exchange: non-zero once a wait for a peer has timed out (sticky), or null
+    const float4* posq;                 // sorted positions of this evaluation
+    float4* posq_ref;                   // reference positions of the pair masks: moved here when k_born rebuilt them
+    int* pq_ctl;                        // PairUnits::ctl
     int* tree_ok_out;                   // build evaluations: 1 if the tree was built without overflow (read by k_tree_rescan)
     double* energy_accum;               // optional device accumulator (+=)
     double* energy_out;                 // optional device/pinned-mapped slot (=)
@@ -781,6 +814,13 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     pdl_release();
     pdl_acquire();
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (A.pq_ctl) {
+        // pair masks rebuilt in this evaluation: they are valid from now on, relative to these positions.  (Only thread 0
+        // writes ctl[0] / ctl[1], nobody in this kernel reads them; ctl[2] was written by k_born.)
+        const bool rebuilt = A.pq_ctl[2] != 0;
+        if (rebuilt && k < A.np) A.posq_ref[k] = A.posq[k];
+        if (k == 0) { if (rebuilt) A.pq_ctl[0] = 1; A.pq_ctl[1] = 0; }
+    }
     // sharded: every shard withholds the delivery when ANY shard overflowed (the shards' status words were summed into
     // SC_FAULT by the ENERGY exchange), and the host of a shard that did not overflow itself learns it from ST_PEER_OVERFLOW
     const bool mine = A.status && *A.status != 0;

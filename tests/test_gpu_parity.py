@@ -353,6 +353,31 @@ def test_jittered_trajectory_frames():
         assert relrms(ctx.getForces(), f_ref) <= F_TOL
 
 
+@pytest.mark.parametrize("method,cutoff", [(0, 1.0), (1, 1.2)])
+def test_pair_mask_reuse_across_moves(method, cutoff):
+    """The range-limited pair passes keep their 32x32 in-range masks between evaluations (built with a 0.05 nm skin,
+    re-tested pair by pair against the exact range, rebuilt on the device once an atom has moved > skin/2).  A walk that
+    alternates small moves (masks reused) with moves beyond skin/2 (rebuild) must give the oracle's Born radii, W+U and
+    forces on every frame -- a pair missing from a stale mask would show in all three."""
+    s = load_system("1li2")
+    rng = np.random.default_rng(77)
+    pos = systems.float_rounded(s["pos"])
+    ctx = plug.Context(systems.make_force(s, 1, method, cutoff))
+    kw = dict(nonbonded_method=portlib.CutoffNonPeriodic, cutoff=cutoff) if method else {}
+    o = portlib.OracleKernel(1, *sys_args(s), **kw)
+    for frame, amp in enumerate([0.0, 0.004, 0.004, 0.02, 0.004, 0.012, 0.03, 0.002]):
+        pos = systems.float_rounded(pos + rng.uniform(-amp, amp, pos.shape))
+        ctx.setPositions(pos)
+        e = ctx.calcForcesAndEnergy()
+        e_ref, f_ref = o.execute(pos)
+        assert abs(e - e_ref) <= E_TOL * abs(e_ref), frame
+        assert relrms(ctx.getForces(), f_ref) <= F_TOL, frame
+        assert np.abs(ctx.kernel.get("BORN_RADIUS") / o.get("born_radius") - 1).max() <= 1e-5, frame
+        assert relrms(ctx.kernel.get("DERIV_WU"), o.get("W") + o.get("U")) <= 1e-5, frame
+        if method:
+            assert int(ctx.kernel.get("WORK_COUNTERS")[0]) == len(portlib.neighbor_pairs(pos.astype(np.float32), cutoff))
+
+
 def test_verlet_energy_conservation():
     """The reference's end-to-end check (example/test_agbnp.py:55-64): Verlet steps, total energy every few steps.  With
     AGBNP1 (NoCutoff) as the only force the solute collapses -- there are no bonded or repulsive terms -- and converts
