@@ -89,6 +89,17 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
 __device__ __forceinline__ float spline_value(float4 v, float fr) { return fmaf(fr, fmaf(fr, fmaf(fr, v.w, v.z), v.y), v.x); }
 __device__ __forceinline__ float spline_deriv(float4 w, float fr) { return fmaf(fr, fmaf(fr, w.z, w.y), w.x); }
 
+// Interval of the uniform-knot spline tables without the two conversion instructions (F2I, I2F: quarter-rate XU pipe, which
+// the pair passes share with MUFU.RSQ): adding 1.5 * 2^23 rounds t - 1/2 to the nearest integer k = floor(t) into the low
+// mantissa bits (an exact tie, t an integer, may give k = t - 1 with fr = 1: the same point of the continuous spline).
+// Returns k clamped to the last interval and sets fr = t - k (pairs beyond the table range are masked by their callers).
+__device__ __forceinline__ int spline_interval(float t, float& fr) {
+    const float tk = (t - 0.5f) + 12582912.f;
+    fr = t - (tk - 12582912.f);
+    return min(__float_as_int(tk) - 0x4B400000, I4_INTERVALS-1);
+}
+__device__ __forceinline__ float rsqrt_fast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 struct PairCommon {
     int np, nhb, nb;            // padded atoms, heavy blocks, all blocks
     const float4* posq;
@@ -181,7 +192,7 @@ struct BornArgs {
     unsigned long long* counters;
 };
 
-struct BornSmem { float4 p[TILE]; int tj[TILE]; };     // p = (x, y, z, s_j/(4 pi)); .w = 0 for non-screeners
+struct BornSmem { float4 p[TILE]; int tj[TILE]; };     // p = (x, y, z, s_j/(4 pi)); .w = 0 for non-screeners; tj = screener type * 15, or < 0
 
 // contribution of partner jj (valid = the pair exists; invalid slots run the same instructions on a harmless atom)
 template <bool CUTOFF>
@@ -191,11 +202,11 @@ __device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o
     const float4 c = o.p[jj];
     const float dx = c.x-px, dy = c.y-py, dz = c.z-pz;
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
-    const float d = d2*rsqrtf(fmaxf(d2, 1e-20f));
-    const float t = d*inv_h;
-    const int k = min((int) t, I4_INTERVALS-1);
+    const float d = d2*rsqrt_fast(fmaxf(d2, 1e-20f));
+    float fr;
+    const int k = spline_interval(d*inv_h, fr);
     const bool use = valid && tj >= 0 && d2 < lim2;          // the masks carry a skin: the range itself is tested here
-    const float q = spline_value(tabv[tbase + max(tj, 0)*I4_INTERVALS + k], t-(float) k);
+    const float q = spline_value(tabv[tbase + max(tj, 0) + k], fr);
     npair += use;
     return use ? c.w*q : 0.f;
 }
@@ -222,7 +233,8 @@ __device__ __forceinline__ void born_load(const BornArgs& A, int blk, int lane, 
     const float4 p = A.c.posq[j];
     const double vj = A.vS[j];
     s.p[lane] = make_float4(p.x, p.y, p.z, vj > 0 ? PIFAC*(A.accS[j].w/(float) vj) : 0.f);
-    s.tj[lane] = A.c.tj[j];
+    const int tj = A.c.tj[j];
+    s.tj[lane] = tj < 0 ? -1 : tj*I4_INTERVALS;
 }
 
 // TAB_SMEM: the spline tables are staged in shared memory (the normal case; a compile-time fact so that the lookups are
@@ -643,9 +655,9 @@ struct DerivArgs {
     float4* dacc;               // out [np]: fx, fy, fz, W+U (zeroed slab; float red.global)
 };
 
-struct DerivSmem { float4 p[TILE]; float bw[TILE]; int pk[TILE]; };    // p = (x, y, z, s); pk = ts | (tj & 0xff) << 8
+struct DerivSmem { float4 p[TILE]; float bw[TILE]; int2 pk[TILE]; };   // p = (x, y, z, s); pk = (ts * ntj * 15, tj * 15 or < 0): table row offsets
 
-struct DerivMe { float px, py, pz, s, bw; int base, tj; };
+struct DerivMe { float px, py, pz, s, bw; int base, tj; };   // base = ts * ntj * 15, tj = tj * 15 or < 0
 
 // The force weight of a pair, w = [bw_me s_o Q'(me,o) + bw_o s_me Q'(o,me)]/d, is symmetric in (me, o).  On an
 // off-diagonal tile the row role (MODE 1) therefore stores it in a 32x33 shared-memory matrix and the column role
@@ -664,21 +676,19 @@ __device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tab
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
     valid = valid && d2 < lim2;                             // the masks carry a skin: the range itself is tested here (both roles
                                                             // of a pair compute the same d2: squares of negated differences)
-    const int pk = o.pk[jj];
-    const int ts_o = pk & 0xff;
-    const float inv_d = rsqrtf(fmaxf(d2, 1e-20f));
+    const int2 pk = o.pk[jj];
+    const float inv_d = rsqrt_fast(fmaxf(d2, 1e-20f));
     const float d = d2*inv_d;
-    const float t = d*inv_h;
-    const int k = min((int) t, I4_INTERVALS-1);
-    const float fr = t-(float) k;
-    const int ix = (ts_o*ntj + max(me.tj, 0))*I4_INTERVALS + k;
+    float fr;
+    const int k = spline_interval(d*inv_h, fr);
+    const int ix = pk.x + max(me.tj, 0) + k;
     const float v2 = spline_value(tabv[ix], fr);
     const float bwo = (valid && me.tj >= 0) ? o.bw[jj] : 0.f;   // me descreens o (needs heavy(me))
     float w;
     if (MODE == 2) w = valid ? wmat[jj*WMAT_STRIDE + lane] : 0.f;
     else {
-        const int tj_o = (int) (signed char) ((pk >> 8) & 0xff);
-        const float q1 = spline_deriv(tabd[me.base + max(tj_o, 0)*I4_INTERVALS + k], fr);
+        const int tj_o = pk.y;
+        const float q1 = spline_deriv(tabd[me.base + max(tj_o, 0) + k], fr);
         const float q2 = spline_deriv(tabd[ix], fr);
         w = (valid && tj_o >= 0) ? me.bw*c.w*q1 : 0.f;          // o descreens me (needs heavy(o))
         w = fmaf(bwo*me.s, q2, w)*inv_d;
@@ -693,7 +703,7 @@ __device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* t
                                              float px, float py, float pz, float s_me, float bw_me, int ts_me, int tj_me,
                                              int ntj, float inv_h, float lim2) {
     float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
-    const DerivMe me{px, py, pz, s_me, bw_me, ts_me*ntj*I4_INTERVALS, tj_me};
+    const DerivMe me{px, py, pz, s_me, bw_me, ts_me, tj_me};
     while (mask) {
         const int j0 = __ffs(mask)-1;
         mask &= mask-1;
@@ -711,7 +721,8 @@ __device__ __forceinline__ void deriv_load(const DerivArgs& A, int blk, int lane
     const float4 p = A.c.posq[j];
     s.p[lane] = make_float4(p.x, p.y, p.z, A.vsf[j]);
     s.bw[lane] = A.brw[j] - PIFAC*A.kdiel*(p.w*p.w + A.gbacc[j].w*A.born[j])*A.bfp[j];
-    s.pk[lane] = (int) A.c.ts[j] | (((int) A.c.tj[j] & 0xff) << 8);
+    const int tj = A.c.tj[j];
+    s.pk[lane] = make_int2((int) A.c.ts[j]*A.c.ntj*I4_INTERVALS, tj < 0 ? -1 : tj*I4_INTERVALS);
 }
 
 template <bool CUTOFF, bool TAB_SMEM>
@@ -745,7 +756,7 @@ __global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
         deriv_load(A, ra, lane, R);
         const int a = ra*TILE+lane;
         const float px = R.p[lane].x, py = R.p[lane].y, pz = R.p[lane].z, s_a = R.p[lane].w, bw_a = R.bw[lane];
-        const int ts_a = A.c.ts[a], tj_a = A.c.tj[a];
+        const int ts_a = R.pk[lane].x, tj_a = R.pk[lane].y;     // premultiplied table offsets
         float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
         while (hits) {
             const int cb = cb0 + __ffs(hits)-1;
@@ -763,10 +774,10 @@ __global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
                 const float4 r = deriv_role<CUTOFF, 1>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h, lim2);
                 racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
                 __syncwarp();                                   // the weights are read by other lanes
-                const int pk = Cc.pk[lane];
+                const int2 pk = Cc.pk[lane];
                 const float4 pc = Cc.p[lane];
                 const float4 c = deriv_role<CUTOFF, 2>(tabv, tabd, R, wmat, lane, colmask, pc.x, pc.y, pc.z, pc.w, Cc.bw[lane],
-                                                       pk & 0xff, (int) (signed char) ((pk >> 8) & 0xff), A.c.ntj, A.c.inv_h, lim2);
+                                                       pk.x, pk.y, A.c.ntj, A.c.inv_h, lim2);
                 if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], c);
             }
         }
