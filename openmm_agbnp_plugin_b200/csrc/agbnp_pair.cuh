@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
 // k_gb: GB pair energy, direct force and Y accumulators over symmetric 32x32 tiles
 // (ReferenceAGBNPKernels.cpp:476-498), in packed FP32x2 arithmetic (fma.rn.f32x2 -> FFMA2 on sm_100a).
 //
-// The pass is bound by the FP32 pipe: one pair costs 29 FP32 operations + 2 MUFU (ex2, rsqrt).  Scalar code spends an
+// The pass is bound by the FP32 pipe: one pair costs 27 FP32 operations + 2 MUFU (ex2, rsqrt).  Scalar code spends an
 // issue slot per operation; here every arithmetic instruction handles the pairs (i0,j) and (i1,j) of two row atoms at
 // once, which halves the issue slots of the FP32 part and leaves the FMA pipe itself as the limit.
 //   lane grid 4 (li) x 8 (lj): a lane owns 8 row atoms (4 packed pairs) for a whole work unit and 4 column atoms per
@@ -430,14 +430,13 @@ __device__ __forceinline__ void gb_prefetch(const GBArgs& A, int cb, int lane, G
 // one 32x32 tile: 4 column atoms x 4 packed row pairs per lane.
 // FAR: every pair of the tile has d^2 > 64 B_i B_j, i.e. exp(-d^2/4B_iB_j) < e^-16 = 1.1e-7 and B_iB_j exp(..)/d^2 < 2e-9:
 // below float resolution in f = 1/sqrt(d^2 + B_iB_j exp(..)), so the pair is plain Coulomb (f = 1/d, no Y term) and
-// costs 19 instead of 29 FP32 operations and 1 instead of 2 MUFU.
+// costs 17 instead of 27 FP32 operations and 1 instead of 2 MUFU.
 template <bool CUTOFF, bool DIAG, bool FAR>
 __device__ __forceinline__ void gb_tile(const GBArgs& A, const GBStage& st, int cb, int li, int lj,
                                         const float2 (&nx)[4], const float2 (&ny)[4], const float2 (&nz)[4],
                                         const float2 (&qi)[4], const float2 (&bi)[4], const float2 (&nib)[4],
                                         float2 (&fi)[4][4], float2& e2, unsigned& npair) {
     const float2 m025 = make_float2(-0.25f, -0.25f), p025 = make_float2(0.25f, 0.25f);
-    const float2 half = make_float2(-0.5f, -0.5f), three_half = make_float2(1.5f, 1.5f);
     const float2 cut2 = make_float2(A.c.cut2, A.c.cut2);
     float sj[4][4];
 #pragma unroll
@@ -478,10 +477,10 @@ __device__ __forceinline__ void gb_tile(const GBArgs& A, const GBStage& st, int 
             }
             const float2 qf = __fmul2_rn(qq, f);
             const float2 ff = __fmul2_rn(f, f);
-            // energy with one Newton step on the reciprocal square root: f (3/2 - t f^2 / 2); MUFU.RSQ alone carries a
-            // ~4e-7 mean relative bias that the 1e8-term pair sum does not average out
-            const float2 corr = __ffma2_rn(__fmul2_rn(t, ff), half, three_half);
-            e2 = __ffma2_rn(qf, corr, e2);
+            // energy straight from MUFU.RSQ: on B200 rsqrt.approx.ftz has a mean relative error of -5e-9 over all mantissas
+            // (rms 3.4e-8, max 1.25e-7; tools/rsqrt_bias.cu), which the pair sum does not see -- a Newton step on f (two
+            // more packed operations per pair) bought nothing measurable in energy parity and cost 9 us (profiles/r2_experiments.md)
+            e2 = __fadd2_rn(e2, qf);
             const float2 g = __fmul2_rn(qf, ff);
             float2 mw = g;
             if (!FAR) {
