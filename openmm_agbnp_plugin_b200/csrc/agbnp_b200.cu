@@ -193,14 +193,15 @@ struct agbnp_b200 {
     DevBuf<double> d_aL, d_vL, d_aS, d_vS;
     DevBuf<unsigned char> d_rcbin, d_ts;
     DevBuf<signed char> d_tj;
-    DevBuf<float> d_rc2, d_rc2max;
+    DevBuf<float> d_rc2, d_rc2max, d_rc2s, d_rc2maxs;     // level-2 pair radii squared; the same with the list skin
+    DevBuf<int> d_l2list, d_l2cnt;          // per-root level-2 candidate lists kept between evaluations (agbnp_tree.cuh)
     DevBuf<float4> d_i4v, d_i4d;
     DevBuf<int2> d_units, d_pq_units;
     DevBuf<int> d_pq_toff;
     DevBuf<unsigned> d_pq_hits;
     DevBuf<uint2> d_pq_masks;
     DevBuf<float4> d_posq_ref;              // sorted positions when the pair masks were last built (agbnp_pair.cuh: PairUnits::ctl)
-    DevBuf<int> d_pq_ctl;                   // [4] persistent control words of the pair-mask reuse
+    DevBuf<int> d_pq_ctl;                   // [LC_COUNT] persistent control words of the list reuse (ListCtl)
     float pq_skin = 0.05f;                  // nm; AGBNP_B200_PAIR_SKIN overrides, 0 = rebuild the masks in every evaluation
     int nunits = 0, npq_units = 0;
     // per-evaluation arrays
@@ -327,10 +328,21 @@ void alloc_store(agbnp_b200* h, int cap) {
     s.root_off = h->d_root_off.p; s.root_cnt = h->d_root_cnt; s.root_lvs = h->d_root_lvs.p;
 }
 
+// per-root level-2 candidate lists (stride nbrmax); a new order or a new stride voids every stored list
+void alloc_l2_lists(agbnp_b200* h, cudaStream_t s) {
+    if (h->nhp <= 0) return;
+    h->d_l2list.alloc((size_t) h->nhp*h->nbrmax);
+    h->d_l2cnt.alloc(h->nhp);
+    h->d_pq_ctl.alloc(LC_COUNT);
+    CK(cudaMemsetAsync(h->d_pq_ctl.p, 0, LC_COUNT*sizeof(int), s));
+}
+
 // choose the launch shape of k_tree for the current capacities and (re)allocate its per-warp buffers
 void alloc_tree_scratch(agbnp_b200* h) {
     h->launch_gen++;
     h->tree_built = false;
+    alloc_l2_lists(h, h->own_stream);
+    if (h->nhp > 0) CK(cudaStreamSynchronize(h->own_stream));
     const size_t per_warp = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
     const size_t smem_sm = 200*1024;                       // of 227 KB; leaves room for L1
     // CTAs of 2 warps (warps never cooperate); 128 registers/thread bound the residency at 16 warps per SM
@@ -526,8 +538,17 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     h->d_aL.upload(aL, s); h->d_vL.upload(vL, s); h->d_aS.upload(aS, s); h->d_vS.upload(vS, s); h->d_inv_vS.upload(inv_vS, s);
     h->d_rcbin.upload(rcbin, s); h->d_ts.upload(ts, s); h->d_tj.upload(tj, s);
     h->d_rc2.upload(sp.rc2, s); h->d_rc2max.upload(sp.rc2max, s);
+    {
+        // the same radii with the list skin: (sqrt(rc2) + skin)^2, rounded up
+        auto skinned = [&](float r2) { const float r = std::sqrt(r2) + h->pq_skin; return r*r*1.000001f; };
+        std::vector<float> a(sp.rc2.size()), b(sp.rc2max.size());
+        for (size_t i = 0; i < a.size(); i++) a[i] = skinned(sp.rc2[i]);
+        for (size_t i = 0; i < b.size(); i++) b[i] = skinned(sp.rc2max[i]);
+        h->d_rc2s.upload(a, s); h->d_rc2maxs.upload(b, s);
+    }
     h->rc2_global = 0.f;
     for (float v : sp.rc2max) h->rc2_global = std::max(h->rc2_global, v);
+    { const float r = std::sqrt(h->rc2_global) + h->pq_skin; h->rc2_global = r*r*1.000001f; }
     h->d_items.upload(h->items, s);
     h->d_bcount.alloc(std::max(1, h->nhb)); h->d_blist.alloc((size_t) std::max(1, h->nhb)*BLIST_MAX);
     // I4 splines in power form around the left knot (see agbnp_pair.cuh): with zl = y2_k h^2/6, zu = y2_{k+1} h^2/6,
@@ -568,10 +589,9 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         h->d_pq_toff.upload(toff, s);
         h->d_pq_hits.alloc(std::max<size_t>(1, pq.size()));
         h->d_pq_masks.alloc((size_t) std::max(1, t)*TILE);
-        // new order, new units: the stored masks are void
+        // new order, new units: the stored masks and candidate lists are void
         h->d_posq_ref.alloc(np);
-        h->d_pq_ctl.alloc(4);
-        CK(cudaMemsetAsync(h->d_pq_ctl.p, 0, 4*sizeof(int), s));
+        alloc_l2_lists(h, s);
     }
     CK(cudaStreamSynchronize(s));      // the host vectors above go out of scope
     // per-evaluation arrays
@@ -658,6 +678,8 @@ void begin_eval(agbnp_b200* h) {
 void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_mask, const ForceSink* sink) {
     const bool cutoff = h->cfg.nonbonded_method == AGBNP_B200_CUTOFF_NONPERIODIC;
     const bool v1 = h->cfg.version == 1;
+    // Verlet lists (pair masks, level-2 candidate lists): rebuild when an atom has moved more than 0.49 skin since the build
+    const float pq_move2 = h->pq_skin > 0.f ? (0.49f*h->pq_skin)*(0.49f*h->pq_skin) : -1.f;
     size_t open_a = 0;
     auto begin = [&](int id) {
         if (h->prof_mask & (1u << id)) { cudaEvent_t e = prof_take(h); open_a = h->prof_used-1; CK(cudaEventRecord(e, s)); }
@@ -693,7 +715,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
             launch(h, k_tree_rescan, h->tree_grid, 32*h->tree_warps, h->tree_warps*rescan_work_bytes(h->tree_cap), s, ra);
             end(K_TREE);
         } else {
-        BlockListArgs bl{h->nhb, h->d_bbc.p, h->d_bbh.p, h->rc2_global, h->d_bcount.p, h->d_blist.p};
+        BlockListArgs bl{h->nhb, h->d_bbc.p, h->d_bbh.p, h->rc2_global, h->d_bcount.p, h->d_blist.p, h->d_pq_ctl.p, pq_move2};
         begin(K_BLIST);
         launch(h, k_blocklist, (h->nhb+7)/8, 256, 0, s, bl);
         end(K_BLIST);
@@ -703,6 +725,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.l2rec = h->d_l2rec.p; ta.rcbin = h->d_rcbin.p;
         ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;
         ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
+        ta.rc2s = h->d_rc2s.p; ta.rc2maxs = h->d_rc2maxs.p; ta.l2list = h->d_l2list.p; ta.l2cnt = h->d_l2cnt.p;
+        ta.ctl = h->d_pq_ctl.p; ta.move2 = pq_move2;
         ta.volmina = h->k.volmina; ta.volminb = h->k.volminb; ta.min_gvol = h->k.min_gvol;
         ta.swd = 1.0/(h->k.volminb-h->k.volmina);
         // FP32 screen: |relative error| of the float overlap volume is < 1e-4 (positions within a subtree are < 2 nm from the
@@ -726,10 +750,9 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         }
     }
     const size_t tab_bytes = pc.tab_smem ? (size_t) pc.ntables*I4_INTERVALS*sizeof(float4) : 0;
-    // pair-mask reuse: list range = pass range + skin; rebuild when an atom has moved more than 0.49 skin since the build
+    // pair-mask reuse: list range = pass range + skin
     const float pq_range = cutoff ? (float) std::min(h->k.i4_maxa, h->cfg.cutoff) : (float) h->k.i4_maxa;
     const float pq_list2 = (pq_range + h->pq_skin)*(pq_range + h->pq_skin);
-    const float pq_move2 = h->pq_skin > 0.f ? (0.49f*h->pq_skin)*(0.49f*h->pq_skin) : -1.f;
     if (v1 && (phase_mask & PH_BORN)) {
         BornArgs ba{};
         ba.c = pc;
@@ -819,10 +842,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         fa.sharded = h->cfg.shard_count > 1;
         fa.peer_fault = h->peer_ready ? h->peer.status : nullptr;
         fa.tree_ok_out = h->cur_eval_rescan ? nullptr : h->d_tree_ok.p;     // a build evaluation (in)validates the stored tree
-        if (v1) {
-            fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; fa.gb_scale = -2.0*h->k.dielectric_factor;
-            fa.posq = h->d_posq.p; fa.posq_ref = h->d_posq_ref.p; fa.pq_ctl = h->d_pq_ctl.p;
-        }
+        if (v1) { fa.gbacc = h->d_gbacc; fa.dacc = h->d_dacc; fa.gacc = h->d_gacc; fa.gb_scale = -2.0*h->k.dielectric_factor; }
+        fa.posq = h->d_posq.p; fa.posq_ref = h->d_posq_ref.p; fa.pq_ctl = h->d_pq_ctl.p;
         fa.padded_n = sink ? sink->padded_n : 0;
         if (sink && sink->ptr) {
             if (sink->layout == 0) fa.out_f32 = (float*) sink->ptr;

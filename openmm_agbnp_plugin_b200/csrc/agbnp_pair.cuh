@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
         if (o >= 0) { const float4 q = A.posq_ref[k]; const float dx = p.x-q.x, dy = p.y-q.y, dz = p.z-q.z; d2 = dx*dx + dy*dy + dz*dz; }
         d2 = warp_max(d2);
         if (lane == 0 && d2 > 0.f) atomicMax(A.pq_ctl+1, __float_as_int(d2));     // non-negative floats order like their bit patterns
+        if (gid == 0) { A.pq_ctl[2] = 0; A.pq_ctl[4] = 0; }        // "rebuilt in this evaluation" flags (k_born, k_tree)
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) { lo[c] = warp_min(lo[c]); hi[c] = warp_max(hi[c]); }
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
     // rebuild the pair masks (all units, this evaluation) or walk the stored ones?  Nothing below writes ctl[0] / ctl[1].
     const bool rebuild = A.u.ctl[0] == 0 || __int_as_float(A.u.ctl[1]) > A.u.move2;
-    if (blockIdx.x == 0 && threadIdx.x == 0) A.u.ctl[2] = rebuild ? 1 : 0;
+    if (rebuild && blockIdx.x == 0 && threadIdx.x == 0) A.u.ctl[2] = 1;
     unsigned npair = 0;
     for (int u = first_unit(); u < A.u.nunits; u = next_unit(A.u.work_counter, lane)) {
         if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
@@ -825,11 +826,16 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     pdl_acquire();
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
     if (A.pq_ctl) {
-        // pair masks rebuilt in this evaluation: they are valid from now on, relative to these positions.  (Only thread 0
-        // writes ctl[0] / ctl[1], nobody in this kernel reads them; ctl[2] was written by k_born.)
-        const bool rebuilt = A.pq_ctl[2] != 0;
-        if (rebuilt && k < A.np) A.posq_ref[k] = A.posq[k];
-        if (k == 0) { if (rebuilt) A.pq_ctl[0] = 1; A.pq_ctl[1] = 0; }
+        // Verlet lists (pair masks: k_born; level-2 candidate lists: k_tree) rebuilt in this evaluation are valid from now on,
+        // relative to these positions; the reference positions are shared, so a list that was NOT rebuilt while they move
+        // becomes void.  (Only thread 0 writes words 0, 1, 3 and nobody in this kernel reads them; 2 and 4 are stable here.)
+        // (a search whose list capacity overflowed left truncated lists: they stay void until the host has grown them)
+        const bool pq = A.pq_ctl[2] != 0, l2 = A.pq_ctl[4] != 0 && !(A.status && (*A.status & ST_NBR_OVERFLOW));
+        if ((pq || l2) && k < A.np) A.posq_ref[k] = A.posq[k];
+        if (k == 0) {
+            if (pq || l2) { A.pq_ctl[0] = pq ? 1 : 0; A.pq_ctl[3] = l2 ? 1 : 0; }
+            A.pq_ctl[1] = 0;
+        }
     }
     // sharded: every shard withholds the delivery when ANY shard overflowed (the shards' status words were summed into
     // SC_FAULT by the ENERGY exchange), and the host of a shard that did not overflow itself learns it from ST_PEER_OVERFLOW

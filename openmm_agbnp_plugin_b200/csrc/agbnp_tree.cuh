@@ -68,14 +68,20 @@ constexpr int BLIST_MAX = 64;       // neighbor blocks listed per heavy block (m
 struct BlockListArgs {
     int nhb;
     const float4 *bbc, *bbh;
-    float rc2;                  // largest conservative pair radius, squared
+    float rc2;                  // largest conservative pair radius (+ list skin), squared
     int* bcount;                // [nhb] number of listed blocks, -1 = more than BLIST_MAX
     unsigned short* blist;      // [nhb*BLIST_MAX]
+    const int* ctl;             // neighbor-list reuse control words (TreeArgs::ctl): the block lists are only needed by an
+    float move2;                // evaluation that rebuilds the level-2 candidate lists
 };
+
+// control words shared by every Verlet-style list of an evaluation (pair masks: agbnp_pair.cuh; level-2 candidate lists: here)
+enum ListCtl { LC_PQ_VALID = 0, LC_DISP2 = 1, LC_PQ_REBUILT = 2, LC_L2_VALID = 3, LC_L2_REBUILT = 4, LC_COUNT = 8 };
 
 __global__ void __launch_bounds__(256) k_blocklist(BlockListArgs A) {
     pdl_release();
     pdl_acquire();
+    if (A.ctl[LC_L2_VALID] != 0 && !(__int_as_float(A.ctl[LC_DISP2]) > A.move2)) return;     // k_tree will walk its stored lists
     const int lane = threadIdx.x & 31;
     const int rb = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     if (rb >= A.nhb) return;
@@ -110,6 +116,16 @@ struct TreeArgs {
     const float4 *bbc, *bbh;
     const float* rc2;
     const float* rc2max;
+    // Level-2 candidate lists kept between evaluations (Verlet style): built with the pair radii enlarged by a skin, valid
+    // while no atom has moved more than skin/2 since (k_prep measures it), every listed candidate re-tested against the
+    // exact radius in every evaluation -- the level-2 candidates of an evaluation, and their order, are exactly those of
+    // a fresh search.
+    const float* rc2s;                // [nbins*nbins] (pair radius + skin)^2
+    const float* rc2maxs;             // [nbins]
+    int* l2list;                      // [nhp*nbrmax] per root (sorted index): candidate atoms, in search order
+    int* l2cnt;                       // [nhp]
+    int* ctl;                         // ListCtl
+    float move2;                      // (0.49 skin)^2, or < 0: search in every evaluation
     int nbins;
     double volmina, volminb, min_gvol, swd;
     float screen;                     // FP32 screen threshold: VOLMINA less the screen's error margin
@@ -347,6 +363,9 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
     double eL_tot = 0, eS_tot = 0, vsumL = 0, vsumS = 0;     // per-lane partial sums, reduced at the end
     unsigned long long c2_tot = 0, c3_tot = 0, m_tot = 0;
     int hw_nn = 0, hw_slots = 0, hw_w = 0;
+    // search the level-2 candidates or walk the stored lists?  (nothing in this kernel writes LC_L2_VALID / LC_DISP2)
+    const bool rebuild_l2 = A.ctl[LC_L2_VALID] == 0 || __int_as_float(A.ctl[LC_DISP2]) > A.move2;
+    if (rebuild_l2 && blockIdx.x == 0 && threadIdx.x == 0) A.ctl[LC_L2_REBUILT] = 1;
 
     // raw claim -> item: with shards, items are dealt block-cyclically (blocks of 32 in longest-first order)
     const int raw_end = A.shard_count > 1 ? (A.nitems+TILE-1)/TILE*TILE : A.nitems;
@@ -365,50 +384,90 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
         const float4 pr = A.posq[r];
         const int orig_r = A.orig[r];
         const int rb = A.rcbin[r];
-        const float rcmax = A.rc2max[rb];
 
         // ---- level-2 candidate list: heavy atoms later in the caller's order within the conservative pair radius ----
         int nn = 0;
-        const int nlist = A.bcount[r >> 5];
-        const int nscan = nlist >= 0 ? nlist : A.nhb;
-        for (int b0 = 0; b0 < nscan; b0 += 32) {
-            int b = b0+lane;
-            bool hit = false;
-            if (b < nscan) {
-                if (nlist >= 0) b = A.blist[(r >> 5)*BLIST_MAX + b];
-                hit = point_box_dist2(pr.x, pr.y, pr.z, A.bbc[b], A.bbh[b]) < rcmax;
-            }
-            unsigned m = __ballot_sync(FULL, hit);
-            while (m) {                                           // four listed blocks per trip: their loads overlap
-                int jq[4];
-                bool act[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    act[q] = m != 0;
-                    const int i = act[q] ? __ffs(m)-1 : 0;
-                    m &= m-1;
-                    jq[q] = __shfl_sync(FULL, b, i)*TILE+lane;
+        if (rebuild_l2) {
+            // search: block lists -> atoms; candidates within the enlarged radius go to the root's stored list, those within
+            // the radius itself are this evaluation's candidates
+            int nl = 0;
+            const float rcmaxs = A.rc2maxs[rb];
+            int* mylist = A.l2list + (size_t) r*nbrmax;
+            const int nlist = A.bcount[r >> 5];
+            const int nscan = nlist >= 0 ? nlist : A.nhb;
+            for (int b0 = 0; b0 < nscan; b0 += 32) {
+                int b = b0+lane;
+                bool hit = false;
+                if (b < nscan) {
+                    if (nlist >= 0) b = A.blist[(r >> 5)*BLIST_MAX + b];
+                    hit = point_box_dist2(pr.x, pr.y, pr.z, A.bbc[b], A.bbh[b]) < rcmaxs;
                 }
-                float4 pj[4];
-                int4 rc[4];
+                unsigned m = __ballot_sync(FULL, hit);
+                while (m) {                                           // four listed blocks per trip: their loads overlap
+                    int jq[4];
+                    bool act[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) { pj[q] = A.posq[jq[q]]; rc[q] = A.l2rec[jq[q]]; }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int ob = rc[q].x;
-                    const float dx = pj[q].x-pr.x, dy = pj[q].y-pr.y, dz = pj[q].z-pr.z;
-                    const float d2 = dx*dx + dy*dy + dz*dz;
-                    const bool ok = act[q] && ((ob < 0 ? -1 : (ob & 0xffffff)) > orig_r) && (d2 < __ldg(A.rc2 + rb*A.nbins + ((ob >> 24) & 0x7f)));
-                    const unsigned am = __ballot_sync(FULL, ok);
-                    if (ok) {
-                        const int p = nn + __popc(am & lanemask_lt());
-                        if (p < nbrmax) {
-                            W.nbi[p] = jq[q]; W.nbx[p] = pj[q].x; W.nby[p] = pj[q].y; W.nbz[p] = pj[q].z;
-                            W.nba[p] = __int_as_float(rc[q].y); W.nbv[p] = __int_as_float(rc[q].z);
-                        }
+                    for (int q = 0; q < 4; q++) {
+                        act[q] = m != 0;
+                        const int i = act[q] ? __ffs(m)-1 : 0;
+                        m &= m-1;
+                        jq[q] = __shfl_sync(FULL, b, i)*TILE+lane;
                     }
-                    nn += __popc(am);
+                    float4 pj[4];
+                    int4 rc[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { pj[q] = A.posq[jq[q]]; rc[q] = A.l2rec[jq[q]]; }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int ob = rc[q].x;
+                        const float dx = pj[q].x-pr.x, dy = pj[q].y-pr.y, dz = pj[q].z-pr.z;
+                        const float d2 = dx*dx + dy*dy + dz*dz;
+                        const int cls = rb*A.nbins + ((ob >> 24) & 0x7f);
+                        const bool later = act[q] && ((ob < 0 ? -1 : (ob & 0xffffff)) > orig_r);
+                        const bool listed = later && d2 < __ldg(A.rc2s + cls);
+                        const bool ok = listed && d2 < __ldg(A.rc2 + cls);
+                        const unsigned lm = __ballot_sync(FULL, listed);
+                        const unsigned am = __ballot_sync(FULL, ok);
+                        if (listed) {
+                            const int p = nl + __popc(lm & lanemask_lt());
+                            if (p < nbrmax) mylist[p] = jq[q];
+                        }
+                        if (ok) {
+                            const int p = nn + __popc(am & lanemask_lt());
+                            if (p < nbrmax) {
+                                W.nbi[p] = jq[q]; W.nbx[p] = pj[q].x; W.nby[p] = pj[q].y; W.nbz[p] = pj[q].z;
+                                W.nba[p] = __int_as_float(rc[q].y); W.nbv[p] = __int_as_float(rc[q].z);
+                            }
+                        }
+                        nl += __popc(lm);
+                        nn += __popc(am);
+                    }
                 }
+            }
+            if (lane == 0) A.l2cnt[r] = min(nl, nbrmax);
+            hw_nn = max(hw_nn, nl);
+            if (nl > nbrmax) nn = nl;                                 // the list itself overflowed: grow (below)
+        } else {
+            // walk the stored list: exact radius test, same order
+            const int nl = A.l2cnt[r];
+            const int* mylist = A.l2list + (size_t) r*nbrmax;
+            hw_nn = max(hw_nn, nl);
+            for (int e0 = 0; e0 < nl; e0 += 32) {
+                const int e = e0+lane;
+                const bool act = e < nl;
+                const int j = act ? mylist[e] : r;
+                const float4 pj = A.posq[j];
+                const int4 rc = A.l2rec[j];
+                const float dx = pj.x-pr.x, dy = pj.y-pr.y, dz = pj.z-pr.z;
+                const float d2 = dx*dx + dy*dy + dz*dz;
+                const bool ok = act && d2 < __ldg(A.rc2 + rb*A.nbins + ((rc.x >> 24) & 0x7f));
+                const unsigned am = __ballot_sync(FULL, ok);
+                if (ok) {
+                    const int p = nn + __popc(am & lanemask_lt());
+                    W.nbi[p] = j; W.nbx[p] = pj.x; W.nby[p] = pj.y; W.nbz[p] = pj.z;
+                    W.nba[p] = __int_as_float(rc.y); W.nbv[p] = __int_as_float(rc.z);
+                }
+                nn += __popc(am);
             }
         }
         hw_nn = max(hw_nn, nn);

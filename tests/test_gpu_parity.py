@@ -374,6 +374,8 @@ def test_pair_mask_reuse_across_moves(method, cutoff):
         assert relrms(ctx.getForces(), f_ref) <= F_TOL, frame
         assert np.abs(ctx.kernel.get("BORN_RADIUS") / o.get("born_radius") - 1).max() <= 1e-5, frame
         assert relrms(ctx.kernel.get("DERIV_WU"), o.get("W") + o.get("U")) <= 1e-5, frame
+        # the overlap tree walks stored level-2 candidate lists on the reuse frames: still node for node the oracle's
+        assert gpu_topology(ctx.kernel.get("TREE_TOPOLOGY")) == portlib.tree_topology(o.tree()), frame
         if method:
             assert int(ctx.kernel.get("WORK_COUNTERS")[0]) == len(portlib.neighbor_pairs(pos.astype(np.float32), cutoff))
 
