@@ -199,8 +199,8 @@ struct TreeWork {
     int* lvs;                // [MAX_LEVELS+2] first slot of each level
     unsigned* hc;            // [cap/32] bit per slot: the node has children
     short *parent, *nbr;     // [cap] parent slot, level-2 neighbor index + 1 of the node's last atom
-    short *cstart, *ccount;  // [wcap] first child slot / number of children of the nodes of the level being expanded (by slot - ls);
-                             //        k_tree_rescan: ccount is [cap], 1 if the node has children
+    short *cstart, *ccount;  // [wcap] first child slot / end of the child range of the nodes of the level being expanded (by
+                             //        slot - ls); k_tree_rescan: ccount is [cap], 1 if the node has children
     short *perm, *gend;      // [wcap] sorted position -> slot, end of the sibling group (both relative to the level start)
     __device__ void bind(unsigned char* base, int nbrmax, int cap, int wcap) {
         sc4 = (float4*) base;
@@ -572,6 +572,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             __syncwarp();
 
             // ---- phase B: exact FP64 evaluation of the screened candidates; accepted ones become nodes ----
+            int last_p = -1;                                              // parent of the newest node so far (warp-uniform)
             for (int k0 = 0; k0 < nmaybe; k0 += 32) {
                 const int k = k0+lane;
                 const bool valid = k < nmaybe;
@@ -604,6 +605,20 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                     accept = (s*gvol > A.min_gvol);                          // gaussvol.cpp:233
                 }
                 const unsigned am = __ballot_sync(FULL, accept);
+                {
+                    // children ranges of the parents: candidates are enumerated parent-major, so the children of one parent
+                    // are contiguous; the first child of a parent opens its range and closes the previous parent's
+                    const unsigned before = am & lanemask_lt();
+                    const int prev_p = __shfl_sync(FULL, p, before ? 31 - __clz(before) : 0);
+                    const int pp = before ? prev_p : last_p;
+                    const int slot = nslots + __popc(before);
+                    if (accept && p != pp && slot-new_start < wcap) {
+                        W.cstart[p-ls] = (short) slot;
+                        if (pp >= 0) W.ccount[pp-ls] = (short) slot;         // ccount holds the END of the range
+                        atomicOr(&W.hc[p >> 5], 1u << (p & 31));
+                    }
+                    if (am) last_p = __shfl_sync(FULL, p, 31 - __clz(am));
+                }
                 if (accept) {
                     const int slot = nslots + __popc(am & lanemask_lt());
                     if (slot < cap && slot-new_start < wcap) {
@@ -646,26 +661,8 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             hw_slots = max(hw_slots, nslots); hw_w = max(hw_w, nslots-new_start);
             if (nslots > cap) { if (lane == 0) atomicOr(A.status, ST_NODE_OVERFLOW); failed = true; break; }
             if (nslots-new_start > wcap) { if (lane == 0) atomicOr(A.status, ST_LEVEL_OVERFLOW); failed = true; break; }
-            __syncwarp();
             if (nslots == new_start) break;
-
-            // children ranges of the parents (children of one parent are contiguous: candidates are enumerated parent-major)
-            for (int s0 = new_start; s0 < nslots; s0 += 32) {
-                const int sl = s0+lane;
-                if (sl < nslots && (sl == new_start || W.parent[sl] != W.parent[sl-1])) {
-                    const int p = W.parent[sl];
-                    W.cstart[p-ls] = (short) sl;
-                    atomicOr(&W.hc[p >> 5], 1u << (p & 31));
-                }
-            }
-            __syncwarp();
-            for (int s0 = new_start; s0 < nslots; s0 += 32) {
-                const int sl = s0+lane;
-                if (sl < nslots && (sl == nslots-1 || W.parent[sl+1] != W.parent[sl])) {
-                    const int p = W.parent[sl] - ls;
-                    W.ccount[p] = (short) (sl+1 - W.cstart[p]);
-                }
-            }
+            if (lane == 0) W.ccount[last_p-ls] = (short) nslots;             // close the last parent's range
             __syncwarp();
             // siblings ordered by switched volume, larger first (gaussvol.cpp:97-100,171); rank sort within each group,
             // ties keep creation order
@@ -673,7 +670,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                 const int sl = s0+lane;
                 if (sl < nslots) {
                     const int p = W.parent[sl] - ls;
-                    const int cs = (int) W.cstart[p] - new_start, ce = cs + W.ccount[p];
+                    const int cs = (int) W.cstart[p] - new_start, ce = (int) W.ccount[p] - new_start;
                     const int me = sl-new_start;
                     const double kv = W.key[me];
                     int rank = 0;
