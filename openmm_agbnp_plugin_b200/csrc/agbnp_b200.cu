@@ -352,7 +352,7 @@ void alloc_tree_scratch(agbnp_b200* h) {
     if (h->tree_work_global) { h->tree_warps = 8; ctas = 2; }
     h->tree_grid = h->num_sm*(int) ctas;
     const size_t nwarps = (size_t) h->tree_grid*h->tree_warps;
-    h->d_tree_stage.alloc(nwarps*tree_stage_bytes(h->tree_cap));
+    h->d_tree_stage.alloc(nwarps*tree_stage_bytes(h->tree_cap, h->tree_wcap));
     if (h->tree_work_global) h->d_tree_work.alloc(nwarps*per_warp); else h->d_tree_work.release();
     const size_t smem = h->tree_work_global ? 0 : h->tree_warps*per_warp;
     // the attribute belongs to the function, not to the handle: several handles in one process (replicas, shards on one
@@ -707,7 +707,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
             ra.items = h->d_items.p; ra.nitems = (int) h->items.size(); ra.posq = h->d_posq.p;
             ra.aL = h->d_aL.p; ra.vL = h->d_vL.p; ra.aS = h->d_aS.p; ra.vS = h->d_vS.p; ra.gamma = h->d_gamma.p;
             ra.volmina = h->k.volmina; ra.volminb = h->k.volminb; ra.swd = 1.0/(h->k.volminb-h->k.volmina);
-            ra.cap = h->tree_cap; ra.stage = h->d_tree_stage.p; ra.stage_stride = tree_stage_bytes(h->tree_cap);
+            ra.cap = h->tree_cap; ra.stage = h->d_tree_stage.p; ra.stage_stride = tree_stage_bytes(h->tree_cap, h->tree_wcap);
             ra.accL = h->d_accL; ra.accS = h->d_accS; ra.scalars = h->d_scalars; ra.counters = h->d_counters;
             ra.st = h->st; ra.st.cursor = h->d_ctrl+CW_TREE_CURSOR;
             ra.work_counter = h->d_ctrl+CW_WORK_TREE; ra.status = h->d_ctrl+CW_STATUS; ra.tree_ok = h->d_tree_ok.p;
@@ -734,7 +734,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         ta.screen = (float) (h->k.volmina*(1.0 - 1.0e-3));
         ta.max_order = h->k.max_order;
         ta.cap = h->tree_cap; ta.wcap = h->tree_wcap; ta.nbrmax = h->nbrmax;
-        ta.stage = h->d_tree_stage.p; ta.stage_stride = tree_stage_bytes(h->tree_cap);
+        ta.stage = h->d_tree_stage.p; ta.stage_stride = tree_stage_bytes(h->tree_cap, h->tree_wcap);
         ta.wk_stride = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
         ta.wk_global = h->tree_work_global ? h->d_tree_work.p : nullptr;
         ta.accL = h->d_accL; ta.accS = h->d_accS; ta.scalars = h->d_scalars; ta.counters = h->d_counters;

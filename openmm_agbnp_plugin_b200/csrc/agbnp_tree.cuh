@@ -131,7 +131,7 @@ struct TreeArgs {
     float screen;                     // FP32 screen threshold: VOLMINA less the screen's error margin
     int max_order;
     int cap, wcap, nbrmax;            // capacities: nodes per root, nodes per level, level-2 neighbors per root
-    unsigned char* stage;             // per-warp global staging (tree_stage_bytes(cap) each)
+    unsigned char* stage;             // per-warp global staging (tree_stage_bytes(cap, wcap) each)
     size_t stage_stride;
     unsigned char* wk_global;         // per-warp work arrays in global memory, or nullptr = shared memory
     size_t wk_stride;
@@ -156,8 +156,12 @@ __host__ __device__ inline size_t tree_work_bytes(int nbrmax, int cap, int wcap)
              + (size_t) (2*cap + 4*wcap)*sizeof(short);       // parent, nbr | cstart, ccount, perm, gend
     return (b + 15) & ~(size_t) 15;
 }
-__host__ __device__ inline size_t tree_stage_bytes(int cap) {
-    size_t b = (size_t) cap*(sizeof(NodeGauss) + 8*sizeof(float4) + sizeof(short));
+__host__ __device__ inline size_t tree_stage_bytes(int cap, int wcap) {
+    // k_tree: two windows of wcap Gaussians (reused for the hand-up sums) + two sweep records and a rank per node;
+    // k_tree_rescan: Gaussians, two sweep records and hand-up sums per node
+    const size_t build = (size_t) 2*wcap*sizeof(NodeGauss) + (size_t) cap*(4*sizeof(float4) + sizeof(short));
+    const size_t rescan = (size_t) cap*(sizeof(NodeGauss) + 8*sizeof(float4));
+    const size_t b = build > rescan ? build : rescan;
     return (b + 255) & ~(size_t) 255;
 }
 
@@ -251,12 +255,18 @@ __device__ __forceinline__ void hu_store(float4* hu, int node, const float (&v)[
 // sums over a parent's children are a segmented warp scan over the child level; the last child of each parent stores
 // the totals into hu[4*parent ..] (global staging, one plain store per parent, read back one level later).
 // STORED: the node's last atom comes from `ja_arr` (k_tree_rescan) instead of the level-2 neighbor list.
+// hu: STORED (k_tree_rescan): one entry per slot.  Build (k_tree): the sums of a level are only needed while its parents' level
+// is swept, so they live in two alternating windows of `hu_w` entries indexed by the slot relative to its level start --
+// the bytes a subtree keeps hot in L2 are what these kernels pay for.
 template <bool STORED>
 __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL, const float4* swS, float4* hu, int nlev, int r, int lane,
                                            float4* accL, float4* accS, const int* ja_arr = nullptr,
-                                           float4* rec_out = nullptr, short* rank_out = nullptr, const short* rk = nullptr) {
+                                           float4* rec_out = nullptr, short* rank_out = nullptr, const short* rk = nullptr, int hu_w = 0) {
     for (int lev = nlev; lev >= 1; lev--) {
         const int b = W.lvs[lev], e = W.lvs[lev+1];
+        // window of this level's own sums (read) and of its parents' (written): slot -> hu index
+        const int rd_off = STORED ? 0 : (lev & 1)*hu_w - b;
+        const int wr_off = STORED ? 0 : (lev > 1 ? ((lev-1) & 1)*hu_w - W.lvs[lev-1] : 0);
         const float coefp = ((lev & 1) ? 1.f : -1.f)/(float) lev;
         int carry_key = -2;                         // parent whose children run across the chunk boundary
         float carry[10];
@@ -273,7 +283,7 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
                 const float4 l0 = swL[2*sl], l1 = swL[2*sl+1], s0v = swS[2*sl], s1v = swS[2*sl+1];
                 float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, h2 = h0;
                 const bool has_kids = STORED ? W.ccount[sl] > 0 : ((W.hc[sl >> 5] >> (sl & 31)) & 1u) != 0;
-                if (has_kids) { h0 = hu[4*sl]; h1 = hu[4*sl+1]; h2 = hu[4*sl+2]; }
+                if (has_kids) { const float4* hs = hu + 4*(sl+rd_off); h0 = hs[0]; h1 = hs[1]; h2 = hs[2]; }
                 int ja;
                 if (STORED) ja = ja_arr[sl];
                 else { const int ia = W.nbr[sl]; ja = ia == 0 ? r : W.nbi[ia-1]; }
@@ -308,7 +318,7 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
 #pragma unroll
                         for (int c = 0; c < 10; c++) v[c] += carry[c];
                     }
-                } else if (lane == 0) hu_store(hu, carry_key, carry);
+                } else if (lane == 0) hu_store(hu, carry_key+wr_off, carry);
             }
             int maxpos;
             const int pos = seg_position(key, lane, maxpos);
@@ -320,12 +330,12 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
             const int kn = __shfl_down_sync(FULL, key, 1);
             const bool tail = valid && (lane == 31 || kn != key);
             const int last = min(31, e-1-s0);       // last valid lane of this chunk: its segment may continue
-            if (tail && lane != last) hu_store(hu, key, v);
+            if (tail && lane != last) hu_store(hu, key+wr_off, v);
             carry_key = __shfl_sync(FULL, key, last);
 #pragma unroll
             for (int c = 0; c < 10; c++) carry[c] = __shfl_sync(FULL, v[c], last);
         }
-        if (lev > 1 && carry_key >= 0 && lane == 0) hu_store(hu, carry_key, carry);
+        if (lev > 1 && carry_key >= 0 && lane == 0) hu_store(hu, carry_key+wr_off, carry);
         __syncwarp();
     }
 }
@@ -353,12 +363,15 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
     TreeWork W;
     if (SMEM_WORK) W.bind(smem_raw + (size_t) warp*tree_work_bytes(nbrmax, cap, wcap), nbrmax, cap, wcap);
     else W.bind(A.wk_global + (size_t) gwarp*A.wk_stride, nbrmax, cap, wcap);
+    // per-warp global staging.  The Gaussians of a level are read only by the candidates of the next one, so they live in two
+    // alternating windows of wcap records (by level parity, indexed by slot - level start); the sweep's hand-up sums reuse
+    // the same bytes afterwards (tree_sweep).  What stays per node until the sweep are the two sweep records and the rank.
     unsigned char* stage = A.stage + (size_t) gwarp*A.stage_stride;
-    NodeGauss* G = (NodeGauss*) stage;
-    float4* swL = (float4*) (G+cap);
+    NodeGauss* G = (NodeGauss*) stage;              // [2*wcap]
+    float4* hu = (float4*) stage;                   // [2*wcap*4] after the build
+    float4* swL = (float4*) (G + 2*(size_t) wcap);
     float4* swS = swL + 2*(size_t) cap;
-    float4* hu = swS + 2*(size_t) cap;              // sweep hand-up sums, 4 float4 per node
-    short* rk = (short*) (hu + 4*(size_t) cap);
+    short* rk = (short*) (swS + 2*(size_t) cap);
 
     double eL_tot = 0, eS_tot = 0, vsumL = 0, vsumS = 0;     // per-lane partial sums, reduced at the end
     unsigned long long c2_tot = 0, c3_tot = 0, m_tot = 0;
@@ -484,7 +497,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
             g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
             g.gam = gam_r; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
-            G[0] = g;
+            G[wcap] = g;                                          // level 1: the odd window
             const float own = part == 0 ? 1.f : 0.f;              // the root's own terms belong to part 0
             swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
             swS[0] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
@@ -586,7 +599,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                     const int pk = W.cand[k];
                     p = pk & 0xffff; kn = pk >> 16;
                     j = W.nbi[kn];
-                    const NodeGauss* gp = G+p;
+                    const NodeGauss* gp = G + ((level & 1)*wcap + p - ls);
                     a1 = gp->aL; v1 = gp->vL; x1 = gp->xL; y1 = gp->yL; z1 = gp->zL;
                     a2 = A.aL[j];
                     const double v2 = A.vL[j];
@@ -640,7 +653,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                         g.aS = b1+b2; g.vS = gS;
                         g.xS = (u1*b1 + x2*b2)*dS; g.yS = (q1*b1 + y2*b2)*dS; g.zS = (r1*b1 + z2*b2)*dS;
                         g.gam = gam; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
-                        G[slot] = g;
+                        G[((level+1) & 1)*wcap + slot-new_start] = g;
                         W.sc4[slot-new_start] = make_float4((float) g.xL, (float) g.yL, (float) g.zL, (float) g.aL);
                         W.scv[slot-new_start] = (float) gvol;
                         const double mS = 2.0*dfS*gS;
@@ -719,7 +732,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             if (lane <= nlev+1 && lane >= 1) A.st.root_lvs[item*MAX_LEVELS+lane] = (short) W.lvs[lane];
         }
         tree_sweep<false>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS, nullptr,
-                          fits ? A.st.rec + 2*(size_t) off : nullptr, fits ? A.st.rank + off : nullptr, rk);
+                          fits ? A.st.rec + 2*(size_t) off : nullptr, fits ? A.st.rank + off : nullptr, rk, wcap);
         __syncwarp();
     }
 
