@@ -140,7 +140,7 @@ typedef enum {
                                                          volume1, volume2, total, n_tree_nodes */
     AGBNP_B200_GET_TREE_SIZE = 6,         /* long long[1] number of overlap-tree nodes below the atom level */
     AGBNP_B200_GET_TREE_TOPOLOGY = 7,     /* int[4*M]   per node: root atom, parent (index into this dump, -1 = root
-                                                         atom), last atom, sibling rank; grouped by root atom */
+                                                         atom), last atom, sibling rank; a parent precedes its children */
     AGBNP_B200_GET_DERIV_Y = 8,           /* double[N]  Y_i (GB derivative accumulator) */
     AGBNP_B200_GET_DERIV_WU = 9,          /* double[N]  (W_i + U_i) before division by the atomic volume */
     AGBNP_B200_GET_NEIGHBOR_PAIRS = 10,   /* int[2*P]   (i<j) with r2 < cutoff2 as used by the GB pass (cutoff mode) */

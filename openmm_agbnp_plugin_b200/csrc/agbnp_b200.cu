@@ -234,7 +234,12 @@ struct agbnp_b200 {
     size_t slab_keep_off = 0;               // slab offset of root_cnt: a rescan evaluation zeroes the slab only up to here
     DevBuf<int> d_root_off, d_bcount;
     DevBuf<int2> d_items;
-    std::vector<int2> items;                // tree work items (root, part | parts << 8), most expensive first (host)
+    // tree work items, most expensive first (host copy): x = index of the item's first root in item_roots,
+    // y = number of roots | part << 8 | parts << 16 (agbnp_tree.cuh: item_roots(), item_part(), item_parts())
+    std::vector<int2> items;
+    std::vector<int> item_roots;            // sorted indices of the items' roots
+    DevBuf<int> d_item_roots;
+    bool tree_group = true;                 // several small neighboring roots per item (AGBNP_B200_TREE_GROUP=0: one root per item)
     int max_items = 0;
     DevBuf<unsigned short> d_blist;
     float rc2_global = 0.f;
@@ -434,26 +439,59 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
         // work items: a root whose neighbor count predicts a large subtree is split into parts (agbnp_tree.cuh), so that no
         // single warp carries a subtree that bounds the kernel's duration
         h->max_items = 2*h->nhp + 64;
-        struct It { int root, part, parts; float cost; };
+        struct It { int first, nroots, part, parts; float cost; };
         std::vector<It> its;
+        h->item_roots.clear();
         int budget = h->max_items - nh;
         // cost model: a subtree grows like the cube of its level-2 list.  A root is split when it alone would exceed twice
         // the balanced load of one resident warp (16 per SM, all shards together): large systems split only their extreme
         // tail (splitting repeats the level-2 work), small ones split everything that shortens the critical path
         double total = 0;
         for (int k = 0; k < nh; k++) total += 1.0 + (double) count[k]*count[k]*count[k];
-        const double per_warp = total/((double) h->num_sm*16*h->cfg.shard_count);
+        const double warps = (double) h->num_sm*16*h->cfg.shard_count;
+        const double per_warp = total/warps;
+        // Small roots that follow each other in the (Morton) order share one item: a warp builds their subtrees together,
+        // level by level, so that the per-level passes run on fuller chunks and their latency is paid once (the average
+        // level of a single root offers 25 nodes to 32 lanes).  Predictions from the later-neighbor count c (fit on 2clr):
+        // nodes ~ 0.85 (c+1)^1.85, widest level ~ 0.4 nodes, listed level-2 candidates (with the skin) ~ 2.5 c.  A group is
+        // closed when it would pass the node target -- sized so that every resident warp still gets about six items (measured on
+        // HIV-RT: k_tree 161.7 / 152.1 / 150.4 / 151.1 us with 3 / 4 / 6 / 10 items per warp, 154.6 us ungrouped: larger groups
+        // lose to load imbalance what they gain in lane use, so in effect only the smallest roots are merged) -- or
+        // what the DEFAULT per-level / level-2 capacities hold comfortably (fixed numbers: every shard must form the same
+        // items whatever its own capacities have grown to); the capacities grow as usual if a prediction was too low.
+        double pred_total = 0;
+        std::vector<float> pred(nh);
+        for (int k = 0; k < nh; k++) { pred[k] = 0.85f*std::pow((float) count[k]+1.f, 1.85f); pred_total += pred[k]; }
+        static const double items_per_warp = std::getenv("AGBNP_B200_TREE_GROUP_TARGET") ? std::atof(std::getenv("AGBNP_B200_TREE_GROUP_TARGET")) : 6.0;
+        const float node_target = (float) std::min(300.0, std::max(40.0, pred_total/(items_per_warp*warps)));
+        const float width_target = 110.f, nbr_target = 50.f;
+        It open{0, 0, 0, 1, 0.f};
+        float g_nodes = 0.f, g_nbr = 0.f;
+        auto close = [&]() { if (open.nroots) { its.push_back(open); open.nroots = 0; } };
         for (int k = 0; k < nh; k++) {
             const double c = 1.0 + (double) count[k]*count[k]*count[k];
             int parts = (int) std::min(8.0, std::ceil(c/std::max(2.0*per_warp, 64.0)));
             parts = std::max(1, std::min(parts, count[k]/4));
             parts = std::min(parts, 1+std::max(0, budget));
             budget -= parts-1;
-            for (int q = 0; q < parts; q++) its.push_back({k, q, parts, (float) (c/parts)});
+            const float nbr_k = 2.5f*(float) count[k];
+            if (parts > 1 || !h->tree_group) {
+                close();
+                const int first = (int) h->item_roots.size();
+                h->item_roots.push_back(k);
+                for (int q = 0; q < parts; q++) its.push_back({first, 1, q, parts, (float) (c/parts)});
+                continue;
+            }
+            if (open.nroots && (open.nroots >= TREE_GROUP_MAX || g_nodes + pred[k] > node_target || 0.4f*(g_nodes + pred[k]) > width_target ||
+                                g_nbr + nbr_k > nbr_target)) close();
+            if (!open.nroots) { open = It{(int) h->item_roots.size(), 0, 0, 1, 0.f}; g_nodes = 0.f; g_nbr = 0.f; }
+            h->item_roots.push_back(k);
+            open.nroots++; open.cost += (float) c; g_nodes += pred[k]; g_nbr += nbr_k;
         }
+        close();
         std::stable_sort(its.begin(), its.end(), [](const It& a, const It& b) { return a.cost > b.cost; });
         h->items.clear();
-        for (const It& t : its) h->items.push_back(make_int2(t.root, t.part | (t.parts << 8)));
+        for (const It& t : its) h->items.push_back(make_int2(t.first, t.nroots | (t.part << 8) | (t.parts << 16)));
     }
     // block bounding boxes at sort time: used only to ORDER and PACK the work units of the range-limited pair passes
     // (heaviest first, far-apart block pairs packed several per unit); membership is decided on the device every evaluation
@@ -550,6 +588,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     for (float v : sp.rc2max) h->rc2_global = std::max(h->rc2_global, v);
     { const float r = std::sqrt(h->rc2_global) + h->pq_skin; h->rc2_global = r*r*1.000001f; }
     h->d_items.upload(h->items, s);
+    h->d_item_roots.upload(h->item_roots, s);
     h->d_bcount.alloc(std::max(1, h->nhb)); h->d_blist.alloc((size_t) std::max(1, h->nhb)*BLIST_MAX);
     // I4 splines in power form around the left knot (see agbnp_pair.cuh): with zl = y2_k h^2/6, zu = y2_{k+1} h^2/6,
     //   y(fr) = yl + fr [(yu-yl) - 2 zl - zu] + fr^2 [3 zl] + fr^3 [zu - zl]
@@ -722,6 +761,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
         ta.items = h->d_items.p; ta.nitems = (int) h->items.size(); ta.bcount = h->d_bcount.p; ta.blist = h->d_blist.p;
+        ta.item_roots = h->d_item_roots.p;
         ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.l2rec = h->d_l2rec.p; ta.rcbin = h->d_rcbin.p;
         ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;
         ta.bbc = h->d_bbc.p; ta.bbh = h->d_bbh.p; ta.rc2 = h->d_rc2.p; ta.rc2max = h->d_rc2max.p; ta.nbins = h->sp.nbins;
@@ -1163,6 +1203,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         { const char* ng = std::getenv("AGBNP_B200_NO_GRAPH"); h->use_graph = !(ng && ng[0] == '1'); }
         { const char* ng = std::getenv("AGBNP_B200_NO_PDL"); h->use_pdl = !(ng && ng[0] == '1'); }
         if (const char* sk = std::getenv("AGBNP_B200_PAIR_SKIN")) h->pq_skin = std::max(0.f, (float) std::atof(sk));
+        if (const char* tg = std::getenv("AGBNP_B200_TREE_GROUP")) h->tree_group = tg[0] != '0';
         for (auto& e2 : h->ev) CK(cudaEventCreate(&e2));
         for (auto& e2 : h->async_ev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->tail_ev, cudaEventDisableTiming));
@@ -1442,32 +1483,39 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             CK(cudaMemcpy(lvs.data(), h->st.root_lvs, sizeof(short)*ni*MAX_LEVELS, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(rec.data(), h->st.rec, sizeof(float4)*2*cur, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(rank.data(), h->st.rank, sizeof(short)*cur, cudaMemcpyDeviceToHost));
-            // items grouped by root, roots in increasing caller index; a node is reported by the part that owns it
+            // items ordered by the caller index of their first root (parts of a split root follow each other); a node is
+            // reported by the part that owns it; a parent always precedes its children
             std::vector<int> order(ni);
             for (int i = 0; i < ni; i++) order[i] = i;
+            auto first_root = [&](int i) { return h->orig[h->item_roots[h->items[i].x]]; };
             std::sort(order.begin(), order.end(), [&](int a, int b) {
-                const int ra = h->orig[h->items[a].x], rb = h->orig[h->items[b].x];
-                return ra != rb ? ra < rb : (h->items[a].y & 0xff) < (h->items[b].y & 0xff);
+                const int ra = first_root(a), rb = first_root(b);
+                return ra != rb ? ra < rb : item_part(h->items[a]) < item_part(h->items[b]);
             });
             int* o = (int*) host_out;
             long long w = 0;
             std::vector<long long> dump_of;
+            std::vector<int> root_of;
             for (int i : order) {
-                const int r = h->items[i].x, part = h->items[i].y & 0xff, parts = h->items[i].y >> 8;
+                const int ng = item_nroots(h->items[i]), part = item_part(h->items[i]), parts = item_parts(h->items[i]);
                 const int n = cnt[i];
-                if (n <= 1) continue;
-                const int l3 = lvs[(size_t) i*MAX_LEVELS+3];         // end of level 2 (level 2 exists: n > 1)
+                if (n <= ng) continue;                                  // roots without overlaps
+                const int l3 = lvs[(size_t) i*MAX_LEVELS+3];         // end of level 2 (level 2 exists: n > ng)
                 dump_of.assign(n, -1);
-                for (int sl = 1; sl < n; sl++) {
+                root_of.assign(n, -1);
+                for (int g = 0; g < ng; g++) root_of[g] = h->orig[h->item_roots[h->items[i].x+g]];
+                for (int sl = ng; sl < n; sl++) {
                     const size_t g = (size_t) off[i]+sl;
                     int a, pk;
                     std::memcpy(&a, &rec[2*g].w, 4); std::memcpy(&pk, &rec[2*g+1].w, 4);
                     const int par = pk & 0xffff;
+                    if (par >= sl) throw CudaFail{"agbnp_b200_get: inconsistent tree store"};
+                    root_of[sl] = root_of[par];
                     if (sl < l3 && rank[g] % parts != part) continue;   // a level-2 node of another part
                     if ((unsigned long long) w >= cm) throw CudaFail{"agbnp_b200_get: inconsistent tree store"};
                     dump_of[sl] = w;
-                    o[4*w+0] = h->orig[r];
-                    o[4*w+1] = par == 0 ? -1 : (int) dump_of[par];
+                    o[4*w+0] = root_of[sl];
+                    o[4*w+1] = par < ng ? -1 : (int) dump_of[par];
                     o[4*w+2] = h->orig[a];
                     o[4*w+3] = rank[g];
                     w++;

@@ -29,6 +29,11 @@
 namespace agbnp_b200_impl {
 
 constexpr int MAX_LEVELS = 10;      // level index 1..8 used (MAX_ORDER 8)
+constexpr int TREE_GROUP_MAX = 4;   // most roots one work item may carry
+// work item (int2): x = index of its first root in item_roots[], y = number of roots | part << 8 | parts << 16
+__host__ __device__ inline int item_nroots(int2 it) { return it.y & 0xff; }
+__host__ __device__ inline int item_part(int2 it) { return (it.y >> 8) & 0xff; }
+__host__ __device__ inline int item_parts(int2 it) { return it.y >> 16; }
 #ifndef SCREEN_UNROLL
 #define SCREEN_UNROLL 1             // candidates per lane and trip of the FP32 screen (measured: 1 is fastest on B200)
 #endif
@@ -36,10 +41,15 @@ constexpr int MAX_LEVELS = 10;      // level index 1..8 used (MAX_ORDER 8)
 // persisted per-node records for the gamma sweep and for the topology dump: two float4 per node,
 //   rec[2*o]   = (coefp*sfp, dvv1, a_i/a_1i, bits of the sorted index of the node's last atom)        (vdW radii)
 //   rec[2*o+1] = (dv1 x, y, z, bits of: parent slot (low 16 bits, 0xffff for the root) | has-children flag << 16)
-// The unit of tree work is an ITEM = (root atom, part k of K): the subtrees below different level-2 nodes of a root never
-// interact, so a large root is split into K parts; part k builds the root and all of its level-2 nodes (cheap, and needed
-// for the sibling lists) but owns and expands only the level-2 nodes at sorted positions t with t mod K == k.  The root's
-// own terms belong to part 0.  Everything a sweep adds is linear in the owned nodes, so the parts just add up.
+// The unit of tree work is an ITEM, one of two kinds (the host decides at sort time, agbnp_b200.cu: build_order):
+//   * (root atom, part k of K): the subtrees below different level-2 nodes of a root never interact, so a large root is
+//     split into K parts; part k builds the root and all of its level-2 nodes (cheap, and needed for the sibling lists) but
+//     owns and expands only the level-2 nodes at sorted positions t with t mod K == k.  The root's own terms belong to
+//     part 0.  Everything a sweep adds is linear in the owned nodes, so the parts just add up.
+//   * a GROUP of up to TREE_GROUP_MAX small roots that are neighbors in the sorted order: subtrees of different roots never
+//     interact either, so the group is built as one forest -- slots 0..G-1 are the roots (level 1), every later level holds
+//     the nodes of all of them, parents first -- and the per-level passes run on chunks that are fuller than any of the
+//     roots would fill alone.  Positions are relative to the first root of the item.
 struct TreeStore {
     int cap;                 // node capacity
     int* cursor;             // bump allocator
@@ -102,7 +112,8 @@ __global__ void __launch_bounds__(256) k_blocklist(BlockListArgs A) {
 
 struct TreeArgs {
     int nh, nhb, np;
-    const int2* items;                // [nitems] (root, part | parts << 8), most expensive first
+    const int2* items;                // [nitems] work items, most expensive first
+    const int* item_roots;            // sorted indices of the items' roots
     int nitems;
     const int* bcount;                // k_blocklist output
     const unsigned short* blist;
@@ -152,6 +163,7 @@ __host__ __device__ inline size_t tree_work_bytes(int nbrmax, int cap, int wcap)
              + (size_t) wcap*sizeof(int)                      // cand
              + (size_t) nbrmax*6*sizeof(float)                // nbx, nby, nbz, nba, nbv, nbi
              + (size_t) (MAX_LEVELS+2)*sizeof(int)            // lvs
+             + (size_t) 2*(TREE_GROUP_MAX+1)*sizeof(int)      // rt, nboff
              + (size_t) ((cap+31)/32)*sizeof(unsigned)        // hc
              + (size_t) (2*cap + 4*wcap)*sizeof(short);       // parent, nbr | cstart, ccount, perm, gend
     return (b + 15) & ~(size_t) 15;
@@ -201,6 +213,8 @@ struct TreeWork {
     float *nba, *nbv;        // [nbrmax] their enlarged-radius Gaussian exponent / volume rounded to float (screen only)
     int* nbi;                // [nbrmax] their sorted atom indices
     int* lvs;                // [MAX_LEVELS+2] first slot of each level
+    int* rt;                 // [TREE_GROUP_MAX+1] sorted atom indices of the item's roots (= slots 0 .. G-1)
+    int* nboff;              // [TREE_GROUP_MAX+1] first level-2 candidate of each root in nb*[]; nboff[G] = their number
     unsigned* hc;            // [cap/32] bit per slot: the node has children
     short *parent, *nbr;     // [cap] parent slot, level-2 neighbor index + 1 of the node's last atom
     short *cstart, *ccount;  // [wcap] first child slot / end of the child range of the nodes of the level being expanded (by
@@ -215,7 +229,8 @@ struct TreeWork {
         nbx = (float*) (cand+wcap); nby = nbx+nbrmax; nbz = nby+nbrmax; nba = nbz+nbrmax; nbv = nba+nbrmax;
         nbi = (int*) (nbv+nbrmax);
         lvs = nbi+nbrmax;
-        hc = (unsigned*) (lvs+MAX_LEVELS+2);
+        rt = lvs+MAX_LEVELS+2; nboff = rt+TREE_GROUP_MAX+1;
+        hc = (unsigned*) (nboff+TREE_GROUP_MAX+1);
         parent = (short*) (hc+(cap+31)/32); nbr = parent+cap; cstart = nbr+cap; ccount = cstart+wcap;
         perm = ccount+wcap; gend = perm+wcap;
     }
@@ -286,7 +301,7 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
                 if (has_kids) { const float4* hs = hu + 4*(sl+rd_off); h0 = hs[0]; h1 = hs[1]; h2 = hs[2]; }
                 int ja;
                 if (STORED) ja = ja_arr[sl];
-                else { const int ia = W.nbr[sl]; ja = ia == 0 ? r : W.nbi[ia-1]; }
+                else { const int ia = W.nbr[sl]; ja = ia == 0 ? W.rt[sl] : W.nbi[ia-1]; }     // ia == 0: a root, slot = its index
                 key = W.parent[sl];
                 if (!STORED && rec_out) {
                     // persist what the gamma sweep needs (TreeStore) while the records are in registers anyway
@@ -390,134 +405,156 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             if (item >= A.nitems) continue;
         } else if (item >= A.nitems) break;
         const int2 itm = A.items[item];
-        const int r = itm.x;
-#define part (itm.y & 0xff)
-#define nparts (itm.y >> 8)
+        const int ng = item_nroots(itm);
+#define part item_part(itm)
+#define nparts item_parts(itm)
+        const float4 pr = A.posq[A.item_roots[itm.x]];                // frame of the item: its first root
+        __syncwarp();                                                 // the previous item is done with the work arrays
+        if (lane < ng) W.rt[lane] = A.item_roots[itm.x+lane];
 
-        const float4 pr = A.posq[r];
-        const int orig_r = A.orig[r];
-        const int rb = A.rcbin[r];
-
-        // ---- level-2 candidate list: heavy atoms later in the caller's order within the conservative pair radius ----
-        int nn = 0;
-        if (rebuild_l2) {
-            // search: block lists -> atoms; candidates within the enlarged radius go to the root's stored list, those within
-            // the radius itself are this evaluation's candidates
-            int nl = 0;
-            const float rcmaxs = A.rc2maxs[rb];
-            int* mylist = A.l2list + (size_t) r*nbrmax;
-            const int nlist = A.bcount[r >> 5];
-            const int nscan = nlist >= 0 ? nlist : A.nhb;
-            for (int b0 = 0; b0 < nscan; b0 += 32) {
-                int b = b0+lane;
-                bool hit = false;
-                if (b < nscan) {
-                    if (nlist >= 0) b = A.blist[(r >> 5)*BLIST_MAX + b];
-                    hit = point_box_dist2(pr.x, pr.y, pr.z, A.bbc[b], A.bbh[b]) < rcmaxs;
-                }
-                unsigned m = __ballot_sync(FULL, hit);
-                while (m) {                                           // four listed blocks per trip: their loads overlap
-                    int jq[4];
-                    bool act[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        act[q] = m != 0;
-                        const int i = act[q] ? __ffs(m)-1 : 0;
-                        m &= m-1;
-                        jq[q] = __shfl_sync(FULL, b, i)*TILE+lane;
+        // ---- level-2 candidate lists: per root, heavy atoms later in the caller's order within the conservative pair radius ----
+        int nn = 0, nl_tot = 0;
+        for (int g = 0; g < ng; g++) {
+            const int r = A.item_roots[itm.x+g];
+            const float4 prg = A.posq[r];
+            const int orig_r = A.orig[r];
+            const int rb = A.rcbin[r];
+            if (lane == 0) W.nboff[g] = min(nn, nbrmax);
+            if (rebuild_l2) {
+                // search: block lists -> atoms; candidates within the enlarged radius go to the root's stored list, those
+                // within the radius itself are this evaluation's candidates
+                int nl = 0;
+                const float rcmaxs = A.rc2maxs[rb];
+                int* mylist = A.l2list + (size_t) r*nbrmax;
+                const int nlist = A.bcount[r >> 5];
+                const int nscan = nlist >= 0 ? nlist : A.nhb;
+                for (int b0 = 0; b0 < nscan; b0 += 32) {
+                    int b = b0+lane;
+                    bool hit = false;
+                    if (b < nscan) {
+                        if (nlist >= 0) b = A.blist[(r >> 5)*BLIST_MAX + b];
+                        hit = point_box_dist2(prg.x, prg.y, prg.z, A.bbc[b], A.bbh[b]) < rcmaxs;
                     }
-                    float4 pj[4];
-                    int4 rc[4];
+                    unsigned m = __ballot_sync(FULL, hit);
+                    while (m) {                                           // four listed blocks per trip: their loads overlap
+                        int jq[4];
+                        bool act[4];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) { pj[q] = A.posq[jq[q]]; rc[q] = A.l2rec[jq[q]]; }
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int ob = rc[q].x;
-                        const float dx = pj[q].x-pr.x, dy = pj[q].y-pr.y, dz = pj[q].z-pr.z;
-                        const float d2 = dx*dx + dy*dy + dz*dz;
-                        const int cls = rb*A.nbins + ((ob >> 24) & 0x7f);
-                        const bool later = act[q] && ((ob < 0 ? -1 : (ob & 0xffffff)) > orig_r);
-                        const bool listed = later && d2 < __ldg(A.rc2s + cls);
-                        const bool ok = listed && d2 < __ldg(A.rc2 + cls);
-                        const unsigned lm = __ballot_sync(FULL, listed);
-                        const unsigned am = __ballot_sync(FULL, ok);
-                        if (listed) {
-                            const int p = nl + __popc(lm & lanemask_lt());
-                            if (p < nbrmax) mylist[p] = jq[q];
+                        for (int q = 0; q < 4; q++) {
+                            act[q] = m != 0;
+                            const int i = act[q] ? __ffs(m)-1 : 0;
+                            m &= m-1;
+                            jq[q] = __shfl_sync(FULL, b, i)*TILE+lane;
                         }
-                        if (ok) {
-                            const int p = nn + __popc(am & lanemask_lt());
-                            if (p < nbrmax) {
-                                W.nbi[p] = jq[q]; W.nbx[p] = pj[q].x; W.nby[p] = pj[q].y; W.nbz[p] = pj[q].z;
-                                W.nba[p] = __int_as_float(rc[q].y); W.nbv[p] = __int_as_float(rc[q].z);
+                        float4 pj[4];
+                        int4 rc[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { pj[q] = A.posq[jq[q]]; rc[q] = A.l2rec[jq[q]]; }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int ob = rc[q].x;
+                            const float dx = pj[q].x-prg.x, dy = pj[q].y-prg.y, dz = pj[q].z-prg.z;
+                            const float d2 = dx*dx + dy*dy + dz*dz;
+                            const int cls = rb*A.nbins + ((ob >> 24) & 0x7f);
+                            const bool later = act[q] && ((ob < 0 ? -1 : (ob & 0xffffff)) > orig_r);
+                            const bool listed = later && d2 < __ldg(A.rc2s + cls);
+                            const bool ok = listed && d2 < __ldg(A.rc2 + cls);
+                            const unsigned lm = __ballot_sync(FULL, listed);
+                            const unsigned am = __ballot_sync(FULL, ok);
+                            if (listed) {
+                                const int p = nl + __popc(lm & lanemask_lt());
+                                if (p < nbrmax) mylist[p] = jq[q];
                             }
+                            if (ok) {
+                                const int p = nn + __popc(am & lanemask_lt());
+                                if (p < nbrmax) {
+                                    W.nbi[p] = jq[q]; W.nbx[p] = pj[q].x; W.nby[p] = pj[q].y; W.nbz[p] = pj[q].z;
+                                    W.nba[p] = __int_as_float(rc[q].y); W.nbv[p] = __int_as_float(rc[q].z);
+                                }
+                            }
+                            nl += __popc(lm);
+                            nn += __popc(am);
                         }
-                        nl += __popc(lm);
-                        nn += __popc(am);
                     }
                 }
-            }
-            if (lane == 0) A.l2cnt[r] = min(nl, nbrmax);
-            hw_nn = max(hw_nn, nl);
-            if (nl > nbrmax) nn = nl;                                 // the list itself overflowed: grow (below)
-        } else {
-            // walk the stored list: exact radius test, same order
-            const int nl = A.l2cnt[r];
-            const int* mylist = A.l2list + (size_t) r*nbrmax;
-            hw_nn = max(hw_nn, nl);
-            for (int e0 = 0; e0 < nl; e0 += 32) {
-                const int e = e0+lane;
-                const bool act = e < nl;
-                const int j = act ? mylist[e] : r;
-                const float4 pj = A.posq[j];
-                const int4 rc = A.l2rec[j];
-                const float dx = pj.x-pr.x, dy = pj.y-pr.y, dz = pj.z-pr.z;
-                const float d2 = dx*dx + dy*dy + dz*dz;
-                const bool ok = act && d2 < __ldg(A.rc2 + rb*A.nbins + ((rc.x >> 24) & 0x7f));
-                const unsigned am = __ballot_sync(FULL, ok);
-                if (ok) {
-                    const int p = nn + __popc(am & lanemask_lt());
-                    W.nbi[p] = j; W.nbx[p] = pj.x; W.nby[p] = pj.y; W.nbz[p] = pj.z;
-                    W.nba[p] = __int_as_float(rc.y); W.nbv[p] = __int_as_float(rc.z);
+                if (lane == 0) A.l2cnt[r] = min(nl, nbrmax);
+                nl_tot += nl;
+            } else {
+                // walk the stored list: exact radius test, same order
+                const int nl = A.l2cnt[r];
+                const int* mylist = A.l2list + (size_t) r*nbrmax;
+                nl_tot += nl;
+                for (int e0 = 0; e0 < nl; e0 += 32) {
+                    const int e = e0+lane;
+                    const bool act = e < nl;
+                    const int j = act ? mylist[e] : r;
+                    const float4 pj = A.posq[j];
+                    const int4 rc = A.l2rec[j];
+                    const float dx = pj.x-prg.x, dy = pj.y-prg.y, dz = pj.z-prg.z;
+                    const float d2 = dx*dx + dy*dy + dz*dz;
+                    const bool ok = act && d2 < __ldg(A.rc2 + rb*A.nbins + ((rc.x >> 24) & 0x7f));
+                    const unsigned am = __ballot_sync(FULL, ok);
+                    if (ok) {
+                        const int p = nn + __popc(am & lanemask_lt());
+                        if (p < nbrmax) {
+                            W.nbi[p] = j; W.nbx[p] = pj.x; W.nby[p] = pj.y; W.nbz[p] = pj.z;
+                            W.nba[p] = __int_as_float(rc.y); W.nbv[p] = __int_as_float(rc.z);
+                        }
+                    }
+                    nn += __popc(am);
                 }
-                nn += __popc(am);
             }
         }
-        hw_nn = max(hw_nn, nn);
-        if (nn > nbrmax) {
+        // the lists of all roots of the item share the level-2 capacity (a stored list is at most as long as it)
+        hw_nn = max(hw_nn, nl_tot);
+        if (nl_tot > nbrmax) {
             if (lane == 0) atomicOr(A.status, ST_NBR_OVERFLOW);
             continue;
         }
+        if (lane == 0) W.nboff[ng] = nn;
 
-        // ---- slot 0: the root atom (gaussvol.cpp:130-148) ----
-        const float gam_r = A.gamma[r];
+        // ---- slots 0 .. G-1: the root atoms (gaussvol.cpp:130-148), level 1 ----
         for (int w = lane; w < (cap+31)/32; w += 32) W.hc[w] = 0u;
-        if (lane == 0) {
-            NodeGauss g;
-            g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
-            g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
-            g.gam = gam_r; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
-            G[wcap] = g;                                          // level 1: the odd window
-            const float own = part == 0 ? 1.f : 0.f;              // the root's own terms belong to part 0
-            swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
-            swS[0] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
-            rk[0] = 0;
-            W.parent[0] = -1; W.nbr[0] = 0; W.perm[0] = 0; W.gend[0] = 1;
-            W.lvs[1] = 0;
-            W.sc4[0] = make_float4(0.f, 0.f, 0.f, (float) g.aL); W.scv[0] = (float) g.vL;
-            eL_tot += (double) (own*gam_r*(float) g.vL); eS_tot += (double) (own*gam_r*(float) g.vS);
-            vsumL += (double) (own*(float) g.vL); vsumS += (double) (own*(float) g.vS);
+        __syncwarp();
+        int npar1 = 0;                                                // roots with candidates, compacted into pl[] below
+        {
+            const bool isroot = lane < ng;
+            const int rg = isroot ? W.rt[lane] : W.rt[0];
+            const int cnt_g = isroot ? W.nboff[lane+1] - W.nboff[lane] : 0;
+            const unsigned hm = __ballot_sync(FULL, cnt_g > 0);
+            npar1 = __popc(hm);
+            if (isroot) {
+                const float4 pg = A.posq[rg];
+                const float gam_r = A.gamma[rg];
+                NodeGauss g;
+                g.aL = A.aL[rg]; g.vL = A.vL[rg];
+                g.xL = (double) pg.x - (double) pr.x; g.yL = (double) pg.y - (double) pr.y; g.zL = (double) pg.z - (double) pr.z;
+                g.aS = A.aS[rg]; g.vS = A.vS[rg]; g.xS = g.xL; g.yS = g.yL; g.zS = g.zL;
+                g.gam = gam_r; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
+                G[wcap+lane] = g;                                     // level 1: the odd window
+                const float own = part == 0 ? 1.f : 0.f;              // the root's own terms belong to part 0
+                swL[2*lane] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[2*lane+1] = make_float4(0.f, 0.f, 0.f, gam_r);
+                swS[2*lane] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[2*lane+1] = make_float4(0.f, 0.f, 0.f, gam_r);
+                rk[lane] = 0;
+                W.parent[lane] = -1; W.nbr[lane] = 0; W.perm[lane] = (short) lane; W.gend[lane] = (short) (lane+1);
+                W.sc4[lane] = make_float4((float) g.xL, (float) g.yL, (float) g.zL, (float) g.aL); W.scv[lane] = (float) g.vL;
+                eL_tot += (double) (own*gam_r*(float) g.vL); eS_tot += (double) (own*gam_r*(float) g.vS);
+                vsumL += (double) (own*(float) g.vL); vsumS += (double) (own*(float) g.vS);
+                // level 1 -> 2 in the candidate enumeration's terms: "parent" g owns candidates nboff[g] .. nboff[g+1]-1
+                if (cnt_g > 0) W.pl[__popc(hm & lanemask_lt())] = make_int2(lane, W.nboff[lane]);
+            }
+            if (lane == 0) { W.lvs[1] = 0; W.pl[npar1] = make_int2(0, nn); }
         }
         __syncwarp();
 
         // ---- breadth-first build: level -> level+1 ----
-        int nslots = 1, ls = 0, le = 1, level = 1;
+        int nslots = ng, ls = 0, le = ng, level = 1;
         bool failed = false;
         while (level < A.max_order) {           // a node at level >= MAX_ORDER gets no children (gaussvol.cpp:211)
             int T, npar = 0;
             const int width = le-ls;
             if (level == 1) {
-                T = nn;
+                T = nn; npar = npar1;           // pl[] was filled with the roots' candidate ranges above
             } else {
                 // candidates of the node at sorted position t: its younger siblings t+1 .. gend[t]-1 (gaussvol.cpp:221).
                 // The parents that have any are compacted into pl[] with the index of their first candidate, parent-major.
@@ -554,15 +591,17 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             for (int k0 = 0; k0 < T; k0 += 32) {
                 const int k = k0 + lane;
                 const bool valid = k < T;
-                int p = 0, kn = valid ? k : 0;
-                if (level > 1) {
+                int p, kn = valid ? k : 0;
+                {
                     const int s = W.pl[min(tp+1+lane, npar)].y - k0 - 1;  // start of parent tp+1+lane, relative to k0+1
                     const unsigned heads = __reduce_or_sync(FULL, (unsigned) s < 32u ? (1u << s) : 0u);
                     const int2 me = W.pl[min(tp + __popc(heads & lanemask_lt()), npar-1)];
                     tp += __popc(heads);
-                    const int u = min(me.x + 1 + (k - me.y), width-1);
                     p = W.perm[me.x];
-                    kn = valid ? (int) W.nbr[ls + W.perm[u]] - 1 : 0;
+                    if (level > 1) {            // the candidate atom is the sibling's; at level 1 it is the k-th listed neighbor
+                        const int u = min(me.x + 1 + (k - me.y), width-1);
+                        kn = valid ? (int) W.nbr[ls + W.perm[u]] - 1 : 0;
+                    }
                 }
                 const float4 g1 = W.sc4[p];
                 const float v1f = W.scv[p];
@@ -643,7 +682,8 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                         W.key[slot-new_start] = keyv;
                         const double mL = 2.0*df*gvol;                        // -dVdr
                         const float vl = (float) keyv;
-                        swL[2*slot] = make_float4(vl, (float) (sp*gvol + s), (float) (v1 > 0 ? gvol/v1 : 0.0), (float) a2/(float) g.aL);
+                        // dvv1 = V/V_parent feeds the sweeps only: a float division (the FP64 one is 30 instructions on the chain)
+                        swL[2*slot] = make_float4(vl, (float) (sp*gvol + s), v1 > 0 ? (float) gvol/(float) v1 : 0.f, (float) a2/(float) g.aL);
                         swL[2*slot+1] = make_float4((float) ((x2-x1)*mL), (float) ((y2-y1)*mL), (float) ((z2-z1)*mL), gam);
                         // vdW radii on the same topology (rescan, gaussvol.cpp:261-279)
                         const double ex = x2-u1, ey = y2-q1, ez = z2-r1;
@@ -658,7 +698,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
                         W.scv[slot-new_start] = (float) gvol;
                         const double mS = 2.0*dfS*gS;
                         const float vs = (float) (sS*gS);
-                        swS[2*slot] = make_float4(vs, (float) (spS*gS + sS), (float) (w1 > 0 ? gS/w1 : 0.0), (float) b2/(float) g.aS);
+                        swS[2*slot] = make_float4(vs, (float) (spS*gS + sS), w1 > 0 ? (float) gS/(float) w1 : 0.f, (float) b2/(float) g.aS);
                         swS[2*slot+1] = make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam);
                         W.parent[slot] = (short) p; W.nbr[slot] = (short) (kn+1);
                         // energies and volumes need no tree accumulation (gaussvol.cpp:425-433 summed over the subtree)
@@ -717,7 +757,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
         if (lane == 0) W.lvs[level+1] = nslots;
         __syncwarp();
         const int nlev = level;
-        if (nparts == 1) m_tot += (lane == 0) ? (unsigned long long) (nslots-1) : 0ull;
+        if (nparts == 1) m_tot += (lane == 0) ? (unsigned long long) (nslots-ng) : 0ull;
         else m_tot += (lane == 0 && nlev >= 2) ? (unsigned long long) (nslots-W.lvs[3]) : 0ull;   // + the owned level-2 nodes counted above
 
         // ---- bottom-up sweep, both radius sets (gaussvol.cpp:400-487); it also persists what the gamma sweep needs ----
@@ -731,7 +771,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CT
             if (lane == 0) { A.st.root_off[item] = off; A.st.root_cnt[item] = nslots; }
             if (lane <= nlev+1 && lane >= 1) A.st.root_lvs[item*MAX_LEVELS+lane] = (short) W.lvs[lane];
         }
-        tree_sweep<false>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS, nullptr,
+        tree_sweep<false>(W, swL, swS, hu, nlev, 0, lane, A.accL, A.accS, nullptr,
                           fits ? A.st.rec + 2*(size_t) off : nullptr, fits ? A.st.rank + off : nullptr, rk, wcap);
         __syncwarp();
     }
@@ -823,8 +863,7 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
         int nlev = 1;
         while (nlev+1 < MAX_LEVELS && slv[nlev+1] < cnt) nlev++;
         const int2 itm = A.items[item];
-        const int r = itm.x, part = itm.y & 0xff, nparts = itm.y >> 8;
-        const float4 pr = A.posq[r];
+        const int ng = item_nroots(itm), part = item_part(itm), nparts = item_parts(itm);
         __syncwarp();                               // the previous item is done with the work arrays
         if (lane >= 1 && lane <= nlev) W.lvs[lane] = slv[lane];
         if (lane == 0) W.lvs[nlev+1] = cnt;
@@ -834,17 +873,22 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
             W.parent[sl] = (short) (pk & 0xffff);   // 0xffff (the root) becomes -1
             W.ccount[sl] = (short) ((pk >> 16) & 1);
         }
-        // slot 0: the root atom (gaussvol.cpp:130-148)
-        const float gam_r = A.gamma[r];
-        if (lane == 0) {
+        __syncwarp();
+        // slots 0 .. G-1: the root atoms (gaussvol.cpp:130-148); positions are relative to the first root, as in k_tree
+        const float4 pr = A.posq[ja[0]];
+        if (lane < ng) {
+            const int rg = ja[lane];
+            const float4 pg = A.posq[rg];
+            const float gam_r = A.gamma[rg];
             NodeGauss g;
-            g.aL = A.aL[r]; g.vL = A.vL[r]; g.xL = g.yL = g.zL = 0.0;
-            g.aS = A.aS[r]; g.vS = A.vS[r]; g.xS = g.yS = g.zS = 0.0;
+            g.aL = A.aL[rg]; g.vL = A.vL[rg];
+            g.xL = (double) pg.x - (double) pr.x; g.yL = (double) pg.y - (double) pr.y; g.zL = (double) pg.z - (double) pr.z;
+            g.aS = A.aS[rg]; g.vS = A.vS[rg]; g.xS = g.xL; g.yS = g.yL; g.zS = g.zL;
             g.gam = gam_r; g.pad[0] = g.pad[1] = g.pad[2] = 0.f;
-            G[0] = g;
+            G[lane] = g;
             const float own = part == 0 ? 1.f : 0.f;
-            swL[0] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[1] = make_float4(0.f, 0.f, 0.f, gam_r);
-            swS[0] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            swL[2*lane] = make_float4(own*(float) g.vL, 1.f, 1.f, 1.f); swL[2*lane+1] = make_float4(0.f, 0.f, 0.f, gam_r);
+            swS[2*lane] = make_float4(own*(float) g.vS, 1.f, 1.f, 1.f); swS[2*lane+1] = make_float4(0.f, 0.f, 0.f, gam_r);
             eL_tot += (double) (own*gam_r*(float) g.vL); eS_tot += (double) (own*gam_r*(float) g.vS);
             vsumL += (double) (own*(float) g.vL); vsumS += (double) (own*(float) g.vS);
         }
@@ -905,7 +949,7 @@ __global__ void __launch_bounds__(64, 8) k_tree_rescan(RescanArgs A) {
             __syncwarp();
         }
         if (lane == 0) atomicAdd(A.st.cursor, cnt);  // the control word reports the size of the tree, as after a build
-        tree_sweep<true>(W, swL, swS, hu, nlev, r, lane, A.accL, A.accS, ja);
+        tree_sweep<true>(W, swL, swS, hu, nlev, 0, lane, A.accL, A.accS, ja);
     }
     eL_tot = warp_sum(eL_tot); eS_tot = warp_sum(eS_tot); vsumL = warp_sum(vsumL); vsumS = warp_sum(vsumS);
     m_tot = (unsigned long long) warp_sum((double) m_tot);
