@@ -87,17 +87,35 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
                             double* energy, double* forces);
 
 /* == CalcAGBNPForceKernel::execute, device buffers (the CUDA-platform calling convention).
- *   d_posq        device float4[padded or N]: x,y,z (nm) and charge slot (ignored; charges come from create/set_params)
+ *   d_posq        device float4[padded or N] (double4 after agbnp_b200_set_device_layout(posq_is_double)): x,y,z (nm) and a
+ *                 charge slot that is ignored (charges come from create/set_params)
  *   stream        cudaStream_t cast to void* (NULL = default stream); all work is enqueued on it
  *   d_force       device force sink, or NULL:
  *                   layout 0: float[3*N] xyz-interleaved, forces are added (+=)
  *                   layout 1: OpenMM CUDA fixed point: unsigned long long[3*padded_n], component-major
  *                             (x[0..padded_n), y[..], z[..]), value*2^32, added with 64-bit atomics
- *   d_energy      device double accumulator to which the energy is added, or NULL
+ *   d_energy      device double (float after agbnp_b200_set_device_layout(energy_is_float)) accumulator to which the energy
+ *                 is added, or NULL
  *   h_energy      host double receiving the energy (forces a stream synchronize), or NULL
  * Returns after enqueueing unless h_energy is given (see "Asynchronous use" below). */
 int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, void* d_force, int force_layout,
                               int padded_n, double* d_energy, double* h_energy);
+
+/* Layout of the caller's DEVICE buffers, for a caller that is OpenMM's CUDA platform (CudaContext):
+ *   atom_index       host int[N]: atom_index[p] = the particle (numbered as in agbnp_b200_create) whose position is stored at
+ *                    index p of d_posq and whose force belongs at index p of d_force -- CudaContext::getAtomIndex(), which
+ *                    changes whenever the context reorders its atoms (call this again from a CudaContext::ReorderListener).
+ *                    NULL = identity.  The array is copied.
+ *   posq_is_double   d_posq is double4[] (CudaContext::getUseDoublePrecision()) instead of float4[]
+ *   energy_is_float  d_energy points to a float accumulator (CudaContext's energy buffer in single-precision mode)
+ * Takes effect from the next evaluation; the handle, its parameters and its internal (spatial) atom order are untouched, so
+ * a reorder costs one N-int upload.  agbnp_b200_execute_host ignores the layout (its arrays are in particle order). */
+typedef struct {
+    const int* atom_index;
+    int posq_is_double;
+    int energy_is_float;
+} agbnp_b200_device_layout;
+int agbnp_b200_set_device_layout(agbnp_b200* h, const agbnp_b200_device_layout* layout /* NULL = defaults */);
 
 /* Asynchronous use of agbnp_b200_execute_device (h_energy == NULL): the call returns after enqueueing; forces and energy
  * are delivered on the stream by the last kernel of the evaluation, and only if no internal capacity overflowed (the

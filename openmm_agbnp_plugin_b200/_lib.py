@@ -21,6 +21,10 @@ class Config(C.Structure):
                 ("tree_reuse_interval", C.c_int)]
 
 
+class DeviceLayout(C.Structure):
+    _fields_ = [("atom_index", C.POINTER(C.c_int)), ("posq_is_double", C.c_int), ("energy_is_float", C.c_int)]
+
+
 _lib = None
 
 
@@ -45,6 +49,7 @@ def lib():
         L.agbnp_b200_execute_host.argtypes = [vp, dp, C.c_int, C.c_int, dp, dp]
         L.agbnp_b200_execute_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, dp]
         L.agbnp_b200_synchronize.argtypes = [vp, vp]
+        L.agbnp_b200_set_device_layout.argtypes = [vp, C.POINTER(DeviceLayout)]
         L.agbnp_b200_profile.argtypes = [vp, C.c_uint]
         L.agbnp_b200_profile_read.argtypes = [vp, dp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_char_p)]
         L.agbnp_b200_launch_count.argtypes = [vp]

@@ -219,6 +219,11 @@ struct agbnp_b200 {
     int* d_ctrl = nullptr;
     size_t slab_bytes = 0;
     DevBuf<float> d_force_out;              // float[3n] for the host path
+    // layout of the caller's DEVICE buffers (agbnp_b200_set_device_layout); the host entry point ignores it
+    DevBuf<int> d_io;                       // particle -> position, when the caller's buffers are in another atom order
+    std::vector<int> io;                    // host copy
+    bool io_set = false, posq_f64 = false, energy_f32 = false;
+    bool cur_io = false;                    // the evaluation being enqueued came in through a device entry point
     // tree
     // tree capacities (grown on overflow): nodes per root, nodes per level, level-2 neighbors per root
     int tree_cap = 512, tree_wcap = 192, nbrmax = 64;
@@ -737,7 +742,7 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         // a rescan evaluation keeps root_cnt (the tail of the slab): it says which stored subtrees exist
         PrepArgs pa{h->np, d_posq_in, h->d_orig.p, h->d_charge.p, h->d_posq.p, h->d_bbc.p, h->d_bbh.p,
                     (float4*) h->d_slab.p, (int) ((rescan ? h->slab_keep_off : h->slab_bytes)/sizeof(float4)),
-                    h->d_posq_ref.p, h->d_pq_ctl.p};
+                    h->d_posq_ref.p, h->d_pq_ctl.p, (h->cur_io && h->io_set) ? h->d_io.p : nullptr, (h->cur_io && h->posq_f64) ? 1 : 0};
         begin(K_PREP);
         launch(h, k_prep, (h->nb+7)/8, 256, 0, s, pa);
         end(K_PREP);
@@ -891,6 +896,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
             else fa.out_set = (float*) sink->ptr;
         }
         fa.energy_accum = sink ? sink->d_energy : nullptr;
+        fa.io = (h->cur_io && h->io_set) ? h->d_io.p : nullptr;
+        fa.energy_f32 = (h->cur_io && h->energy_f32) ? 1 : 0;
         begin(K_FINISH);
         launch(h, k_finish, (h->np+255)/256, 256, 0, s, fa);
         end(K_FINISH);
@@ -1040,9 +1047,22 @@ void prepare(agbnp_b200* h, const float* host_xyz, int stride, const void* d_pos
     if (!h->order_valid || h->evals_since_sort >= interval) {
         std::vector<float> tmp;
         if (!host_xyz) {
+            // positions from the caller's device buffer, in its layout (agbnp_b200_set_device_layout), to particle order
             tmp.resize((size_t) 4*h->n);
-            CK(cudaMemcpyAsync(tmp.data(), d_posq_in, sizeof(float4)*h->n, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            if (h->posq_f64) {
+                std::vector<double> t64((size_t) 4*h->n);
+                CK(cudaMemcpyAsync(t64.data(), d_posq_in, sizeof(double)*4*h->n, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                for (int o = 0; o < h->n; o++) for (int c = 0; c < 4; c++) tmp[(size_t) 4*o+c] = (float) t64[(size_t) 4*(h->io_set ? h->io[o] : o)+c];
+            } else {
+                CK(cudaMemcpyAsync(tmp.data(), d_posq_in, sizeof(float4)*h->n, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                if (h->io_set) {
+                    std::vector<float> t2(tmp.size());
+                    for (int o = 0; o < h->n; o++) for (int c = 0; c < 4; c++) t2[(size_t) 4*o+c] = tmp[(size_t) 4*h->io[o]+c];
+                    tmp.swap(t2);
+                }
+            }
             host_xyz = tmp.data(); stride = 4;
         }
         wait_own_work(h);                              // queued evaluations still read the arrays about to be replaced
@@ -1279,6 +1299,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         const double t0 = timing ? now() : 0;
         const int rc_deferred = async_drain(h);      // a fault of an earlier asynchronous evaluation is reported by this call
         std::string deferred_msg = h->err;
+        h->cur_io = false;
         pack_positions(pos, (float*) h->h_posq, h->n);
         CK(cudaMemcpyAsync(h->d_posq_in.p, h->h_posq, sizeof(float4)*h->n, cudaMemcpyHostToDevice, s));
         const double t1 = timing ? now() : 0;
@@ -1325,6 +1346,7 @@ int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, v
     try {
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = (cudaStream_t) stream;
+        h->cur_io = true;
         prepare(h, nullptr, 0, d_posq, s);
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
         if (!h_energy) return run_async(h, (const float4*) d_posq, s, &sink);
@@ -1334,6 +1356,32 @@ int agbnp_b200_execute_device(agbnp_b200* h, const void* d_posq, void* stream, v
         if (rc != AGBNP_B200_OK) return rc;
         *h_energy = h->h_scal[SC_TOTAL];
         if (rc_deferred != AGBNP_B200_OK) { h->err = deferred_msg; return rc_deferred; }
+    } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
+    return AGBNP_B200_OK;
+}
+
+int agbnp_b200_set_device_layout(agbnp_b200* h, const agbnp_b200_device_layout* lay) {
+    if (!h) return AGBNP_B200_ERR_ARG;
+    try {
+        CK(cudaSetDevice(h->cfg.device));
+        wait_own_work(h);                               // queued evaluations read the old index map
+        TrashScope ts(&h->trash);
+        h->launch_gen++;                                // cached graphs carry the old layout in their kernel arguments
+        if (!lay || !lay->atom_index) { h->io_set = false; h->io.clear(); }
+        else {
+            std::vector<int> inv(h->n, -1);
+            for (int p = 0; p < h->n; p++) {
+                const int o = lay->atom_index[p];
+                if (o < 0 || o >= h->n || inv[o] >= 0) { h->err = "agbnp_b200_set_device_layout: atom_index is not a permutation of 0..N-1"; return AGBNP_B200_ERR_ARG; }
+                inv[o] = p;
+            }
+            h->io = inv;
+            h->d_io.alloc(h->n);
+            CK(cudaMemcpy(h->d_io.p, inv.data(), sizeof(int)*h->n, cudaMemcpyHostToDevice));
+            h->io_set = true;
+        }
+        h->posq_f64 = lay && lay->posq_is_double;
+        h->energy_f32 = lay && lay->energy_is_float;
     } catch (const CudaFail& f) { h->err = f.msg; return AGBNP_B200_ERR_CUDA; }
     return AGBNP_B200_OK;
 }
@@ -1555,6 +1603,7 @@ int agbnp_b200_shard_phase(agbnp_b200* h, int phase, const void* d_posq, void* s
     try {
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = (cudaStream_t) stream;
+        h->cur_io = true;
         if (phase == 0) {
             if (!d_posq) return AGBNP_B200_ERR_ARG;
             prepare(h, nullptr, 0, d_posq, s);
@@ -1588,6 +1637,7 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
         CK(cudaSetDevice(h->cfg.device));
         cudaStream_t s = (cudaStream_t) stream;
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
+        h->cur_io = true;
         enqueue(h, nullptr, s, PH_FINISH, &sink);
         mark_tail(h, s);
         // asynchronous: the status words follow the evaluation through the same ring as agbnp_b200_execute_device's; the
@@ -1736,6 +1786,7 @@ int agbnp_b200_shard_evaluate(agbnp_b200* h, void* d_posq, int owner, void* stre
         cudaStream_t s = (cudaStream_t) stream;
         k_peer_broadcast<<<(int) std::min<size_t>(64, ((size_t) h->n+255)/256), 256, 0, s>>>((float4*) d_posq, (size_t) h->n, h->peer, owner);
         h->launches += 1;
+        h->cur_io = true;
         prepare(h, nullptr, 0, d_posq, s);                  // (re)sorting reads the broadcast positions; same evaluation count on every shard
         ForceSink sink{d_force, force_layout, padded_n > 0 ? padded_n : h->n, d_energy};
         launch_all(h, (const float4*) d_posq, s, &sink, true);

@@ -42,6 +42,10 @@ struct PrepArgs {
     int slab_vec;
     const float4* posq_ref;     // sorted positions at the time the pair masks were built (PairUnits::ctl)
     int* pq_ctl;                // [1] max over atoms of |x - x_ref|^2 (float bits; reset by k_finish)
+    // layout of the caller's device buffers (agbnp_b200_set_device_layout): particle -> position in the buffers (the CUDA
+    // platform reorders atoms), or null = identity; positions as double4 instead of float4 (its double-precision mode)
+    const int* io;
+    int posq_f64;
 };
 
 __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
@@ -57,7 +61,9 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
     float4 p;
     float lo[3], hi[3];
     if (o >= 0) {
-        p = A.posq_in[o];
+        const int src = A.io ? A.io[o] : o;
+        if (A.posq_f64) { const double4 q = ((const double4*) A.posq_in)[src]; p = make_float4((float) q.x, (float) q.y, (float) q.z, 0.f); }
+        else p = A.posq_in[src];
         p.w = A.charge[k];
         lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
     } else {
@@ -809,8 +815,10 @@ struct FinishArgs {
     float4* posq_ref;                   // reference positions of the pair masks: moved here when k_born rebuilt them
     int* pq_ctl;                        // PairUnits::ctl
     int* tree_ok_out;                   // build evaluations: 1 if the tree was built without overflow (read by k_tree_rescan)
-    double* energy_accum;               // optional device accumulator (+=)
+    double* energy_accum;               // optional device accumulator (+=); a float accumulator if energy_f32
     double* energy_out;                 // optional device/pinned-mapped slot (=)
+    const int* io;                      // particle -> position in the caller's force buffers, or null (see PrepArgs)
+    int energy_f32;
 };
 
 // sharded evaluations: this shard's status word, as 0/1, into the energy scalars, which the ENERGY exchange sums over the shards
@@ -854,7 +862,7 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
         const double e = (A.scalars[SC_EVOL_L] - A.scalars[SC_EVOL_S])*(double) A.inv_roffset + A.scalars[SC_EGB] + A.scalars[SC_EVDW];
         A.scalars[SC_TOTAL] = e;
         if (A.energy_out) *A.energy_out = e;
-        if (A.energy_accum) atomicAdd(A.energy_accum, e);
+        if (A.energy_accum) { if (A.energy_f32) atomicAdd((float*) A.energy_accum, (float) e); else atomicAdd(A.energy_accum, e); }
     }
     if (k >= A.np) return;
     const int o = A.orig[k];
@@ -869,11 +877,12 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
         fz += A.gb_scale*(double) g.z + (double) d.z + (double) t.z;
     }
     if (A.out_set) { A.out_set[3*o+0] = (float) fx; A.out_set[3*o+1] = (float) fy; A.out_set[3*o+2] = (float) fz; }
-    if (A.out_f32) { A.out_f32[3*o+0] += (float) fx; A.out_f32[3*o+1] += (float) fy; A.out_f32[3*o+2] += (float) fz; }
+    const int dst = A.io ? A.io[o] : o;
+    if (A.out_f32) { A.out_f32[3*dst+0] += (float) fx; A.out_f32[3*dst+1] += (float) fy; A.out_f32[3*dst+2] += (float) fz; }
     if (A.out_fixed) {
-        atomicAdd(&A.out_fixed[o], (unsigned long long) (long long) (fx*FORCE_SCALE));
-        atomicAdd(&A.out_fixed[(size_t) A.padded_n+o], (unsigned long long) (long long) (fy*FORCE_SCALE));
-        atomicAdd(&A.out_fixed[2*(size_t) A.padded_n+o], (unsigned long long) (long long) (fz*FORCE_SCALE));
+        atomicAdd(&A.out_fixed[dst], (unsigned long long) (long long) (fx*FORCE_SCALE));
+        atomicAdd(&A.out_fixed[(size_t) A.padded_n+dst], (unsigned long long) (long long) (fy*FORCE_SCALE));
+        atomicAdd(&A.out_fixed[2*(size_t) A.padded_n+dst], (unsigned long long) (long long) (fz*FORCE_SCALE));
     }
 }
 

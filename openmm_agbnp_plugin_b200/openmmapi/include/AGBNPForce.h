@@ -30,7 +30,7 @@ public:
     void updateParametersInContext(OpenMM::Context& context);
     bool usesPeriodicBoundaryConditions() const { return false; }
     void setVersion(int agbnp_version);          // 0 GVolSA, 1 AGBNP1, 2 AGBNP2; anything else throws
-    int getVersion() const { return version; }
+    unsigned int getVersion() const { return (unsigned int) version; }
 protected:
     OpenMM::ForceImpl* createImpl() const;
 private:

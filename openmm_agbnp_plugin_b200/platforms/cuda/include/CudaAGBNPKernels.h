@@ -6,24 +6,27 @@
 
 #include "AGBNPKernels.h"
 #include "agbnp_b200.h"
+#include "openmm/cuda/CudaContext.h"     // OpenMM's, or the stand-in under standalone/ (same interface)
 
 namespace AGBNPPlugin {
 
 class CudaCalcAGBNPForceKernel : public CalcAGBNPForceKernel {
 public:
-    CudaCalcAGBNPForceKernel(std::string name, const OpenMM::Platform& platform, void* platformContext, int device)
-        : CalcAGBNPForceKernel(name, platform), platformContext(platformContext), device(device), handle(0), numParticles(0) {}
+    CudaCalcAGBNPForceKernel(std::string name, const OpenMM::Platform& platform, OpenMM::CudaContext& cu)
+        : CalcAGBNPForceKernel(name, platform), cu(cu), handle(0), numParticles(0) {}
     ~CudaCalcAGBNPForceKernel();
     void initialize(const OpenMM::System& system, const AGBNPForce& force);
     double execute(OpenMM::ContextImpl& context, bool includeForces, bool includeEnergy);
     void copyParametersToContext(OpenMM::ContextImpl& context, const AGBNPForce& force);
     agbnp_b200* getHandle() { return handle; }
+    // tell the library where each particle lives in the context's buffers (CudaContext::getAtomIndex) and which precision
+    // they have; called at initialize and by the reorder listener
+    void syncDeviceLayout();
 private:
-    void* platformContext;      // CudaContext* with OpenMM, unused in the standalone build
-    int device;
+    class ReorderListener;
+    OpenMM::CudaContext& cu;
     agbnp_b200* handle;
     int numParticles;
-    std::vector<double> posBuffer, forceBuffer;
 };
 
 class CudaAGBNPKernelFactory : public OpenMM::KernelFactory {

@@ -1,13 +1,14 @@
 // CudaCalcAGBNPForceKernel + factory + plugin registration (see CudaAGBNPKernels.h).
+// One code path for OpenMM's CUDA platform and for the stand-in of this repository (platforms/cuda/standalone): positions
+// are read from the context's posq buffer, forces are added to its 64-bit fixed-point force buffer and the energy to its
+// energy buffer, all on the device and in the context's own atom order -- what platforms/opencl does with cl.getPosq() /
+// cl.getForceBuffers() / cl.getEnergyBuffer() in the reference (OpenCLAGBNPKernels.cpp:602,1448,555).
 #include "CudaAGBNPKernels.h"
 
 #include <string>
 #include <vector>
 
-#ifdef AGBNP_B200_WITH_OPENMM
-#include "openmm/cuda/CudaContext.h"
 #include "openmm/cuda/CudaPlatform.h"
-#endif
 
 using namespace AGBNPPlugin;
 using namespace OpenMM;
@@ -34,46 +35,54 @@ void check(int rc, agbnp_b200* h) {
 
 } // namespace
 
+// CudaContext reorders its atoms from time to time (and tells its listeners): the library keeps its parameters by particle
+// and only needs the new particle -> buffer position map
+class CudaCalcAGBNPForceKernel::ReorderListener : public CudaContext::ReorderListener {
+public:
+    explicit ReorderListener(CudaCalcAGBNPForceKernel& owner) : owner(owner) {}
+    void execute() { owner.syncDeviceLayout(); }
+private:
+    CudaCalcAGBNPForceKernel& owner;
+};
+
 CudaCalcAGBNPForceKernel::~CudaCalcAGBNPForceKernel() { agbnp_b200_destroy(handle); }
 
 void CudaCalcAGBNPForceKernel::initialize(const System& system, const AGBNPForce& force) {
     (void) system;
     numParticles = force.getNumParticles();
+    if (numParticles != cu.getNumAtoms()) throw OpenMMException("AGBNPForce must have exactly as many particles as the System it belongs to.");
     agbnp_b200_config cfg;
     agbnp_b200_default_config(&cfg);
     cfg.version = force.getVersion();
     cfg.nonbonded_method = (int) force.getNonbondedMethod();
     cfg.cutoff = force.getCutoffDistance();
-    cfg.device = device;
+    cfg.device = cu.getDeviceIndex();
     const ParamArrays p(force);
     check(agbnp_b200_create(&cfg, numParticles, p.radius.data(), p.gamma.data(), p.alpha.data(), p.charge.data(),
                             p.ishydrogen.data(), &handle), 0);
+    syncDeviceLayout();
+    cu.addReorderListener(new ReorderListener(*this));      // owned (and deleted) by the context
+}
+
+void CudaCalcAGBNPForceKernel::syncDeviceLayout() {
+    if (!handle) return;
+    agbnp_b200_device_layout lay;
+    lay.atom_index = cu.getAtomIndex().data();
+    lay.posq_is_double = cu.getUseDoublePrecision() ? 1 : 0;                                    // posq: double4 | float4
+    lay.energy_is_float = (cu.getUseDoublePrecision() || cu.getUseMixedPrecision()) ? 0 : 1;    // energy buffer: "mixed" type
+    check(agbnp_b200_set_device_layout(handle, &lay), handle);
 }
 
 double CudaCalcAGBNPForceKernel::execute(ContextImpl& context, bool includeForces, bool includeEnergy) {
-#ifdef AGBNP_B200_WITH_OPENMM
-    // positions and forces stay on the GPU: posq float4 in, fixed-point force buffer and energy buffer out
-    CudaContext& cu = *static_cast<CudaContext*>(platformContext);
+    (void) context;
     cu.setAsCurrent();
-    double* d_energy = includeEnergy ? (double*) cu.getEnergyBuffer().getDevicePointer() : 0;   // mixed/double precision energy buffer
+    // Asynchronous: everything is enqueued on the context's stream.  A capacity overflow of an evaluation is repaired inside
+    // the library but reported a few calls later (include/agbnp_b200.h, "Asynchronous use"): that step ran without the
+    // AGBNP forces, so the simulation must not silently continue -- the exception carries the library's message.
     check(agbnp_b200_execute_device(handle, (const void*) cu.getPosq().getDevicePointer(), (void*) cu.getCurrentStream(),
-                                    includeForces ? (void*) cu.getForce().getDevicePointer() : 0, 1, cu.getPaddedNumAtoms(),
-                                    d_energy, 0), handle);
-    return 0.0;                         // like the OpenCL platform: the energy is in the buffer
-#else
-    // host arrays, the Reference platform's convention (ReferenceAGBNPKernels.cpp:27-35): energy returned, forces added
-    HostPlatformData* data = static_cast<HostPlatformData*>(context.getPlatformData());
-    std::vector<Vec3>& pos = *data->positions;
-    std::vector<Vec3>& frc = *data->forces;
-    posBuffer.resize(3*(size_t) numParticles);
-    forceBuffer.assign(3*(size_t) numParticles, 0.0);
-    for (int i = 0; i < numParticles; i++) for (int c = 0; c < 3; c++) posBuffer[3*(size_t) i+c] = pos[i][c];
-    double energy = 0.0;
-    check(agbnp_b200_execute_host(handle, posBuffer.data(), includeForces, includeEnergy, &energy, forceBuffer.data()), handle);
-    if (includeForces)
-        for (int i = 0; i < numParticles; i++) frc[i] += Vec3(forceBuffer[3*(size_t) i], forceBuffer[3*(size_t) i+1], forceBuffer[3*(size_t) i+2]);
-    return energy;
-#endif
+                                    includeForces ? (void*) cu.getForce().getDevicePointer() : 0, 1 /* fixed point */, cu.getPaddedNumAtoms(),
+                                    includeEnergy ? (double*) cu.getEnergyBuffer().getDevicePointer() : 0, 0), handle);
+    return 0.0;                         // like the reference's OpenCL platform: the energy is in the context's buffer
 }
 
 void CudaCalcAGBNPForceKernel::copyParametersToContext(ContextImpl& context, const AGBNPForce& force) {
@@ -86,13 +95,9 @@ void CudaCalcAGBNPForceKernel::copyParametersToContext(ContextImpl& context, con
 KernelImpl* CudaAGBNPKernelFactory::createKernelImpl(std::string name, const Platform& platform, ContextImpl& context) const {
     if (name != CalcAGBNPForceKernel::Name())
         throw OpenMMException("Tried to create kernel with illegal kernel name '" + name + "'");
-#ifdef AGBNP_B200_WITH_OPENMM
+    // same shape as the reference's OpenCL factory (OpenCLAGBNPKernelFactory.cpp:40-45)
     CudaContext& cu = *static_cast<CudaPlatform::PlatformData*>(context.getPlatformData())->contexts[0];
-    return new CudaCalcAGBNPForceKernel(name, platform, &cu, cu.getDeviceIndex());
-#else
-    HostPlatformData* data = static_cast<HostPlatformData*>(context.getPlatformData());
-    return new CudaCalcAGBNPForceKernel(name, platform, 0, data->device);
-#endif
+    return new CudaCalcAGBNPForceKernel(name, platform, cu);
 }
 
 // ---- OpenMM plugin entry points (the names are OpenMM's plugin ABI) ----
@@ -111,11 +116,7 @@ extern "C" void registerAGBNPCudaKernelFactories() {
     try {
         Platform::getPlatformByName("CUDA");
     } catch (const std::exception&) {
-#ifdef AGBNP_B200_WITH_OPENMM
         Platform::registerPlatform(new CudaPlatform());
-#else
-        Platform::registerPlatform(new Platform("CUDA"));
-#endif
     }
     registerKernelFactories();
 }

@@ -1,7 +1,8 @@
 // Minimal stand-in for the handful of OpenMM types the AGBNP plugin touches, used ONLY when the plugin is built without an
 // OpenMM installation (this image has none): enough of Platform / KernelFactory / KernelImpl / ContextImpl / Context for
-// AGBNPForce -> AGBNPForceImpl -> CalcAGBNPForceKernel to run exactly as it does inside OpenMM, with the Reference
-// platform's host-array calling convention (positions and forces as std::vector<Vec3>).
+// AGBNPForce -> AGBNPForceImpl -> CalcAGBNPForceKernel to run exactly as it does inside OpenMM's CUDA platform: the
+// context owns a CudaContext (openmm/cuda/CudaContext.h stand-in) with device-resident posq / force / energy buffers in
+// the platform's atom order and precision, and the kernel object reads and writes those.
 // With -DAGBNP_B200_WITH_OPENMM the real headers are used and this file is not included.
 #ifndef AGBNP_B200_OPENMM_MINI_H_
 #define AGBNP_B200_OPENMM_MINI_H_
@@ -129,20 +130,16 @@ public:
     virtual std::vector<std::string> getKernelNames() = 0;
 };
 
-// what a platform hangs on the context; the standalone "CUDA" platform uses host arrays like the Reference platform
-struct HostPlatformData {
-    std::vector<Vec3>* positions;
-    std::vector<Vec3>* forces;
-    int device;
-};
+class CudaContext;
 
 class ContextImpl {
 public:
-    ContextImpl(Context& owner, const System& system, Platform& platform, int device);
+    ContextImpl(Context& owner, const System& system, Platform& platform, int device, const std::string& precision);
     ~ContextImpl();
     const System& getSystem() const { return *system; }
     Platform& getPlatform() { return *platform; }
-    void* getPlatformData() { return &data; }
+    void* getPlatformData() { return data; }                // CudaPlatform::PlatformData*
+    CudaContext& getCudaContext();
     Context& getOwner() { return *owner; }
     double calcForcesAndEnergy(bool includeForces, bool includeEnergy);
     ForceImpl& getImpl(const Force* f);
@@ -151,15 +148,17 @@ private:
     Context* owner;
     const System* system;
     Platform* platform;
-    HostPlatformData data;
+    void* data;
     std::vector<ForceImpl*> impls;
 };
 
 class Context {
 public:
-    Context(const System& system, Platform& platform, int device = 0) : impl(new ContextImpl(*this, system, platform, device)) {}
+    // precision: the CUDA platform's "Precision" property ("single" | "mixed" | "double")
+    Context(const System& system, Platform& platform, int device = 0, const std::string& precision = "single")
+        : impl(new ContextImpl(*this, system, platform, device, precision)) {}
     ~Context() { delete impl; }
-    void setPositions(const std::vector<Vec3>& p) { impl->positions = p; }
+    void setPositions(const std::vector<Vec3>& p);
     double getPotentialEnergy() { return impl->calcForcesAndEnergy(true, true); }     // State::Energy | State::Forces
     const std::vector<Vec3>& getForces() const { return impl->forces; }
     ContextImpl& getImpl() { return *impl; }

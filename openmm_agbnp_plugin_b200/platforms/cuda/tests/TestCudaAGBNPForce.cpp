@@ -1,10 +1,12 @@
-// TestCudaAGBNPForce [version] < system.dat
+// TestCudaAGBNPForce [version] [precision: single|mixed|double] < system.dat
 // The CUDA-platform twin of the reference's platforms/reference/tests/TestReferenceAGBNPForce.cpp: same stdin format
 // (N, then per line: id x y z radius[A] charge gamma[kcal/mol/A^2] ishydrogen), same unit conversions and alpha rule
 // (:47-70), same "Energy:" output, plus the finite-difference lines of v0.reference / v1.reference (atom 121, +2e-3 nm in y).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "AGBNPForce.h"
@@ -38,11 +40,27 @@ int main(int argc, char** argv) {
             const double alpha = -16.0*M_PI*rho*eij*std::pow(sij, 6)/3.0;
             force->addParticle(radius, gamma, alpha, charge, ih > 0);
         }
-        Context context(system, Platform::getPlatformByName("CUDA"));
+        const std::string precision = argc > 2 ? argv[2] : "single";
+        Context context(system, Platform::getPlatformByName("CUDA"), 0, precision);
         context.setPositions(positions);
         const double e1 = context.getPotentialEnergy();
         const std::vector<Vec3> forces = context.getForces();
         std::cout << "Energy: " << e1 << std::endl;
+#ifndef AGBNP_B200_WITH_OPENMM
+        // The CUDA platform reorders its atoms between steps (CudaContext::reorderAtoms -> ReorderListener): the kernel must
+        // follow the new buffer order, and no particle's force may change.  (Stand-in only: with OpenMM the context decides.)
+        for (int round = 0; round < 2; round++) {
+            context.getImpl().getCudaContext().reorderAtoms();
+            const double er = context.getPotentialEnergy();
+            const std::vector<Vec3>& fr = context.getForces();
+            double dmax = 0.0, fmax = 0.0;
+            for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) {
+                dmax = std::max(dmax, std::fabs(fr[i][c]-forces[i][c])); fmax = std::max(fmax, std::fabs(forces[i][c]));
+            }
+            std::cout << "Reorder relative energy change: " << std::fabs(er-e1)/std::fabs(e1) << std::endl;
+            std::cout << "Reorder relative force change: " << dmax/fmax << std::endl;
+        }
+#endif
         const int pmove = 121, direction = 1;
         if (n > pmove) {
             const double offset = 2.e-3;

@@ -281,6 +281,54 @@ def test_device_buffer_entry_point():
     assert relrms(ffix, f) <= 1e-6
 
 
+def test_device_layout_of_the_cuda_platform():
+    """agbnp_b200_set_device_layout: the caller's device buffers as OpenMM's CudaContext keeps them -- atoms in a platform
+    order that changes between evaluations (CudaContext::getAtomIndex + ReorderListener), positions as double4
+    (double-precision mode), energy buffer in float (single-precision mode), forces in 64-bit fixed point.  Permuting the
+    atom order between evaluations must not change the forces of any particle."""
+    import torch
+    s = load_system("trpcage")
+    pos = systems.float_rounded(s["pos"])
+    n = len(pos)
+    ctx, e, f = _gpu(s, pos, 1)
+    L = _lib.lib()
+    h = ctx.kernel.handle
+    stream = torch.cuda.current_stream().cuda_stream
+    padded = (n + 31) // 32 * 32
+    rng = np.random.default_rng(3)
+    results = []
+    for trial, (f64, ef32) in enumerate([(1, 1), (0, 0), (1, 0)]):
+        order = rng.permutation(n).astype(np.int32)               # order[p] = particle stored at buffer index p
+        lay = _lib.DeviceLayout(order.ctypes.data_as(C.POINTER(C.c_int)), f64, ef32)
+        assert L.agbnp_b200_set_device_layout(h, C.byref(lay)) == 0
+        buf = np.zeros((padded, 4), dtype=np.float64 if f64 else np.float32)
+        buf[:n, :3] = pos[order]
+        d_posq = torch.from_numpy(buf).cuda()
+        d_fix = torch.zeros((3, padded), dtype=torch.int64, device="cuda")
+        d_e = torch.zeros(1, dtype=torch.float32 if ef32 else torch.float64, device="cuda")
+        for rep in range(2):                                       # asynchronous, then synchronous
+            he = C.c_double(0)
+            rc = L.agbnp_b200_execute_device(h, C.c_void_p(d_posq.data_ptr()), C.c_void_p(stream), C.c_void_p(d_fix.data_ptr()), 1, padded,
+                                             C.c_void_p(d_e.data_ptr()), C.byref(he) if rep else None)
+            assert rc == 0, L.agbnp_b200_last_error(h)
+        assert L.agbnp_b200_synchronize(h, C.c_void_p(stream)) == 0
+        ffix = d_fix.cpu().numpy().astype(np.float64)[:, :n].T / 2.0 ** 32 / 2.0      # two evaluations accumulated
+        f_particle = np.zeros_like(ffix)
+        f_particle[order] = ffix                                   # buffer index p -> particle order[p]
+        assert relrms(f_particle, f) <= 1e-6
+        assert abs(d_e.item() / 2.0 - e) <= (2e-6 if ef32 else 1e-6) * abs(e)
+        assert abs(he.value - e) <= 1e-6 * abs(e)
+        results.append(f_particle)
+    assert relrms(results[0], results[1]) <= 1e-6 and relrms(results[1], results[2]) <= 1e-6
+    assert L.agbnp_b200_set_device_layout(h, None) == 0           # back to particle order, float4, double energy
+    bad = np.zeros(n, dtype=np.int32)
+    lay = _lib.DeviceLayout(bad.ctypes.data_as(C.POINTER(C.c_int)), 0, 0)
+    assert L.agbnp_b200_set_device_layout(h, C.byref(lay)) == _lib.ERR_ARG
+    ctx.setPositions(pos)
+    assert abs(ctx.calcForcesAndEnergy() - e) <= 1e-6 * abs(e)    # the host entry point ignores the layout
+    assert relrms(ctx.getForces(), f) <= 1e-6
+
+
 def test_edge_cases():
     """Edge inputs: a single heavy atom; only hydrogens besides one heavy atom; two atoms at overlap distance;
     a system smaller than one 32-atom block; coincident-free random cloud with all-distinct radii."""

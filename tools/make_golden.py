@@ -49,6 +49,14 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     g = load_gaussvol_dat(os.path.join(REF_TESTS, "gaussvol.dat"))
     np.savez_compressed(os.path.join(OUT, "gaussvol.npz"), **g)
+    # the same input in the reference's own text format (TestReferenceAGBNPForce.cpp:45-58), for the C++ test program
+    # (platforms/cuda/tests/TestCudaAGBNPForce < tests/golden/gaussvol.dat; CMake's ctest)
+    with open(os.path.join(OUT, "gaussvol.dat"), "w") as fh:
+        fh.write("%d\n" % len(g["radius"]))
+        for i in range(len(g["radius"])):
+            x, y, z = g["pos"][i] * 10.0
+            fh.write("%d %.17g %.17g %.17g %.17g %.17g %.17g %d\n" % (i, x, y, z, g["radius"][i] * 10.0, g["charge"][i],
+                                                                      g["gamma"][i] * 0.01 / 4.184, int(g["ishydrogen"][i])))
 
     def nums(path):
         return [float(x) for x in re.findall(r":\s*(-?[0-9.]+(?:e-?[0-9]+)?)", open(path).read())]
