@@ -612,6 +612,65 @@ def b200_arm(args):
         dist.destroy_process_group()
 
 
+def md_arm(args):
+    """bench.py --md STEPS [--workload W --cutoff C]: the reference's MD-benchmark protocol (example/hivrt_benchmark.py:17-33:
+    LangevinIntegrator(300 K, 1/ps, 1 fs), simulation.step(N)) driven on the GPU through md.LangevinMD -- per step one
+    asynchronous AGBNP evaluation and one fused integrator kernel.  Unlike the evaluation benchmark (independent jittered
+    inputs), consecutive steps here are a trajectory: the Verlet lists (pair masks, level-2 candidates) are rebuilt when
+    atoms have moved, as in production.  One JSON line: ns/day (BASELINE configs 2-3) next to steps/s."""
+    import torch
+    from openmm_agbnp_plugin_b200 import systems, md
+    s = workload()
+    n = len(s["pos"])
+    force = systems.make_force(s, 1, _WORKLOAD["method"], _WORKLOAD["cutoff"])
+    masses = np.where(s["ishydrogen"] > 0, 1.008, 12.0)
+    sim = md.LangevinMD(force, s["pos"], masses, temperature=300.0, friction_per_ps=args.md_friction, dt_ps=0.001, restraint_k=args.md_tether, seed=20261018)
+    warm = max(200, args.warmup)
+    sim.step(warm)                      # thermalise: lists get rebuilt at the rate of a running simulation
+    sim.synchronize()
+    st0 = sim.stats()
+    dropped0 = sim.dropped
+    sampler = ClockSampler(0)
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_r0 = time.time()
+    e0.record(stream)
+    sim.step(args.md)
+    e1.record(stream)
+    sim.synchronize()
+    torch.cuda.synchronize()
+    t_r1 = time.time()
+    clocks = sampler.result(t_r0, t_r1)
+    st1 = sim.stats()
+    ms = e0.elapsed_time(e1) / args.md
+    temp = sim.temperature()
+    ls = sim.list_stats()
+    # per-kernel times at the end state of the trajectory (separate, untimed: the profiling hooks need the plain-launch path)
+    from openmm_agbnp_plugin_b200 import _lib
+    L = _lib.lib()
+    hnd = sim.kernel.handle
+    sums = (C.c_double * 16)(); cnts = (C.c_int * 16)(); names_p = C.c_char_p()
+    L.agbnp_b200_profile(hnd, 0xffffffff)
+    sim.step(40)
+    sim.synchronize()
+    nk = L.agbnp_b200_profile_read(hnd, sums, cnts, 16, C.byref(names_p))
+    L.agbnp_b200_profile(hnd, 0)
+    kn = names_p.value.decode().split("\n")
+    kernels_us = {kn[i]: round(sums[i] / max(1, cnts[i]) * 1e3, 2) for i in range(nk) if cnts[i] > 0}
+    line = {"metric": "AGBNP1 MD throughput", "value": (1e3 / ms) * NS_PER_DAY_PER_EVAL_PER_S, "unit": "ns/day",
+            "steps_per_s": 1e3 / ms, "ms_per_step": ms, "n_gpus": 1, "steps": args.md, "warmup": warm, "higher_is_better": True, "dtype": "f32",
+            "data": s.get("name", _WORKLOAD["name"]), "config": config_dict(s, args, "1 GPU, Langevin 300 K, %g/ps, dt 1 fs, AGBNP only + %g kJ/mol/nm^2 tether" % (args.md_friction, args.md_tether)),
+            "temperature_K": temp, "clocks": clocks, "kernels_us": kernels_us,
+            "capacities": {"nodes_per_root": int(st1[4]), "nodes_per_level": int(st1[5]), "level2_neighbors": int(st1[6])},
+            "during_timed_region": {"capacity_growths": int(st1[0]-st0[0]), "re_sorts": int(st1[1]-st0[1]), "async_faults": int(st1[3]-st0[3]),
+                                    "evaluations_not_delivered": int(sim.dropped-dropped0)},
+            "verlet_lists": {"skin_nm": float(ls[3]), "evaluations_since_voided": int(ls[2]), "pair_mask_rebuilds": int(ls[0]), "level2_list_rebuilds": int(ls[1])},
+            "note": "one AGBNP evaluation + one integrator kernel per step, nothing on the host; device time by CUDA events over all steps"}
+    line["config"]["inputs"] = "a Langevin trajectory (consecutive steps), not independent jittered inputs"
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+    sim.close()
+
+
 def main():
     # stdout carries exactly ONE JSON line: libraries that print banners there (NCCL's version line) go to stderr instead
     global _JSON_OUT
@@ -627,6 +686,14 @@ def main():
     ap.add_argument("--workload", default="hivrt", help="hivrt (the metric's workload, default) | 2clr | 1dwc | rnaseh | 1li2 | trpcage")
     ap.add_argument("--cutoff", type=float, default=0.0, help="> 0: CutoffNonPeriodic with this cutoff (nm); the Reference platform, and "
                     "therefore the CPU baseline / parity check, has no cutoff: they are skipped")
+    ap.add_argument("--md", type=int, default=0, help="> 0: MD-driven throughput instead (this many Langevin steps at 1 fs through md.LangevinMD, "
+                    "the reference's example/*_benchmark.py protocol); prints ns/day for --workload / --cutoff")
+    ap.add_argument("--md-tether", type=float, default=100000.0, help="harmonic tether of every atom to its start position (kJ/mol/nm^2) in --md: stands in "
+                    "for the bonded and repulsive terms AGBNP does not have; 1e5 gives 0.005 nm rms per coordinate at 300 K, i.e. contact "
+                    "distances that fluctuate about as in a protein")
+    ap.add_argument("--md-friction", type=float, default=10.0, help="Langevin friction (1/ps) of --md.  The reference scripts use 1/ps with the "
+                    "full force field; with AGBNP alone and CutoffNonPeriodic (pair terms truncated without switching, by the reference's "
+                    "definition) 1/ps does not hold 300 K -- the truncation heats -- so the default is 10/ps; the line reports the temperature")
     ap.add_argument("--tree-reuse", type=int, default=0, help="> 1: OPT-IN tree reuse (not the reference's semantics): the overlap tree is "
                     "rebuilt every K-th evaluation and re-evaluated on its stored topology in between; reported in config")
     args = ap.parse_args()
@@ -639,6 +706,8 @@ def main():
         args.no_cpu_baseline = True
     if args.impl == "reference":
         reference_arm(args)
+    elif args.md > 0:
+        md_arm(args)
     else:
         b200_arm(args)
 

@@ -167,6 +167,9 @@ typedef enum {
     AGBNP_B200_GET_STATS = 13             /* double[8]  since creation: capacity growths, spatial re-sorts, CUDA-graph instantiations,
                                                          asynchronous evaluations found overflowed; now: nodes-per-root capacity,
                                                          nodes-per-level capacity, level-2 neighbor capacity, 1 if a growth is pending */
+    ,AGBNP_B200_GET_LIST_STATS = 14       /* double[4]  since the Verlet lists were last voided (re-sort, capacity growth): evaluations
+                                                         that rebuilt the pair masks, that rebuilt the level-2 candidate lists,
+                                                         evaluations in all; the list skin (nm) */
 } agbnp_b200_get_what;
 
 int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);

@@ -356,7 +356,7 @@ void alloc_tree_scratch(agbnp_b200* h) {
     const size_t per_warp = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
     const size_t smem_sm = 200*1024;                       // of 227 KB; leaves room for L1
     // CTAs of 2 warps (warps never cooperate); 128 registers/thread bound the residency at 16 warps per SM
-    h->tree_warps = 2;
+    h->tree_warps = TREE_WARPS;
     size_t ctas = std::min<size_t>(TREE_SMEM_CTAS, smem_sm/(h->tree_warps*per_warp + 1024));
     h->tree_work_global = ctas < 2;                        // fewer than 4 warps per SM: shared memory no longer pays
     if (h->tree_work_global) { h->tree_warps = 8; ctas = 2; }
@@ -469,7 +469,7 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
         for (int k = 0; k < nh; k++) { pred[k] = 0.85f*std::pow((float) count[k]+1.f, 1.85f); pred_total += pred[k]; }
         static const double items_per_warp = std::getenv("AGBNP_B200_TREE_GROUP_TARGET") ? std::atof(std::getenv("AGBNP_B200_TREE_GROUP_TARGET")) : 6.0;
         const float node_target = (float) std::min(300.0, std::max(40.0, pred_total/(items_per_warp*warps)));
-        const float width_target = 110.f, nbr_target = 50.f;
+        const float width_target = 80.f, nbr_target = 36.f;
         It open{0, 0, 0, 1, 0.f};
         float g_nodes = 0.f, g_nbr = 0.f;
         auto close = [&]() { if (open.nroots) { its.push_back(open); open.nroots = 0; } };
@@ -1507,6 +1507,13 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             need(sizeof(double)*8);
             od[0] = (double) h->n_grow; od[1] = (double) h->n_resort; od[2] = (double) h->n_graph_inst; od[3] = (double) h->n_async_fault;
             od[4] = h->tree_cap; od[5] = h->tree_wcap; od[6] = h->nbrmax; od[7] = h->ahead_pending ? 1.0 : 0.0;
+            break;
+        }
+        case AGBNP_B200_GET_LIST_STATS: {
+            need(sizeof(double)*4);
+            int c[LC_COUNT] = {};
+            if (h->d_pq_ctl.p) CK(cudaMemcpy(c, h->d_pq_ctl.p, sizeof(c), cudaMemcpyDeviceToHost));
+            od[0] = c[LC_N_PQ]; od[1] = c[LC_N_L2]; od[2] = c[LC_N_EVAL]; od[3] = h->pq_skin;
             break;
         }
         case AGBNP_B200_GET_TREE_SIZE: {

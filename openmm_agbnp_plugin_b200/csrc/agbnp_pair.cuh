@@ -843,6 +843,7 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
         if (k == 0) {
             if (pq || l2) { A.pq_ctl[0] = pq ? 1 : 0; A.pq_ctl[3] = l2 ? 1 : 0; }
             A.pq_ctl[1] = 0;
+            A.pq_ctl[5] += pq ? 1 : 0; A.pq_ctl[6] += l2 ? 1 : 0; A.pq_ctl[7] += 1;     // statistics: rebuilds / evaluations
         }
     }
     // sharded: every shard withholds the delivery when ANY shard overflowed (the shards' status words were summed into

@@ -86,7 +86,8 @@ struct BlockListArgs {
 };
 
 // control words shared by every Verlet-style list of an evaluation (pair masks: agbnp_pair.cuh; level-2 candidate lists: here)
-enum ListCtl { LC_PQ_VALID = 0, LC_DISP2 = 1, LC_PQ_REBUILT = 2, LC_L2_VALID = 3, LC_L2_REBUILT = 4, LC_COUNT = 8 };
+enum ListCtl { LC_PQ_VALID = 0, LC_DISP2 = 1, LC_PQ_REBUILT = 2, LC_L2_VALID = 3, LC_L2_REBUILT = 4,
+               LC_N_PQ = 5, LC_N_L2 = 6, LC_N_EVAL = 7 /* statistics since the lists were last voided */, LC_COUNT = 8 };
 
 __global__ void __launch_bounds__(256) k_blocklist(BlockListArgs A) {
     pdl_release();
@@ -361,11 +362,14 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
 // ---------------------------------------------------------------------------------------------------------------
 // SMEM_WORK: work arrays in shared memory, CTAs of 2 warps (the normal case; TREE_SMEM_CTAS per SM bounds the registers);
 // otherwise work arrays in global scratch, CTAs of 8 warps
+#ifndef TREE_WARPS
+#define TREE_WARPS 2                // warps per CTA of the shared-memory instantiation (warps never cooperate)
+#endif
 #ifndef TREE_SMEM_CTAS
-#define TREE_SMEM_CTAS 8
+#define TREE_SMEM_CTAS (16/TREE_WARPS)
 #endif
 template <bool SMEM_WORK>
-__global__ void __launch_bounds__(SMEM_WORK ? 64 : 256, SMEM_WORK ? TREE_SMEM_CTAS : 2) k_tree(TreeArgs A) {
+__global__ void __launch_bounds__(SMEM_WORK ? 32*TREE_WARPS : 256, SMEM_WORK ? TREE_SMEM_CTAS : 2) k_tree(TreeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_release();
     pdl_acquire();

@@ -452,6 +452,39 @@ def test_verlet_energy_conservation():
     sim.close()
 
 
+def test_langevin_md_protocol_of_the_reference_benchmarks():
+    """example/hivrt_benchmark.py:17-33: Langevin dynamics at 300 K, 1 fs steps, one AGBNP evaluation per step (here with
+    CutoffNonPeriodic 1.2 nm as BASELINE configs 2-3 and a tether standing in for the bonded terms).  The kinetic temperature
+    must settle at the thermostat's, every evaluation must be delivered (no overflow along the way), and the final state
+    must still agree with the oracle -- after hundreds of steps of list reuse and rebuilds."""
+    from openmm_agbnp_plugin_b200 import md
+    s = load_system("trpcage")
+    pos = systems.float_rounded(s["pos"])
+    masses = np.where(s["ishydrogen"] > 0, 1.008, 12.0)
+    sim = md.LangevinMD(systems.make_force(s, 1, 1, 1.2), pos, masses, temperature=300.0, friction_per_ps=20.0, dt_ps=0.001,
+                        restraint_k=20000.0, seed=7)
+    sim.step(600)
+    temps = []
+    for _ in range(40):
+        sim.step(10)
+        temps.append(sim.temperature())
+    t_mean = float(np.mean(temps))
+    assert 270.0 < t_mean < 330.0, t_mean              # 816 degrees of freedom: 5 % per sample, 40 samples
+    assert sim.dropped == 0 and sim.stats()[3] == 0     # no asynchronous evaluation was dropped
+    # the state after 1000 steps, re-evaluated synchronously, against the oracle
+    x = sim.posq[:, :3].cpu().numpy().astype(np.float64)
+    o = portlib.OracleKernel(1, *sys_args(s), nonbonded_method=portlib.CutoffNonPeriodic, cutoff=1.2)
+    e_ref, f_ref = o.execute(x)
+    ctx = plug.Context(systems.make_force(s, 1, 1, 1.2))
+    ctx.setPositions(x)
+    e = ctx.calcForcesAndEnergy()
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    sim.frc.zero_()
+    sim._force(sync=True)                               # the MD context itself (reused lists) on the same positions
+    assert relrms(sim.frc.cpu().numpy().astype(np.float64), f_ref) <= F_TOL
+    sim.close()
+
+
 @pytest.mark.parametrize("name,method,cutoff", [("trpcage", 0, 1.0), ("rnaseh", 1, 1.2)])
 def test_tree_reuse_tracks_the_rebuilt_tree(name, method, cutoff):
     """Opt-in tree reuse (agbnp_b200_config::tree_reuse_interval, SURVEY 8f-3): between builds the stored overlaps are only
