@@ -170,6 +170,9 @@ typedef enum {
     ,AGBNP_B200_GET_LIST_STATS = 14       /* double[4]  since the Verlet lists were last voided (re-sort, capacity growth): evaluations
                                                          that rebuilt the pair masks, that rebuilt the level-2 candidate lists,
                                                          evaluations in all; the list skin (nm) */
+    ,AGBNP_B200_GET_PEER_STATE = 15       /* double[7 + 7*8 + 1] diagnostics of the peer-memory exchange: exchanges completed per buffer
+                                                         kind (0..5 = agbnp_b200_buffer, 6 = positions), the flags the peers have raised in
+                                                         this shard's mailbox [kind][source shard], the sticky fault word */
 } agbnp_b200_get_what;
 
 int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes);

@@ -11,7 +11,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_PARAM_CHANGE = 0, -1, -2, -3, -4
 NOCUTOFF, CUTOFF_NONPERIODIC, CUTOFF_PERIODIC = 0, 1, 2
 
 GET = dict(SELF_VOLUME_VDW=0, SELF_VOLUME_LARGE=1, SURFACE_AREA=2, BORN_RADIUS=3, VOLUME_SCALING=4, SCALARS=5,
-           TREE_SIZE=6, TREE_TOPOLOGY=7, DERIV_Y=8, DERIV_WU=9, NEIGHBOR_PAIRS=10, NEIGHBOR_COUNT=11, WORK_COUNTERS=12, STATS=13, LIST_STATS=14)
+           TREE_SIZE=6, TREE_TOPOLOGY=7, DERIV_Y=8, DERIV_WU=9, NEIGHBOR_PAIRS=10, NEIGHBOR_COUNT=11, WORK_COUNTERS=12, STATS=13, LIST_STATS=14, PEER_STATE=15)
 BUF = dict(SELFVOL=0, YQ=1, FORCE=2, ENERGY=3, WU=4, BSUM=5)
 
 

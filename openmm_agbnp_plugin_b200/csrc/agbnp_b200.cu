@@ -43,11 +43,11 @@ struct PeerBox {
 // Wait until a peer's flag reaches `epoch`.  Bounded: a peer that never arrives (its process died, or the shards were driven
 // out of step) must not hang this GPU for ever -- after ~4 s of spinning the wait gives up, raises ST_PEER_TIMEOUT in the
 // status word (the evaluation then delivers nothing and the host reports it) and the kernel runs to completion.
-__device__ __forceinline__ void peer_wait(const volatile int* flag, int epoch, int* status) {
+__device__ __forceinline__ void peer_wait(const volatile int* flag, int epoch, int* status, int kind = 0) {
     if (*flag >= epoch) return;
     const long long t0 = clock64();
     while (*flag < epoch) {
-        if (clock64() - t0 > 8000000000ll) { atomicOr(status, ST_PEER_TIMEOUT); break; }
+        if (clock64() - t0 > 8000000000ll) { atomicOr(status, ST_PEER_TIMEOUT | (1 << (8+kind))); break; }   // bits 8+: which exchange (diagnostics)
         __nanosleep(64);
     }
 }
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(T* buf, size_t n, PeerBo
         }
         const volatile int* flags = (const volatile int*) (pb.mail[pb.rank] + pb.flag_off) + kind*PEER_MAX;
         for (int q = 0; q < pb.count; q++)
-            if (q != pb.rank) peer_wait(flags+q, epoch, pb.status);
+            if (q != pb.rank) peer_wait(flags+q, epoch, pb.status, kind);
         __threadfence_system();
     }
     __syncthreads();
@@ -88,6 +88,56 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(T* buf, size_t n, PeerBo
         for (int q = 0; q < pb.count; q++)
             if (q != pb.rank) acc = peer_add(acc, __ldcg((const T*) (base + (size_t) q*pb.kind_bytes[kind]) + i));
         buf[i] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(pb.counter+1, 1) == (int) gridDim.x-1) { pb.counter[1] = 0; pb.epochs[kind] = epoch; }
+}
+
+// The last exchange of an evaluation, three in one: the partial forces of the gamma sweep (float4[n]), the energy scalars
+// (SC_COUNT doubles) and this shard's status word, which travels as 0/1 in the SC_FAULT slot so that every shard's finish
+// kernel knows whether ANY shard overflowed.  Same protocol as k_peer_allreduce, one flag (the FORCE kind's).
+__global__ void __launch_bounds__(256) k_peer_allreduce_final(float4* buf, size_t n, double* scalars, const int* status, PeerBox pb) {
+    const int kind = AGBNP_B200_BUF_FORCE, ekind = AGBNP_B200_BUF_ENERGY;
+    const int epoch = pb.epochs[kind]+1;
+    for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) {
+        const float4 v = buf[i];
+        for (int p = 0; p < pb.count; p++)
+            if (p != pb.rank) ((float4*) (pb.mail[p] + pb.kind_off[kind] + (size_t) pb.rank*pb.kind_bytes[kind]))[i] = v;
+    }
+    double mine = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x < SC_COUNT) {
+        mine = threadIdx.x == SC_FAULT ? (*status != 0 ? 1.0 : 0.0) : scalars[threadIdx.x];
+        for (int p = 0; p < pb.count; p++)
+            if (p != pb.rank) ((double*) (pb.mail[p] + pb.kind_off[ekind] + (size_t) pb.rank*pb.kind_bytes[ekind]))[threadIdx.x] = mine;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(pb.counter, 1);
+        if (done == (int) gridDim.x-1) {
+            *pb.counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < pb.count; p++)
+                if (p != pb.rank) *(volatile int*) (pb.mail[p] + pb.flag_off + sizeof(int)*(kind*PEER_MAX + pb.rank)) = epoch;
+        }
+        const volatile int* flags = (const volatile int*) (pb.mail[pb.rank] + pb.flag_off) + kind*PEER_MAX;
+        for (int q = 0; q < pb.count; q++)
+            if (q != pb.rank) peer_wait(flags+q, epoch, pb.status, kind);
+        __threadfence_system();
+    }
+    __syncthreads();
+    const unsigned char* base = pb.mail[pb.rank] + pb.kind_off[kind];
+    for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) {
+        float4 acc = buf[i];
+        for (int q = 0; q < pb.count; q++)
+            if (q != pb.rank) acc = peer_add(acc, __ldcg((const float4*) (base + (size_t) q*pb.kind_bytes[kind]) + i));
+        buf[i] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < SC_COUNT) {
+        const unsigned char* ebase = pb.mail[pb.rank] + pb.kind_off[ekind];
+        for (int q = 0; q < pb.count; q++)
+            if (q != pb.rank) mine += __ldcg((const double*) (ebase + (size_t) q*pb.kind_bytes[ekind]) + threadIdx.x);
+        scalars[threadIdx.x] = mine;
     }
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(pb.counter+1, 1) == (int) gridDim.x-1) { pb.counter[1] = 0; pb.epochs[kind] = epoch; }
@@ -114,7 +164,7 @@ __global__ void __launch_bounds__(256) k_peer_broadcast(float4* buf, size_t n, P
     } else {
         if (threadIdx.x == 0) {
             const volatile int* flags = (const volatile int*) (pb.mail[pb.rank] + pb.flag_off) + kind*PEER_MAX;
-            peer_wait(flags+owner, epoch, pb.status);
+            peer_wait(flags+owner, epoch, pb.status, kind);
             __threadfence_system();
         }
         __syncthreads();
@@ -317,6 +367,26 @@ struct agbnp_b200 {
 };
 
 namespace {
+
+// CUDA loads a kernel's code lazily, at its first launch, and the load waits for the device to drain: a shard whose first
+// launch of some kernel comes while a PEER shard on the same device is already spinning in an exchange (waiting for this very
+// shard) would stall until the peer's wait times out.  Every kernel of the library is therefore loaded when a handle is
+// created, before anything can be waiting (cudaFuncGetAttributes forces the load).
+template <class K> void preload(K kernel) { cudaFuncAttributes a; CK(cudaFuncGetAttributes(&a, kernel)); }
+void preload_kernels() {
+    static bool done[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (done[dev & 63]) return;
+    done[dev & 63] = true;
+    preload(k_prep); preload(k_blocklist); preload(k_tree<true>); preload(k_tree<false>); preload(k_tree_rescan);
+    preload(k_born<false, true>); preload(k_born<true, true>); preload(k_born<false, false>); preload(k_born<true, false>);
+    preload(k_born_finish); preload(k_gb<false>); preload(k_gb<true>);
+    preload(k_deriv<false, true>); preload(k_deriv<true, true>); preload(k_deriv<false, false>); preload(k_deriv<true, false>);
+    preload(k_tree_gamma<true>); preload(k_tree_gamma<false>); preload(k_status_fold); preload(k_finish); preload(k_list_pairs);
+    preload(k_peer_allreduce<float4>); preload(k_peer_allreduce<float>); preload(k_peer_allreduce<double>);
+    preload(k_peer_allreduce_final); preload(k_peer_broadcast);
+}
 
 // wait for the work THIS handle has enqueued (never cudaDeviceSynchronize: see TrashScope)
 void wait_own_work(agbnp_b200* h) {
@@ -682,7 +752,8 @@ PairCommon pair_common(agbnp_b200* h) {
     return c;
 }
 
-enum Phase { PH_TREE = 1, PH_GB = 2, PH_DERIV = 4, PH_FINISH = 8, PH_GAMMA = 16, PH_BORN = 32, PH_BORNFIN = 64 };
+enum Phase { PH_TREE = 1, PH_GB = 2, PH_DERIV = 4, PH_FINISH = 8, PH_GAMMA = 16, PH_BORN = 32, PH_BORNFIN = 64,
+             PH_NOFOLD = 128 /* the caller's exchange carries the status word itself (k_peer_allreduce_final) */ };
 
 struct ForceSink { void* ptr; int layout; int padded_n; double* d_energy; };
 
@@ -868,12 +939,13 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         gm.gacc = h->d_gacc; gm.scratch_stride = gamma_work_bytes(h->tree_cap);
         gm.scratch = h->gamma_work_global ? h->d_gamma_scratch.p : nullptr;
         gm.cap = h->tree_cap; gm.work_counter = h->d_ctrl+CW_WORK_GAMMA;
+        gm.shard_rank = h->cfg.shard_rank; gm.shard_count = h->cfg.shard_count;
         begin(K_GAMMA);
         if (h->gamma_work_global) launch(h, k_tree_gamma<false>, h->gamma_grid, 32*h->gamma_warps, 0, s, gm);
         else launch(h, k_tree_gamma<true>, h->gamma_grid, 32*h->gamma_warps, h->gamma_warps*gm.scratch_stride, s, gm);
         end(K_GAMMA);
     }
-    if ((phase_mask & PH_GAMMA) && h->cfg.shard_count > 1) {
+    if ((phase_mask & PH_GAMMA) && !(phase_mask & PH_NOFOLD) && h->cfg.shard_count > 1) {
         // the status word joins the energy scalars, so that the ENERGY exchange tells every shard whether ANY shard overflowed
         StatusFoldArgs sf{h->d_ctrl+CW_STATUS, h->d_scalars};
         launch(h, k_status_fold, 1, 32, 0, s, sf);
@@ -930,8 +1002,21 @@ void enqueue_sharded(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, con
     enqueue(h, d_posq_in, s, PH_BORN, nullptr);            peer_enqueue(h, AGBNP_B200_BUF_BSUM, s);
     enqueue(h, d_posq_in, s, PH_BORNFIN|PH_GB, nullptr);   peer_enqueue(h, AGBNP_B200_BUF_YQ, s);
     enqueue(h, d_posq_in, s, PH_DERIV, nullptr);           peer_enqueue(h, AGBNP_B200_BUF_WU, s);
-    enqueue(h, d_posq_in, s, PH_GAMMA, nullptr);           peer_enqueue(h, AGBNP_B200_BUF_FORCE, s);
-    peer_enqueue(h, AGBNP_B200_BUF_ENERGY, s);
+    static const bool split_final = std::getenv("AGBNP_B200_PEER_SPLIT_FINAL") != nullptr;     // diagnostics: the three exchanges one by one
+    if (split_final) {
+        enqueue(h, d_posq_in, s, PH_GAMMA, nullptr);       peer_enqueue(h, AGBNP_B200_BUF_FORCE, s);
+        peer_enqueue(h, AGBNP_B200_BUF_ENERGY, s);
+        enqueue(h, d_posq_in, s, PH_FINISH, sink);
+        return;
+    }
+    enqueue(h, d_posq_in, s, PH_GAMMA|PH_NOFOLD, nullptr);
+    {   // forces of the gamma sweep + energy scalars + status word in one exchange
+        const size_t nvec = (size_t) h->np;
+        const int grid = (int) std::min<size_t>(64, (nvec+255)/256);
+        k_peer_allreduce_final<<<grid, 256, 0, s>>>(h->d_gacc, nvec, h->d_scalars, h->d_ctrl+CW_STATUS, h->peer);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    }
     enqueue(h, d_posq_in, s, PH_FINISH, sink);
 }
 
@@ -1220,6 +1305,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         h->num_sm = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        preload_kernels();
         { const char* ng = std::getenv("AGBNP_B200_NO_GRAPH"); h->use_graph = !(ng && ng[0] == '1'); }
         { const char* ng = std::getenv("AGBNP_B200_NO_PDL"); h->use_pdl = !(ng && ng[0] == '1'); }
         if (const char* sk = std::getenv("AGBNP_B200_PAIR_SKIN")) h->pq_skin = std::max(0.f, (float) std::atof(sk));
@@ -1507,6 +1593,16 @@ int agbnp_b200_get(agbnp_b200* h, int what, void* host_out, size_t bytes) {
             need(sizeof(double)*8);
             od[0] = (double) h->n_grow; od[1] = (double) h->n_resort; od[2] = (double) h->n_graph_inst; od[3] = (double) h->n_async_fault;
             od[4] = h->tree_cap; od[5] = h->tree_wcap; od[6] = h->nbrmax; od[7] = h->ahead_pending ? 1.0 : 0.0;
+            break;
+        }
+        case AGBNP_B200_GET_PEER_STATE: {
+            need(sizeof(double)*(PEER_KINDS + PEER_KINDS*PEER_MAX + 1));
+            std::vector<int> ep(PEER_KINDS+1, 0), fl(PEER_KINDS*PEER_MAX, 0);
+            if (h->d_peer_counter) CK(cudaMemcpy(ep.data(), h->d_peer_counter+2, sizeof(int)*(PEER_KINDS+1), cudaMemcpyDeviceToHost));
+            if (h->d_mailbox) CK(cudaMemcpy(fl.data(), h->d_mailbox + h->peer.flag_off, sizeof(int)*PEER_KINDS*PEER_MAX, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < PEER_KINDS; k++) od[k] = ep[k];
+            for (int k = 0; k < PEER_KINDS*PEER_MAX; k++) od[PEER_KINDS+k] = fl[k];
+            od[PEER_KINDS + PEER_KINDS*PEER_MAX] = ep[PEER_KINDS];
             break;
         }
         case AGBNP_B200_GET_LIST_STATS: {

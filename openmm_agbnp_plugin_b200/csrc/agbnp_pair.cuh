@@ -266,8 +266,11 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
     const bool rebuild = A.u.ctl[0] == 0 || __int_as_float(A.u.ctl[1]) > A.u.move2;
     if (rebuild && blockIdx.x == 0 && threadIdx.x == 0) A.u.ctl[2] = 1;
     unsigned npair = 0;
-    for (int u = first_unit(); u < A.u.nunits; u = next_unit(A.u.work_counter, lane)) {
-        if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
+    // units are dealt round-robin to the shards: claim c is this shard's c-th unit (a shard never touches, or pays a claim
+    // for, the units of another)
+    for (int c = first_unit(); ; c = next_unit(A.u.work_counter, lane)) {
+        const int u = c*A.u.shard_count + A.u.shard_rank;
+        if (u >= A.u.nunits) break;
         const int2 un = A.u.units[u];
         const int ra = un.x;
         const int cb0 = un.y & 0xfffff, nc = un.y >> 20;
@@ -538,8 +541,9 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
     GBStage* stage = s_stage[warp];
     double e_acc = 0.0;
     unsigned long long npair = 0, ntile = 0;
-    for (int u = claim_unit(A.work_counter, lane); u < A.nunits; u = claim_unit(A.work_counter, lane)) {
-        if (A.shard_count > 1 && (u % A.shard_count) != A.shard_rank) continue;
+    for (int c = claim_unit(A.work_counter, lane); ; c = claim_unit(A.work_counter, lane)) {
+        const int u = c*A.shard_count + A.shard_rank;             // this shard's c-th unit (round-robin deal)
+        if (u >= A.nunits) break;
         const int2 un = A.units[u];
         const int ra = un.x;
         const int cend = min(un.y+A.chunk, A.c.nb);
@@ -750,8 +754,9 @@ __global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
     DerivSmem& R = sm[2*warp];
     DerivSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
-    for (int u = first_unit(); u < A.u.nunits; u = next_unit(A.u.work_counter, lane)) {
-        if (A.u.shard_count > 1 && (u % A.u.shard_count) != A.u.shard_rank) continue;
+    for (int c = first_unit(); ; c = next_unit(A.u.work_counter, lane)) {
+        const int u = c*A.u.shard_count + A.u.shard_rank;         // this shard's c-th unit (round-robin deal, as in k_born)
+        if (u >= A.u.nunits) break;
         const int2 un = A.u.units[u];
         const int ra = un.x;
         const int cb0 = un.y & 0xfffff;

@@ -982,6 +982,7 @@ struct GammaArgs {
     size_t scratch_stride;
     int cap;
     int* work_counter;
+    int shard_rank, shard_count;    // items are dealt to shards as in k_tree (blocks of 32 in longest-first order)
 };
 
 __host__ __device__ inline size_t gamma_work_bytes(int cap) { return ((size_t) cap*(sizeof(float) + sizeof(float4) + sizeof(short)) + 15) & ~(size_t) 15; }
@@ -999,7 +1000,14 @@ __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
     float* gam = (float*) (hu + A.cap);             // [cap] gamma_1..n per slot
     short* par = (short*) (gam + A.cap);            // [cap] parent slot
     // r: item index (stored subtrees are per item; not-owned nodes carry zeros)
-    for (int r = claim_unit(A.work_counter, lane); r < A.nitems; r = claim_unit(A.work_counter, lane)) {
+    const int raw_end = A.shard_count > 1 ? (A.nitems+TILE-1)/TILE*TILE : A.nitems;
+    for (int raw = claim_unit(A.work_counter, lane); ; raw = claim_unit(A.work_counter, lane)) {
+        int r = raw;
+        if (A.shard_count > 1) {                    // this shard's raw-th item (the same deal as k_tree)
+            r = ((raw >> 5)*A.shard_count + A.shard_rank)*TILE + (raw & 31);
+            if (r >= raw_end) break;
+            if (r >= A.nitems) continue;
+        } else if (r >= A.nitems) break;
         const int cnt = A.st.root_cnt[r];
         if (cnt <= 1) continue;             // an atom without overlaps: dv1 = 0, no force (gaussvol.cpp:472)
         const float4* rec = A.st.rec + 2*(size_t) A.st.root_off[r];

@@ -152,7 +152,7 @@ class ShardedEvaluator:
         if self.world > 1 and not want_energy and broadcast_positions and getattr(self.k, "peer", False) and hasattr(self.k, "evaluate_graph"):
             # asynchronous evaluation over peer memory: broadcast, phases and exchanges enqueued by one library call
             self.k.evaluate_graph(posq, self.position_owner, stream, d_force, layout, padded_n, d_energy)
-            self.collectives += 1 + sum(len(x) for x in EXCHANGES)
+            self.collectives += 1 + len(EXCHANGES)       # broadcast + one exchange per phase (the last carries forces, energies and status)
             return None
         if self.world > 1 and broadcast_positions:
             if getattr(self.k, "peer", False):

@@ -81,7 +81,7 @@ def test_cpp_host_reproduces_the_golden_files(golden, version, precision):
     assert abs(vals["Energy Change"] - g["energy_change"]) <= 3e-3        # difference of two float-path energies of ~1e3
     assert abs(vals["Energy Change from Gradient"] - g["energy_change_from_gradient"]) <= 1e-4 * abs(g["energy_change_from_gradient"]) + 1e-7
     assert len(reorder["Reorder relative force change"]) == 2
-    assert max(reorder["Reorder relative force change"]) <= 1e-6          # float summation order is the only difference
+    assert max(reorder["Reorder relative force change"]) <= 5e-6          # max norm; float summation order is the only difference (measured 1e-6)
     assert max(reorder["Reorder relative energy change"]) <= 2e-6
     if version == 1:
         assert abs(vals["Energy after charge update"] - energies[1]) > 1.0
