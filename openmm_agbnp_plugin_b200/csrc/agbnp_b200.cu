@@ -978,6 +978,10 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
 }
 
 constexpr int PH_ALL = PH_TREE|PH_BORN|PH_BORNFIN|PH_GB|PH_DERIV|PH_GAMMA|PH_FINISH;
+// an evaluation whose caller wants no forces (includeForces == false, or no force sink) needs neither the Born-radius
+// derivative pass nor the gamma sweep: they produce forces only (the Reference platform computes them regardless)
+constexpr int PH_ENERGY_ONLY = PH_TREE|PH_BORN|PH_BORNFIN|PH_GB|PH_FINISH;
+inline int phases_for(const ForceSink* sink) { return (sink && !sink->ptr) ? PH_ENERGY_ONLY : PH_ALL; }
 
 // one whole evaluation on stream s: a cached CUDA graph of the kernel sequence (one launch instead of eight; the capture
 // happens on the handle's own stream because the caller's may be the legacy default stream, which cannot be captured)
@@ -1025,7 +1029,7 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
     // a sharded evaluation is bounded by the waits of its exchange kernels, not by launch latency: measured on 2 and 8 B200 a
     // graph of it is no faster than the plain launches (490 vs 466 us, 372 vs 367 us), so it is launched directly
     if (!h->use_graph || h->prof_mask || sharded) {
-        if (sharded) enqueue_sharded(h, d_posq_in, s, sink); else enqueue(h, d_posq_in, s, PH_ALL, sink);
+        if (sharded) enqueue_sharded(h, d_posq_in, s, sink); else enqueue(h, d_posq_in, s, phases_for(sink), sink);
         mark_tail(h, s);
         return;
     }
@@ -1048,7 +1052,7 @@ void launch_all(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, const Fo
         const long long before = h->launches;
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-        try { if (sharded) enqueue_sharded(h, d_posq_in, h->own_stream, sink); else enqueue(h, d_posq_in, h->own_stream, PH_ALL, sink); }
+        try { if (sharded) enqueue_sharded(h, d_posq_in, h->own_stream, sink); else enqueue(h, d_posq_in, h->own_stream, phases_for(sink), sink); }
         catch (...) { cudaStreamEndCapture(h->own_stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
         CK(cudaStreamEndCapture(h->own_stream, &graph));
         agbnp_b200::GraphEntry e{h->launch_gen, d_posq_in, sink->ptr, sink->layout, sink->padded_n, sink->d_energy, sharded, h->cur_eval_rescan, nullptr,
@@ -1392,7 +1396,8 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         prepare(h, (const float*) h->h_posq, 4, nullptr, s);
         const double t2 = timing ? now() : 0;
         double t3 = 0;
-        ForceSink sink{h->d_force_out.p, 2, h->n, nullptr};      // layout 2: float[3n], assigned
+        const bool want_forces = include_forces && forces;
+        ForceSink sink{want_forces ? h->d_force_out.p : nullptr, 2, h->n, nullptr};      // layout 2: float[3n], assigned; none: energy only
         for (int attempt = 0; ; attempt++) {
             launch_all(h, h->d_posq_in.p, s, &sink);
             if (include_forces && forces)

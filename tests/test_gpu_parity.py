@@ -223,6 +223,25 @@ def test_execute_accumulates_forces_like_the_reference():
     assert abs(e2 - e) <= 1e-6 * abs(e)       # float red.global accumulation order varies run to run
 
 
+def test_energy_only_evaluation_skips_the_force_kernels():
+    """execute(includeForces=False): the energy must be the full evaluation's, the caller's force array untouched, and the
+    two force-only kernels (Born-radius derivative pass, gamma sweep) must not have been launched."""
+    s = load_system("rnaseh")
+    pos = systems.float_rounded(s["pos"])
+    ctx, e, f = _gpu(s, pos, 1)
+    L = _lib.lib()
+    n0 = L.agbnp_b200_launch_count(ctx.kernel.handle)
+    ctx.calcForcesAndEnergy()
+    full = L.agbnp_b200_launch_count(ctx.kernel.handle) - n0
+    ctx.forces[:] = 7.0
+    e_only = ctx.kernel.execute(ctx, False, True)
+    assert L.agbnp_b200_launch_count(ctx.kernel.handle) - n0 - full == full - 2
+    assert abs(e_only - e) <= 1e-6 * abs(e)
+    assert np.all(ctx.forces == 7.0)
+    e_again = ctx.calcForcesAndEnergy()                     # and the full evaluation still works afterwards
+    assert abs(e_again - e) <= 1e-6 * abs(e) and relrms(ctx.getForces(), f) <= 1e-5
+
+
 def test_update_parameters_in_context():
     """copyParametersToContext (ReferenceAGBNPKernels.cpp:1796-1815): gamma/alpha/charge may change, the rest may not."""
     s = load_system("trpcage")
