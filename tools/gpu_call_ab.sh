@@ -1,5 +1,4 @@
 #!/bin/sh
-for caps in "512,192,64" "576,224,96" "640,256,96"; do
- echo "== caps $caps default"; AGBNP_B200_INIT_CAPS=$caps python tools/quick_time.py hivrt 2>&1 | grep -A1 "method=0" | grep k_tree | sed 's/k_born=.*//'
- echo "== caps $caps 1-warp CTAs"; AGBNP_B200_INIT_CAPS=$caps AGBNP_B200_LIB=variants/warp1/libagbnp_b200.so python tools/quick_time.py hivrt 2>&1 | grep -A1 "method=0" | grep k_tree | sed 's/k_born=.*//'
-done
+echo "== default 320"; python tools/quick_time.py hivrt 2clr 2>&1 | grep -A1 "method=0" | grep "k_tree_gamma" | sed 's/.*k_tree_gamma/k_tree_gamma/'
+for n in 192 256 448; do echo "== $n"; AGBNP_B200_LIB=variants/gam$n/libagbnp_b200.so python tools/quick_time.py hivrt 2clr 2>&1 | grep -A1 "method=0" | grep "k_tree_gamma" | sed 's/.*k_tree_gamma/k_tree_gamma/'; done
+python tools/quick_parity.py hivrt_standin 2clr
