@@ -245,7 +245,7 @@ struct agbnp_b200 {
     DevBuf<signed char> d_tj;
     DevBuf<float> d_rc2, d_rc2max, d_rc2s, d_rc2maxs;     // level-2 pair radii squared; the same with the list skin
     DevBuf<int> d_l2list, d_l2cnt;          // per-root level-2 candidate lists kept between evaluations (agbnp_tree.cuh)
-    DevBuf<float4> d_i4v, d_i4d;
+    DevBuf<float4> d_i4v;
     DevBuf<int2> d_units, d_pq_units;
     DevBuf<int> d_pq_toff;
     DevBuf<unsigned> d_pq_hits;
@@ -277,7 +277,9 @@ struct agbnp_b200 {
     // tree
     // tree capacities (grown on overflow): nodes per root, nodes per level, level-2 neighbors per root
     int tree_cap = 512, tree_wcap = 192, nbrmax = 64;
-    int tree_grid = 0, tree_warps = 4, gamma_grid = 0, gb_grid = 0, pq_grid = 0, gb_chunk = 8;
+    int tree_grid = 0, tree_warps = 4, gamma_grid = 0, gb_grid = 0, gb_chunk = 8;
+    int born_w = 8, born_c = 1, deriv_w = 8, deriv_c = 1, pq_shape_cutoff = -1;     // launch shapes of k_born / k_deriv (pq_shape)
+    size_t pq_shape_tab = (size_t) -1;
     bool tree_work_global = false;          // work arrays too large for shared memory: per-warp global scratch instead
     DevBuf<unsigned char> d_tree_stage, d_tree_work, d_gamma_scratch;
     TreeStore st{};
@@ -670,15 +672,14 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     {
         const I4Tables& t = sp.i4;
         const int ntab = t.ntypes_screened*t.ntypes_screener, ni = t.nodes-1;
-        std::vector<float4> tv((size_t) ntab*ni), td((size_t) ntab*ni);
+        std::vector<float4> tv((size_t) ntab*ni);
         for (int tb = 0; tb < ntab; tb++) for (int k = 0; k < ni; k++) {
             const double yl = t.y[(size_t) tb*t.nodes+k], yu = t.y[(size_t) tb*t.nodes+k+1];
             const double zl = t.y2[(size_t) tb*t.nodes+k]*t.h*t.h/6.0, zu = t.y2[(size_t) tb*t.nodes+k+1]*t.h*t.h/6.0;
             const double v0 = yl, v1 = (yu-yl) - 2.0*zl - zu, v2 = 3.0*zl, v3 = zu-zl;
             tv[(size_t) tb*ni+k] = make_float4((float) v0, (float) v1, (float) v2, (float) v3);
-            td[(size_t) tb*ni+k] = make_float4((float) (v1/t.h), (float) (2.0*v2/t.h), (float) (3.0*v3/t.h), 0.f);
         }
-        h->d_i4v.upload(tv, s); h->d_i4d.upload(td, s);
+        h->d_i4v.upload(tv, s);
     }
     // GB work units: triangular cover of the block-pair matrix in chunks of gb_chunk column tiles -- up to GB_CHUNK, fewer for
     // small systems so that every resident warp still gets about four units (2clr: 17.6 k tiles over 1776 warps)
@@ -733,11 +734,31 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     h->params_dirty = false;
 }
 
+// launch shape of the range-limited pair passes: the warps per CTA (w) and CTAs per SM (c) that put the most warps on an SM
+// (one copy of the spline table per CTA, warp_bytes of shared memory per warp; registers and everything else through the
+// occupancy calculator); ties go to the smaller CTAs.  The grid is num_sm*c CTAs, all resident (first_unit).
+template <typename Args>
+void pq_shape(void (*kern)(Args), size_t tab_bytes, size_t warp_bytes, const char* env, int& w_out, int& c_out) {
+    const char* e = std::getenv(env);
+    const int force_w = e ? std::atoi(e) : 0;
+    int best = 0;
+    w_out = 8; c_out = 1;
+    for (int w = 4; w <= PQ_MAX_THREADS/32; w++) {
+        if (force_w && w != force_w) continue;
+        const size_t sm = tab_bytes + w*warp_bytes;
+        if (sm > (size_t) 227*1024) continue;
+        int c = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, 32*w, sm) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (c < 1) continue;
+        if (c*w > best || (c*w == best && c > c_out)) { best = c*w; w_out = w; c_out = c; }
+    }
+}
+
 PairCommon pair_common(agbnp_b200* h) {
     PairCommon c;
     c.np = h->np; c.nhb = h->nhb; c.nb = h->nb;
     c.posq = h->d_posq.p; c.orig = h->d_orig.p; c.bbc = h->d_bbc.p; c.bbh = h->d_bbh.p;
-    c.ts = h->d_ts.p; c.tj = h->d_tj.p; c.i4v = h->d_i4v.p; c.i4d = h->d_i4d.p;
+    c.ts = h->d_ts.p; c.tj = h->d_tj.p; c.i4v = h->d_i4v.p;
     c.ntj = h->sp.i4.ntypes_screener;
     c.ntables = h->sp.i4.ntypes_screened*h->sp.i4.ntypes_screener;
     c.tab_smem = (size_t) c.ntables*I4_INTERVALS*sizeof(float4) <= 24*1024;     // both tables + atom staging stay under 64 KB
@@ -869,19 +890,32 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
     // pair-mask reuse: list range = pass range + skin
     const float pq_range = cutoff ? (float) std::min(h->k.i4_maxa, h->cfg.cutoff) : (float) h->k.i4_maxa;
     const float pq_list2 = (pq_range + h->pq_skin)*(pq_range + h->pq_skin);
+    if (v1 && (h->pq_shape_tab != tab_bytes || h->pq_shape_cutoff != (int) cutoff)) {         // launch shapes: once per table size / kernel variant
+        if (pc.tab_smem) {
+            if (cutoff) { pq_shape(k_born<true, true>, tab_bytes, BORN_WARP_SMEM, "AGBNP_B200_BORN_WARPS", h->born_w, h->born_c);
+                          pq_shape(k_deriv<true, true>, tab_bytes, DERIV_WARP_SMEM, "AGBNP_B200_DERIV_WARPS", h->deriv_w, h->deriv_c); }
+            else { pq_shape(k_born<false, true>, tab_bytes, BORN_WARP_SMEM, "AGBNP_B200_BORN_WARPS", h->born_w, h->born_c);
+                   pq_shape(k_deriv<false, true>, tab_bytes, DERIV_WARP_SMEM, "AGBNP_B200_DERIV_WARPS", h->deriv_w, h->deriv_c); }
+        } else {
+            if (cutoff) { pq_shape(k_born<true, false>, tab_bytes, BORN_WARP_SMEM, "AGBNP_B200_BORN_WARPS", h->born_w, h->born_c);
+                          pq_shape(k_deriv<true, false>, tab_bytes, DERIV_WARP_SMEM, "AGBNP_B200_DERIV_WARPS", h->deriv_w, h->deriv_c); }
+            else { pq_shape(k_born<false, false>, tab_bytes, BORN_WARP_SMEM, "AGBNP_B200_BORN_WARPS", h->born_w, h->born_c);
+                   pq_shape(k_deriv<false, false>, tab_bytes, DERIV_WARP_SMEM, "AGBNP_B200_DERIV_WARPS", h->deriv_w, h->deriv_c); }
+        }
+        h->pq_shape_tab = tab_bytes; h->pq_shape_cutoff = (int) cutoff;
+    }
     if (v1 && (phase_mask & PH_BORN)) {
         BornArgs ba{};
         ba.c = pc;
         ba.u = PairUnits{h->d_pq_units.p, h->npq_units, h->d_pq_toff.p, h->d_pq_hits.p, h->d_pq_masks.p,
                          h->d_ctrl+CW_WORK_BORN, h->cfg.shard_rank, h->cfg.shard_count, h->d_pq_ctl.p, pq_list2, pq_move2};
         ba.accS = h->d_accS; ba.vS = h->d_vS.p; ba.bsum = h->d_bsum; ba.counters = h->d_counters;
-        const size_t sm = tab_bytes + PQ_WARPS*2*sizeof(BornSmem);
-        int bocc = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bocc, k_born<false, true>, PQ_THREADS, sm));
-        const int bgrid = std::min(h->pq_grid, h->num_sm*std::max(1, bocc));      // resident CTAs only (first_unit)
+        const int bw = h->born_w, bc = h->born_c;
+        const size_t sm = tab_bytes + bw*BORN_WARP_SMEM;
+        const int bgrid = h->num_sm*bc;                                                 // resident CTAs only (first_unit)
         begin(K_BORN);
-        if (pc.tab_smem) { if (cutoff) launch(h, k_born<true, true>, bgrid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, true>, bgrid, PQ_THREADS, sm, s, ba); }
-        else { if (cutoff) launch(h, k_born<true, false>, bgrid, PQ_THREADS, sm, s, ba); else launch(h, k_born<false, false>, bgrid, PQ_THREADS, sm, s, ba); }
+        if (pc.tab_smem) { if (cutoff) launch(h, k_born<true, true>, bgrid, 32*bw, sm, s, ba); else launch(h, k_born<false, true>, bgrid, 32*bw, sm, s, ba); }
+        else { if (cutoff) launch(h, k_born<true, false>, bgrid, 32*bw, sm, s, ba); else launch(h, k_born<false, false>, bgrid, 32*bw, sm, s, ba); }
         end(K_BORN);
     }
     if (v1 && (phase_mask & PH_BORNFIN)) {
@@ -913,20 +947,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
                          h->d_ctrl+CW_WORK_DERIV, h->cfg.shard_rank, h->cfg.shard_count, h->d_pq_ctl.p, pq_list2, pq_move2};
         da.vsf = h->d_vsf.p; da.gbacc = h->d_gbacc; da.born = h->d_born.p; da.bfp = h->d_bfp.p; da.brw = h->d_brw.p;
         da.kdiel = (float) h->k.dielectric_factor; da.dacc = h->d_dacc;
-        // launch shape: the warps per CTA (and CTAs per SM) that put the most warps on an SM within 227 KB of shared memory
-        // and 32 warps of 64 registers; ties go to the smaller CTAs
-        int dw = PQ_WARPS, dc = 1;
-        {
-            static const int force_w = std::getenv("AGBNP_B200_DERIV_WARPS") ? std::atoi(std::getenv("AGBNP_B200_DERIV_WARPS")) : 0;
-            int best = 0;
-            for (int w = 4; w <= DERIV_MAX_THREADS/32; w++) {
-                if (force_w && w != force_w) continue;
-                const size_t per_cta = 2*tab_bytes + w*DERIV_WARP_SMEM + 1024;
-                const int c = (int) std::min<size_t>((size_t) 227*1024/per_cta, (size_t) (32/w));
-                if (c*w > best || (c*w == best && c > dc)) { best = c*w; dw = w; dc = c; }
-            }
-        }
-        const size_t sm = 2*tab_bytes + dw*DERIV_WARP_SMEM;
+        const int dw = h->deriv_w, dc = h->deriv_c;          // set with k_born's shape above
+        const size_t sm = tab_bytes + dw*DERIV_WARP_SMEM;
         const int dgrid = h->num_sm*dc;
         begin(K_DERIV);
         if (pc.tab_smem) { if (cutoff) launch(h, k_deriv<true, true>, dgrid, 32*dw, sm, s, da); else launch(h, k_deriv<false, true>, dgrid, 32*dw, sm, s, da); }
@@ -1325,12 +1347,7 @@ int agbnp_b200_create(const agbnp_b200_config* cfg, int n, const double* radius,
 #define GB_CTAS 4
 #endif
         h->gb_grid = h->num_sm*GB_CTAS;
-#ifndef PQ_CTAS
-#define PQ_CTAS 5
-#endif
-        h->pq_grid = h->num_sm*PQ_CTAS;
-        const int pair_smem = 2*24*1024 + (int) (PQ_WARPS*DERIV_WARP_SMEM);
-        const int deriv_smem = (int) prop.sharedMemPerBlockOptin;
+        const int pair_smem = (int) prop.sharedMemPerBlockOptin, deriv_smem = pair_smem;
         CK(cudaFuncSetAttribute(k_born<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
         CK(cudaFuncSetAttribute(k_born<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));

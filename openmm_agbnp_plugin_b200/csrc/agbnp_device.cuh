@@ -45,6 +45,9 @@ __device__ __forceinline__ void pdl_acquire() { asm volatile("griddepcontrol.wai
 //     26 -> 21 us, k_deriv 30 -> 24 us; Trp-cage k_tree 57 -> 50 us) and is neutral for them on 18 k atoms; k_gb and the gamma
 //     sweep lose 5-10 % with it (their warps then run in lockstep through equal-sized units, and the math-bound and the
 //     latency-bound phases of the warps of a scheduler no longer overlap), so those two keep (a).
+// Tried (r2r): claims issued one unit ahead of the work (the atomic's round trip shows as 10-20 % of the stall samples of
+// k_born / k_deriv / k_gb) -- every kernel got SLOWER (k_gb 154 -> 159 us, 2clr k_born 23 -> 30 us): other warps already cover
+// the wait, and a warp that holds its next unit early unbalances the tail.
 // The counter starts at 0 for every evaluation; grids using (b) must be fully resident.
 __device__ __forceinline__ int claim_unit(int* counter, int lane) {
     int u = 0;

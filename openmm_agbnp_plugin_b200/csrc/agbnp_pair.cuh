@@ -88,13 +88,11 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs A) {
     }
 }
 
-// I4 splines in power form, one float4 pair per (table, interval): with fr = fraction of the interval in [0,1),
-//   Q(d)  = v.x + fr (v.y + fr (v.z + fr v.w))          (value table `tabv`)
-//   Q'(d) = w.x + fr (w.y + fr w.z)                      (derivative table `tabd`, 1/h folded in)
-// -- the natural cubic spline of AGBNPI4LookupTable (AGBNPUtils.cpp:102-130, AGBNPUtils.h:104-115) expanded around the
-// left knot on the host in double (agbnp_b200.cu: upload_static).
+// I4 splines in power form, one float4 per (table, interval): with fr = fraction of the interval in [0,1),
+//   Q(d)  = v.x + fr (v.y + fr (v.z + fr v.w)),   Q'(d) = (v.y + 2 fr v.z + 3 fr^2 v.w)/h   (spline_slope, k_deriv)
+// -- the natural cubic spline of AGBNPI4LookupTable and its derivative (AGBNPUtils.cpp:102-130, AGBNPUtils.h:104-115)
+// expanded around the left knot on the host in double (agbnp_b200.cu: upload_static).
 __device__ __forceinline__ float spline_value(float4 v, float fr) { return fmaf(fr, fmaf(fr, fmaf(fr, v.w, v.z), v.y), v.x); }
-__device__ __forceinline__ float spline_deriv(float4 w, float fr) { return fmaf(fr, fmaf(fr, w.z, w.y), w.x); }
 
 // Interval of the uniform-knot spline tables without the two conversion instructions (F2I, I2F: quarter-rate XU pipe, which
 // the pair passes share with MUFU.RSQ): adding 1.5 * 2^23 rounds t - 1/2 to the nearest integer k = floor(t) into the low
@@ -114,8 +112,7 @@ struct PairCommon {
     const float4 *bbc, *bbh;
     const unsigned char* ts;    // screened radius type
     const signed char* tj;      // screener radius type, -1 hydrogens / padding
-    const float4* i4v;          // value tables  [ntables*15]
-    const float4* i4d;          // derivative tables
+    const float4* i4v;          // value tables  [ntables*15] (the derivative comes from the same cubic)
     int ntj, ntables;
     int tab_smem;               // 1: tables are staged in shared memory; 0 (too many radius classes): read through L1
     float inv_h;
@@ -132,19 +129,30 @@ struct PairCommon {
 // range it
 //   1. tests the 32x32 atom pairs ONCE: lane a scans the 32 column atoms (staged in shared memory) and keeps a 32-bit
 //      row mask; the ballot of each test, kept by lane b, is column atom b's mask of row atoms (the transposed matrix);
-//   2. row role: lane a walks the set bits of its row mask and accumulates everything atom a RECEIVES from those
-//      partners in registers;
-//   3. column role: lane b walks its column mask and accumulates what column atom b receives.
-// Steps 2/3 run the same code with the roles of "me" and "other" swapped, only on pairs that are in range (in-range
-// pairs are ~18% of the tested ones for the 2.0 nm range and 32-atom blocks, so walking masks instead of predicating
-// the 32x32 loop cuts the spline work by the lane-utilisation factor), and every sum lives in a register: no atomics
-// inside a tile.  Row sums leave once per unit, column sums once per tile, as one red.global per atom.
-// Units: heavy rows x heavy columns cb >= ra (both roles; the diagonal tile is handled by the row role alone) and
-// hydrogen rows x heavy columns (hydrogens never descreen, ReferenceAGBNPKernels.cpp:442,563).
+//   2. primary role: lane a walks the set bits of its row mask.  The distance, the spline interval and BOTH table rows
+//      of a pair -- (screened a, screener b) and (screened b, screener a) -- are evaluated once, here: what atom a
+//      receives stays in registers, what column atom b receives from a goes into a per-warp 32x33 shared-memory matrix;
+//   3. secondary role: lane b walks its column mask and only adds up its column of the matrix.
+// Only pairs that are in range are visited (~18% of the tested ones for the 2.0 nm range and 32-atom blocks), and every
+// sum lives in a register or in a matrix slot written by exactly one lane: no atomics inside a tile.  Row sums leave
+// once per unit, column sums once per tile, as one red.global per atom.
+// Both passes are bound by the shared-memory pipe (random-address table and partner loads: ncu r2p has k_deriv at 82 %
+// of the l1tex wavefront peak), so the design minimises table lookups per pair: one 16-byte row gives the spline value
+// AND its derivative (the derivative of the same cubic, AGBNPUtils.h:104-115), two rows serve both directions of a pair.
+// Units: heavy rows x heavy columns cb >= ra (the diagonal tile is handled by the primary role alone: every lane visits
+// all its partners) and hydrogen rows x heavy columns (hydrogens never descreen, ReferenceAGBNPKernels.cpp:442,563: one
+// table row per pair).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PQ_CHUNK = 8;             // most column blocks one unit may cover (far-apart block pairs are packed)
-constexpr int PQ_THREADS = 256;
-constexpr int PQ_WARPS = PQ_THREADS/32;
+constexpr int PQ_MAX_THREADS = 1024;
+constexpr int WMAT_STRIDE = 33;         // row stride of the per-warp pair matrices: lanes writing the same column hit different banks
+
+// staged atom: table row offsets of both roles in one word -- bits 12..: ts*ntj*15 (row base as the SCREENED atom), bits 0..10:
+// tj*15 (row offset as the SCREENER, 0 for hydrogens / padding), bit 11: not a screener
+constexpr int PK_TJ = 0x7ff, PK_HYD = 0x800, PK_TS_SHIFT = 12;
+__device__ __forceinline__ int pk_pack(int ts, int tj, int ntj) {
+    return (ts*ntj*I4_INTERVALS << PK_TS_SHIFT) | (tj < 0 ? PK_HYD : tj*I4_INTERVALS);
+}
 
 struct PairUnits {
     const int2* units;          // (row block, first column block | number of column blocks << 20), heaviest first
@@ -199,29 +207,39 @@ struct BornArgs {
     unsigned long long* counters;
 };
 
-struct BornSmem { float4 p[TILE]; int tj[TILE]; };     // p = (x, y, z, s_j/(4 pi)); .w = 0 for non-screeners; tj = screener type * 15, or < 0
+struct BornSmem { float4 p[TILE]; int pk[TILE]; };      // p = (x, y, z, s_j/(4 pi)); .w = 0 for non-screeners; pk: see pk_pack
+struct BornMe { float px, py, pz, s; int ts, tj; bool heavy; };        // ts = row base as the screened atom, tj = row offset as the screener
+constexpr size_t BORN_WARP_SMEM = 2*sizeof(BornSmem) + WMAT_STRIDE*TILE*sizeof(float);
 
-// contribution of partner jj (valid = the pair exists; invalid slots run the same instructions on a harmless atom)
-template <bool CUTOFF>
-__device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o, int jj, bool valid, float px, float py, float pz,
-                                           int tbase, float inv_h, float lim2, unsigned& npair) {
-    const int tj = o.tj[jj];
+// partner jj of atom "me" (valid = the pair exists; invalid slots run the same instructions on a harmless atom): returns what
+// me receives; BOTH: what the partner receives from me goes into vm[lane][jj] (off-diagonal tiles of heavy row blocks)
+template <bool CUTOFF, bool BOTH>
+__device__ __forceinline__ float born_term(const float4* tabv, const BornSmem& o, float* vm, int lane, int jj, bool valid, const BornMe& me,
+                                           float inv_h, float lim2, unsigned& npair) {
+    const int pk = o.pk[jj];
     const float4 c = o.p[jj];
-    const float dx = c.x-px, dy = c.y-py, dz = c.z-pz;
+    const float dx = c.x-me.px, dy = c.y-me.py, dz = c.z-me.pz;
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
     const float d = d2*rsqrt_fast(fmaxf(d2, 1e-20f));
     float fr;
     const int k = spline_interval(d*inv_h, fr);
-    const bool use = valid && tj >= 0 && d2 < lim2;          // the masks carry a skin: the range itself is tested here
-    const float q = spline_value(tabv[tbase + max(tj, 0) + k], fr);
+    const bool in = valid && d2 < lim2;                      // the masks carry a skin: the range itself is tested here
+    const bool use = in && !(pk & PK_HYD);
+    const float q = spline_value(tabv[me.ts + (pk & PK_TJ) + k], fr);
     npair += use;
+    if (BOTH) {
+        const bool rev = in && me.heavy;
+        const float qr = spline_value(tabv[(pk >> PK_TS_SHIFT) + me.tj + k], fr);
+        npair += rev;
+        if (valid) vm[lane*WMAT_STRIDE + jj] = rev ? me.s*qr : 0.f;
+    }
     return use ? c.w*q : 0.f;
 }
 
-// everything atom "me" receives from the partners in `mask`; two partners per trip for instruction-level parallelism
-template <bool CUTOFF>
-__device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o, unsigned mask, float px, float py, float pz,
-                                           int tbase, float inv_h, float lim2, unsigned& npair) {
+// primary role: everything atom "me" receives from the partners in `mask`; two partners per trip for instruction-level parallelism
+template <bool CUTOFF, bool BOTH>
+__device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o, float* vm, int lane, unsigned mask, const BornMe& me,
+                                           float inv_h, float lim2, unsigned& npair) {
     float s0 = 0.f, s1 = 0.f;
     while (mask) {
         const int j0 = __ffs(mask)-1;
@@ -229,8 +247,24 @@ __device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o
         const bool two = mask != 0;
         const int j1 = two ? __ffs(mask)-1 : j0;
         mask &= mask-1;
-        s0 += born_term<CUTOFF>(tabv, o, j0, true, px, py, pz, tbase, inv_h, lim2, npair);
-        s1 += born_term<CUTOFF>(tabv, o, j1, two, px, py, pz, tbase, inv_h, lim2, npair);
+        s0 += born_term<CUTOFF, BOTH>(tabv, o, vm, lane, j0, true, me, inv_h, lim2, npair);
+        s1 += born_term<CUTOFF, BOTH>(tabv, o, vm, lane, j1, two, me, inv_h, lim2, npair);
+    }
+    return s0+s1;
+}
+
+// secondary role: column `lane` of the matrix over the rows in `mask`
+__device__ __forceinline__ float born_column(const float* vm, int lane, unsigned mask) {
+    float s0 = 0.f, s1 = 0.f;
+    while (mask) {
+        const int a0 = __ffs(mask)-1;
+        mask &= mask-1;
+        const bool two = mask != 0;
+        const int a1 = two ? __ffs(mask)-1 : a0;
+        mask &= mask-1;
+        s0 += vm[a0*WMAT_STRIDE + lane];
+        const float v1 = vm[a1*WMAT_STRIDE + lane];
+        s1 += two ? v1 : 0.f;
     }
     return s0+s1;
 }
@@ -240,19 +274,21 @@ __device__ __forceinline__ void born_load(const BornArgs& A, int blk, int lane, 
     const float4 p = A.c.posq[j];
     const double vj = A.vS[j];
     s.p[lane] = make_float4(p.x, p.y, p.z, vj > 0 ? PIFAC*(A.accS[j].w/(float) vj) : 0.f);
-    const int tj = A.c.tj[j];
-    s.tj[lane] = tj < 0 ? -1 : tj*I4_INTERVALS;
+    s.pk[lane] = pk_pack((int) A.c.ts[j], (int) A.c.tj[j], A.c.ntj);
 }
 
 // TAB_SMEM: the spline tables are staged in shared memory (the normal case; a compile-time fact so that the lookups are
-// LDS instead of generic loads); otherwise (too many radius classes) they are read from global memory through L1
+// LDS instead of generic loads); otherwise (too many radius classes) they are read from global memory through L1.
+// Launch shape (warps per CTA, CTAs per SM): pq_shape() on the host; the grid is fully resident (first_unit).
 template <bool CUTOFF, bool TAB_SMEM>
-__global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
+__global__ void __launch_bounds__(PQ_MAX_THREADS) k_born(BornArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ntab = TAB_SMEM ? A.c.ntables*I4_INTERVALS : 0;
     float4* s_tabv = (float4*) smem_raw;                                // [ntables*15]
-    BornSmem* sm = (BornSmem*) (s_tabv + ntab);                         // [PQ_WARPS][2]: row block, column block
+    const int nwarp = blockDim.x >> 5;
+    BornSmem* sm = (BornSmem*) (s_tabv + ntab);                         // [nwarp][2]: row block, column block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* vm = (float*) (sm + 2*nwarp) + warp*WMAT_STRIDE*TILE;        // [nwarp][32*33]: what column atoms receive
     pdl_release();
     for (int i = threadIdx.x; i < ntab; i += blockDim.x) s_tabv[i] = A.c.i4v[i];      // per-context constants: before the wait
     pdl_acquire();
@@ -285,32 +321,33 @@ __global__ void __launch_bounds__(PQ_THREADS) k_born(BornArgs A) {
         const int toff = A.u.tile_off[u];
         __syncwarp();
         born_load(A, ra, lane, R);
+        __syncwarp();
         const bool row_heavy = ra < A.c.nhb;                 // hydrogen rows receive but never descreen
-        const float4 pa = A.c.posq[ra*TILE+lane];
-        const int tbase_a = (int) A.c.ts[ra*TILE+lane]*A.c.ntj*I4_INTERVALS;
+        BornMe me;
+        { const float4 pa = R.p[lane]; const int pk = R.pk[lane];
+          me.px = pa.x; me.py = pa.y; me.pz = pa.z; me.s = pa.w; me.ts = pk >> PK_TS_SHIFT; me.tj = pk & PK_TJ; me.heavy = !(pk & PK_HYD); }
         float rsum = 0.f;
         while (hits) {
             const int cb = cb0 + __ffs(hits)-1;
             hits &= hits-1;
             const bool diag = cb == ra;
-            __syncwarp();
+            __syncwarp();                                    // the previous tile's column sums have been read
             born_load(A, cb, lane, Cc);
             __syncwarp();
             unsigned rowmask, colmask;
             if (rebuild) {
-                pq_masks<CUTOFF>(Cc.p, pa.x, pa.y, pa.z, A.u.list2, diag, lane, rowmask, colmask);
+                pq_masks<CUTOFF>(Cc.p, me.px, me.py, me.pz, A.u.list2, diag, lane, rowmask, colmask);
                 A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane] = make_uint2(rowmask, colmask);
             } else {
                 const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
                 rowmask = mk.x; colmask = mk.y;
             }
-            rsum += born_role<CUTOFF>(tabv, Cc, rowmask, pa.x, pa.y, pa.z, tbase_a, A.c.inv_h, lim2, npair);
-            if (!diag && row_heavy) {
-                const int b = cb*TILE+lane;
-                const int tbase_b = (int) A.c.ts[b]*A.c.ntj*I4_INTERVALS;
-                const float4 pc = Cc.p[lane];
-                const float csum = born_role<CUTOFF>(tabv, R, colmask, pc.x, pc.y, pc.z, tbase_b, A.c.inv_h, lim2, npair);
-                if (csum != 0.f) atomicAdd(&A.bsum[b], csum);
+            if (diag || !row_heavy) rsum += born_role<CUTOFF, false>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
+            else {
+                rsum += born_role<CUTOFF, true>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
+                __syncwarp();                                // the matrix is read by other lanes
+                const float csum = born_column(vm, lane, colmask);
+                if (csum != 0.f) atomicAdd(&A.bsum[cb*TILE+lane], csum);
             }
         }
         if (rsum != 0.f) atomicAdd(&A.bsum[ra*TILE+lane], rsum);
@@ -561,9 +598,10 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
             fartiles = __ballot_sync(FULL, far);
         }
         if (!tiles) continue;
+        const int col0 = un.y;
         __syncwarp();                                             // the previous unit is done with the stages
         int cur = 0;
-        gb_prefetch(A, un.y + __ffs(tiles)-1, lane, stage[0]);
+        gb_prefetch(A, col0 + __ffs(tiles)-1, lane, stage[0]);
         // row atoms: 4 packed pairs (even atom in .x, odd atom in .y); positions negated, ib negated
         float2 nx[4], ny[4], nz[4], qi[4], bi[4], nib[4], fi[4][4];
 #pragma unroll
@@ -579,9 +617,9 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
         unsigned np32 = 0;
         while (tiles) {
             const int tb = __ffs(tiles)-1;
-            const int cb = un.y + tb;
+            const int cb = col0 + tb;
             tiles &= tiles-1;
-            if (tiles) { gb_prefetch(A, un.y + __ffs(tiles)-1, lane, stage[cur^1]); cp_async_wait<1>(); }
+            if (tiles) { gb_prefetch(A, col0 + __ffs(tiles)-1, lane, stage[cur^1]); cp_async_wait<1>(); }
             else cp_async_wait<0>();
             __syncwarp();
             ntile++;
@@ -649,9 +687,12 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
 // ---------------------------------------------------------------------------------------------------------------
 // k_deriv: Born-radius derivative pass (ReferenceAGBNPKernels.cpp:555-586), regrouped by the atom that RECEIVES each
 // contribution.  For atom "me" and partner "o" (d < 2.0, o != me), with D = r_o - r_me:
-//   F_me  += D/d [ heavy(o) bw_me s_o Q'(d; ts_me, tj_o)  +  heavy(me) bw_o s_me Q'(d; ts_o, tj_me) ]
+//   F_me  += D/d [ heavy(o) bw_me s_o Q'(d; ts_me, tj_o)  +  heavy(me) bw_o s_me Q'(d; ts_o, tj_me) ]  =  D w(me,o)
 //   WU_me += heavy(me) bw_o Q(d; ts_o, tj_me)                   (W and U merged: both are linear in brw / bru)
-// Same unit / mask / role structure as k_born.
+// Same unit / mask / role structure as k_born.  The force weight w is symmetric in (me, o) and the two table rows a pair
+// needs -- (ts_me, tj_o) and (ts_o, tj_me) -- give Q and Q' of both directions, so the primary role (row atom) evaluates
+// the pair completely and leaves (w, what the column atom's WU receives) in a 32x33 float2 matrix; the secondary role
+// (column atom) adds up its column: F_o -= D w, WU_o += heavy(o) bw_me Q(d; ts_me, tj_o).
 // ---------------------------------------------------------------------------------------------------------------
 struct DerivArgs {
     PairCommon c;
@@ -665,63 +706,80 @@ struct DerivArgs {
     float4* dacc;               // out [np]: fx, fy, fz, W+U (zeroed slab; float red.global)
 };
 
-struct DerivSmem { float4 p[TILE]; float bw[TILE]; int2 pk[TILE]; };   // p = (x, y, z, s); pk = (ts * ntj * 15, tj * 15 or < 0): table row offsets
+struct DerivSmem { float4 p[TILE]; float bw[TILE]; int pk[TILE]; };     // p = (x, y, z, s); pk: see pk_pack
 
-struct DerivMe { float px, py, pz, s, bw; int base, tj; };   // base = ts * ntj * 15, tj = tj * 15 or < 0
+struct DerivMe { float px, py, pz, s, bw; int ts, tj; bool heavy; };    // ts = row base as the screened atom, tj = row offset as the screener
 
-// The force weight of a pair, w = [bw_me s_o Q'(me,o) + bw_o s_me Q'(o,me)]/d, is symmetric in (me, o).  On an
-// off-diagonal tile the row role (MODE 1) therefore stores it in a 32x33 shared-memory matrix and the column role
-// (MODE 2) only looks it up: one spline value instead of two derivatives and a value.  MODE 0: plain (diagonal tile).
-constexpr int WMAT_STRIDE = 33;         // row stride: lanes writing the same column hit different banks
-// k_deriv holds 64 registers per thread, i.e. 32 warps fit one SM, but every warp needs 5.8 KB of shared memory next to the
-// CTA's two spline tables: the host picks the warps per CTA that bring the most warps onto an SM (deriv_shape)
-constexpr int DERIV_MAX_THREADS = 1024;
-constexpr size_t DERIV_WARP_SMEM = 2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float);
+constexpr size_t DERIV_WARP_SMEM = 2*sizeof(DerivSmem) + WMAT_STRIDE*TILE*sizeof(float2);
 
+// dQ/dfr of the power-form cubic (x + fr (y + fr (z + fr w)))' = y + 2 fr (z + 1.5 fr w); fr2 = 2 fr, fr15 = 1.5 fr
+__device__ __forceinline__ float spline_slope(float4 v, float fr2, float fr15) { return fmaf(fr2, fmaf(fr15, v.w, v.z), v.y); }
+
+// MODE 0: diagonal tile (both directions of a pair are visited by their own lanes: nothing is stored);
+// MODE 1: off-diagonal tile of a heavy row block (both table rows, the column atom's share is stored);
+// MODE 2: hydrogen row block: the row atoms never descreen, one table row, the column atom's share is stored.
 template <bool CUTOFF, int MODE>
-__device__ __forceinline__ void deriv_term(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, int jj,
-                                           bool valid, const DerivMe& me, int ntj, float inv_h, float lim2, float& fx, float& fy, float& fz, float& wu) {
+__device__ __forceinline__ void deriv_term(const float4* tabv, const DerivSmem& o, float2* wm, int lane, int jj, bool valid,
+                                           const DerivMe& me, float inv_h, float lim2, float& fx, float& fy, float& fz, float& wu) {
     const float4 c = o.p[jj];
     const float dx = c.x-me.px, dy = c.y-me.py, dz = c.z-me.pz;
     const float d2 = pq_dist2(CUTOFF, dx, dy, dz);
-    valid = valid && d2 < lim2;                             // the masks carry a skin: the range itself is tested here (both roles
-                                                            // of a pair compute the same d2: squares of negated differences)
-    const int2 pk = o.pk[jj];
+    const bool in = valid && d2 < lim2;                      // the masks carry a skin: the range itself is tested here
+    const int pk = o.pk[jj];
     const float inv_d = rsqrt_fast(fmaxf(d2, 1e-20f));
     const float d = d2*inv_d;
     float fr;
     const int k = spline_interval(d*inv_h, fr);
-    const int ix = pk.x + max(me.tj, 0) + k;
-    const float v2 = spline_value(tabv[ix], fr);
-    const float bwo = (valid && me.tj >= 0) ? o.bw[jj] : 0.f;   // me descreens o (needs heavy(me))
-    float w;
-    if (MODE == 2) w = valid ? wmat[jj*WMAT_STRIDE + lane] : 0.f;
-    else {
-        const int tj_o = pk.y;
-        const float q1 = spline_deriv(tabd[me.base + max(tj_o, 0) + k], fr);
-        const float q2 = spline_deriv(tabd[ix], fr);
-        w = (valid && tj_o >= 0) ? me.bw*c.w*q1 : 0.f;          // o descreens me (needs heavy(o))
-        w = fmaf(bwo*me.s, q2, w)*inv_d;
-        if (MODE == 1 && valid) wmat[lane*WMAT_STRIDE + jj] = w;
+    const float fr2 = fr+fr, fr15 = 1.5f*fr;
+    // row (ts_me, tj_o): o descreens me (needs heavy(o))
+    const float4 tb = tabv[me.ts + (pk & PK_TJ) + k];
+    const bool okb = in && !(pk & PK_HYD);
+    float w = okb ? me.bw*c.w*spline_slope(tb, fr2, fr15) : 0.f;
+    float vcol = 0.f;
+    if (MODE != 0) vcol = okb ? me.bw*spline_value(tb, fr) : 0.f;
+    if (MODE != 2) {
+        // row (ts_o, tj_me): me descreens o (needs heavy(me))
+        const float4 ta = tabv[(pk >> PK_TS_SHIFT) + me.tj + k];
+        const float bwo = (in && me.heavy) ? o.bw[jj] : 0.f;
+        w = fmaf(bwo*me.s, spline_slope(ta, fr2, fr15), w);
+        wu = fmaf(bwo, spline_value(ta, fr), wu);
     }
-    wu = fmaf(bwo, v2, wu);
+    w *= inv_d*inv_h;
+    if (MODE != 0 && valid) wm[lane*WMAT_STRIDE + jj] = make_float2(w, vcol);
     fx = fmaf(dx, w, fx); fy = fmaf(dy, w, fy); fz = fmaf(dz, w, fz);
 }
 
 template <bool CUTOFF, int MODE>
-__device__ __forceinline__ float4 deriv_role(const float4* tabv, const float4* tabd, const DerivSmem& o, float* wmat, int lane, unsigned mask,
-                                             float px, float py, float pz, float s_me, float bw_me, int ts_me, int tj_me,
-                                             int ntj, float inv_h, float lim2) {
+__device__ __forceinline__ float4 deriv_role(const float4* tabv, const DerivSmem& o, float2* wm, int lane, unsigned mask,
+                                             const DerivMe& me, float inv_h, float lim2) {
     float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
-    const DerivMe me{px, py, pz, s_me, bw_me, ts_me, tj_me};
     while (mask) {
         const int j0 = __ffs(mask)-1;
         mask &= mask-1;
         const bool two = mask != 0;
         const int j1 = two ? __ffs(mask)-1 : j0;
         mask &= mask-1;
-        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j0, true, me, ntj, inv_h, lim2, fx0, fy0, fz0, wu0);
-        deriv_term<CUTOFF, MODE>(tabv, tabd, o, wmat, lane, j1, two, me, ntj, inv_h, lim2, fx1, fy1, fz1, wu1);
+        deriv_term<CUTOFF, MODE>(tabv, o, wm, lane, j0, true, me, inv_h, lim2, fx0, fy0, fz0, wu0);
+        deriv_term<CUTOFF, MODE>(tabv, o, wm, lane, j1, two, me, inv_h, lim2, fx1, fy1, fz1, wu1);
+    }
+    return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
+}
+
+// secondary role: column atom `lane` at (px, py, pz) adds up its column of the pair matrix over the rows in `mask`
+__device__ __forceinline__ float4 deriv_column(const DerivSmem& r, const float2* wm, int lane, unsigned mask, float px, float py, float pz) {
+    float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
+    while (mask) {
+        const int a0 = __ffs(mask)-1;
+        mask &= mask-1;
+        const bool two = mask != 0;
+        const int a1 = two ? __ffs(mask)-1 : a0;
+        mask &= mask-1;
+        const float4 r0 = r.p[a0], r1 = r.p[a1];
+        const float2 m0 = wm[a0*WMAT_STRIDE + lane];
+        float2 m1 = wm[a1*WMAT_STRIDE + lane];
+        if (!two) m1 = make_float2(0.f, 0.f);
+        fx0 = fmaf(r0.x-px, m0.x, fx0); fy0 = fmaf(r0.y-py, m0.x, fy0); fz0 = fmaf(r0.z-pz, m0.x, fz0); wu0 += m0.y;
+        fx1 = fmaf(r1.x-px, m1.x, fx1); fy1 = fmaf(r1.y-py, m1.x, fy1); fz1 = fmaf(r1.z-pz, m1.x, fz1); wu1 += m1.y;
     }
     return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
 }
@@ -731,26 +789,26 @@ __device__ __forceinline__ void deriv_load(const DerivArgs& A, int blk, int lane
     const float4 p = A.c.posq[j];
     s.p[lane] = make_float4(p.x, p.y, p.z, A.vsf[j]);
     s.bw[lane] = A.brw[j] - PIFAC*A.kdiel*(p.w*p.w + A.gbacc[j].w*A.born[j])*A.bfp[j];
-    const int tj = A.c.tj[j];
-    s.pk[lane] = make_int2((int) A.c.ts[j]*A.c.ntj*I4_INTERVALS, tj < 0 ? -1 : tj*I4_INTERVALS);
+    s.pk[lane] = pk_pack((int) A.c.ts[j], (int) A.c.tj[j], A.c.ntj);
 }
 
+// Launch shape: pq_shape() on the host picks the warps per CTA that bring the most warps onto an SM (every warp needs
+// DERIV_WARP_SMEM next to the CTA's copy of the spline table)
 template <bool CUTOFF, bool TAB_SMEM>
-__global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
+__global__ void __launch_bounds__(PQ_MAX_THREADS) k_deriv(DerivArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ntab = TAB_SMEM ? A.c.ntables*I4_INTERVALS : 0;
     float4* s_tabv = (float4*) smem_raw;
-    float4* s_tabd = s_tabv + ntab;
     const int nwarp = blockDim.x >> 5;
-    DerivSmem* sm = (DerivSmem*) (s_tabd + ntab);                       // [nwarp][2]
-    float* wmat = (float*) (sm + 2*nwarp) + (threadIdx.x >> 5)*WMAT_STRIDE*TILE;      // [nwarp][32*33] pair force weights
+    DerivSmem* sm = (DerivSmem*) (s_tabv + ntab);                       // [nwarp][2]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* wm = (float2*) (sm + 2*nwarp) + warp*WMAT_STRIDE*TILE;      // [nwarp][32*33] (force weight, column atom's WU share)
     pdl_release();
-    for (int i = threadIdx.x; i < ntab; i += blockDim.x) { s_tabv[i] = A.c.i4v[i]; s_tabd[i] = A.c.i4d[i]; }   // constants: before the wait
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) s_tabv[i] = A.c.i4v[i];      // constants: before the wait
     pdl_acquire();
     __syncthreads();
-    const float4 *tabv, *tabd;
-    if (TAB_SMEM) { tabv = s_tabv; tabd = s_tabd; } else { tabv = A.c.i4v; tabd = A.c.i4d; }
+    const float4* tabv;
+    if (TAB_SMEM) tabv = s_tabv; else tabv = A.c.i4v;
     DerivSmem& R = sm[2*warp];
     DerivSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
@@ -765,31 +823,33 @@ __global__ void __launch_bounds__(DERIV_MAX_THREADS) k_deriv(DerivArgs A) {
         const int toff = A.u.tile_off[u];
         __syncwarp();
         deriv_load(A, ra, lane, R);
+        __syncwarp();
         const int a = ra*TILE+lane;
-        const float px = R.p[lane].x, py = R.p[lane].y, pz = R.p[lane].z, s_a = R.p[lane].w, bw_a = R.bw[lane];
-        const int ts_a = R.pk[lane].x, tj_a = R.pk[lane].y;     // premultiplied table offsets
+        const bool row_heavy = ra < A.c.nhb;
+        DerivMe me;
+        { const float4 pa = R.p[lane]; const int pk = R.pk[lane];
+          me.px = pa.x; me.py = pa.y; me.pz = pa.z; me.s = pa.w; me.bw = R.bw[lane];
+          me.ts = pk >> PK_TS_SHIFT; me.tj = pk & PK_TJ; me.heavy = !(pk & PK_HYD); }
         float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
         while (hits) {
             const int cb = cb0 + __ffs(hits)-1;
             hits &= hits-1;
             const bool diag = cb == ra;
-            __syncwarp();
+            __syncwarp();                                       // the previous tile's column sums have been read
             deriv_load(A, cb, lane, Cc);
             __syncwarp();
             const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
             const unsigned rowmask = mk.x, colmask = mk.y;
-            if (diag) {
-                const float4 r = deriv_role<CUTOFF, 0>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h, lim2);
-                racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
-            } else {
-                const float4 r = deriv_role<CUTOFF, 1>(tabv, tabd, Cc, wmat, lane, rowmask, px, py, pz, s_a, bw_a, ts_a, tj_a, A.c.ntj, A.c.inv_h, lim2);
-                racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
-                __syncwarp();                                   // the weights are read by other lanes
-                const int2 pk = Cc.pk[lane];
+            float4 r;
+            if (diag) r = deriv_role<CUTOFF, 0>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+            else if (row_heavy) r = deriv_role<CUTOFF, 1>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+            else r = deriv_role<CUTOFF, 2>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+            racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
+            if (!diag) {
+                __syncwarp();                                   // the matrix is read by other lanes
                 const float4 pc = Cc.p[lane];
-                const float4 c = deriv_role<CUTOFF, 2>(tabv, tabd, R, wmat, lane, colmask, pc.x, pc.y, pc.z, pc.w, Cc.bw[lane],
-                                                       pk.x, pk.y, A.c.ntj, A.c.inv_h, lim2);
-                if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], c);
+                const float4 cs = deriv_column(R, wm, lane, colmask, pc.x, pc.y, pc.z);
+                if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], cs);
             }
         }
         atomicAdd(&A.dacc[a], racc);
