@@ -851,13 +851,20 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
             launch(h, k_tree_rescan, h->tree_grid, 32*h->tree_warps, h->tree_warps*rescan_work_bytes(h->tree_cap), s, ra);
             end(K_TREE);
         } else {
-        BlockListArgs bl{h->nhb, h->d_bbc.p, h->d_bbh.p, h->rc2_global, h->d_bcount.p, h->d_blist.p, h->d_pq_ctl.p, pq_move2};
-        begin(K_BLIST);
-        launch(h, k_blocklist, (h->nhb+7)/8, 256, 0, s, bl);
-        end(K_BLIST);
+        // Block lists shorten the level-2 SEARCH of a root from all heavy blocks to ~10.  Searches are rare (the candidate lists
+        // are kept between evaluations), and below ~65 k heavy atoms a root scans every block's box in 64 trips or fewer, which
+        // costs k_tree less (+3 % of a search evaluation on HIV-RT) than every evaluation pays for one more kernel in the chain
+        // (4-6 us): the kernel only runs for larger systems.
+        const bool use_blist = h->nhb > BLIST_MIN_BLOCKS;
+        if (use_blist) {
+            BlockListArgs bl{h->nhb, h->d_bbc.p, h->d_bbh.p, h->rc2_global, h->d_bcount.p, h->d_blist.p, h->d_pq_ctl.p, pq_move2};
+            begin(K_BLIST);
+            launch(h, k_blocklist, (h->nhb+7)/8, 256, 0, s, bl);
+            end(K_BLIST);
+        }
         TreeArgs ta{};
         ta.nh = h->nh; ta.nhb = h->nhb; ta.np = h->np;
-        ta.items = h->d_items.p; ta.nitems = (int) h->items.size(); ta.bcount = h->d_bcount.p; ta.blist = h->d_blist.p;
+        ta.items = h->d_items.p; ta.nitems = (int) h->items.size(); ta.bcount = use_blist ? h->d_bcount.p : nullptr; ta.blist = h->d_blist.p;
         ta.item_roots = h->d_item_roots.p;
         ta.posq = h->d_posq.p; ta.orig = h->d_orig.p; ta.l2rec = h->d_l2rec.p; ta.rcbin = h->d_rcbin.p;
         ta.aL = h->d_aL.p; ta.vL = h->d_vL.p; ta.aS = h->d_aS.p; ta.vS = h->d_vS.p; ta.gamma = h->d_gamma.p;

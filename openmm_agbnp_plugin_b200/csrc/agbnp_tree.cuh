@@ -70,6 +70,9 @@ struct __align__(16) NodeGauss {
 static_assert(sizeof(NodeGauss) == 96, "NodeGauss layout");
 
 constexpr int BLIST_MAX = 64;       // neighbor blocks listed per heavy block (more: the root scans all blocks)
+#ifndef BLIST_MIN_BLOCKS
+#define BLIST_MIN_BLOCKS 2048        // systems with fewer heavy blocks skip k_blocklist: their roots scan every block's box when they search
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_blocklist: for every heavy block, the heavy blocks whose bounding box comes within the largest level-2 pair radius
@@ -116,7 +119,7 @@ struct TreeArgs {
     const int2* items;                // [nitems] work items, most expensive first
     const int* item_roots;            // sorted indices of the items' roots
     int nitems;
-    const int* bcount;                // k_blocklist output
+    const int* bcount;                // k_blocklist output, or null: no block lists (every root scans all heavy blocks)
     const unsigned short* blist;
     const float4* posq;
     const int* orig;
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 32*TREE_WARPS : 256, SMEM_WORK ? T
                 int nl = 0;
                 const float rcmaxs = A.rc2maxs[rb];
                 int* mylist = A.l2list + (size_t) r*nbrmax;
-                const int nlist = A.bcount[r >> 5];
+                const int nlist = A.bcount ? A.bcount[r >> 5] : -1;
                 const int nscan = nlist >= 0 ? nlist : A.nhb;
                 for (int b0 = 0; b0 < nscan; b0 += 32) {
                     int b = b0+lane;
