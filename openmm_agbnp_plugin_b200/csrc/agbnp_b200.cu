@@ -598,19 +598,36 @@ void build_pq_units(agbnp_b200* h, std::vector<int2>& out) {
         }
         return std::sqrt(d2);
     };
+    auto tile_cost = [&](int ra, int cb) {
+        const double d = box_dist(ra, cb);
+        const double f = std::min(1.0, std::max(0.0, (lim-d)/1.0 + 0.3));
+        float cost = 0.02f + (float) (f*f)*((ra < h->nhb && cb != ra) ? 2.f : 1.f);
+        if (!(d < 1e30)) cost = 0.02f;                      // a block of padding only
+        return cost;
+    };
+    // Unit size: a unit is closed at `unit_cost` (one near tile of heavy rows costs 2).  Every unit pays a claim and three or
+    // four dependent loads before its first pair, so large systems want larger units -- measured on B200 (r2w): HIV-RT
+    // (41.7 k cost units) k_born 56.2 / 55.6 / 53.9 / 52.1 / 64.7 us at 0.5 / 1 / 2 / 4 / 8, 2clr (12 k) 23.3 / 23.3 / 25.0 /
+    // 33.2 / 43.4 us -- about two and a half units per resident warp of k_born (36 per SM), within [1, 4].
+    float unit_cost = 1.0f;
+    {
+        double total = 0;
+        for (int ra = 0; ra < h->nb; ra++)
+            for (int cb = ra < h->nhb ? ra : 0; cb < h->nhb; cb++) total += tile_cost(ra, cb);
+        unit_cost = (float) std::min(4.0, std::max(1.0, total/(2.5*36.0*h->num_sm*h->cfg.shard_count)));
+        if (const char* e = std::getenv("AGBNP_B200_PQ_UNIT_COST")) unit_cost = (float) std::atof(e);
+    }
     for (int ra = 0; ra < h->nb; ra++) {
         U cur{ra, 0, 0, 0.f};
         for (int cb = ra < h->nhb ? ra : 0; cb < h->nhb; cb++) {
-            const double d = box_dist(ra, cb);
-            double f = std::min(1.0, std::max(0.0, (lim-d)/1.0 + 0.3));
-            float cost = 0.02f + (float) (f*f)*((ra < h->nhb && cb != ra) ? 2.f : 1.f);
-            if (!(d < 1e30)) cost = 0.02f;                  // a block of padding only
+            const float cost = tile_cost(ra, cb);
             if (cur.n == 0) cur.cb0 = cb;
             cur.n++; cur.cost += cost;
-            if (cur.cost >= 1.0f || cur.n == PQ_CHUNK) { us.push_back(cur); cur.n = 0; cur.cost = 0.f; }
+            if (cur.cost >= unit_cost || cur.n == PQ_CHUNK) { us.push_back(cur); cur.n = 0; cur.cost = 0.f; }
         }
         if (cur.n) us.push_back(cur);
     }
+    if (std::getenv("AGBNP_B200_DEBUG_UNITS")) { double ct = 0; for (const U& u : us) ct += u.cost; std::fprintf(stderr, "pq units %zu total cost %.1f unit_cost %.2f nb %d nhb %d\n", us.size(), ct, unit_cost, h->nb, h->nhb); }
     std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
     out.clear();
     for (const U& u : us) out.push_back(make_int2(u.ra, u.cb0 | (u.n << 20)));

@@ -253,6 +253,31 @@ __device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o
     return s0+s1;
 }
 
+// DENSE tiles (at least PQ_DENSE of the 1024 pairs listed; most in-range pairs live in such tiles): the same terms without the
+// mask walk -- every lane visits partner jj = 0..31 in step, so the partner's data is one broadcast load instead of a gather,
+// the matrix is written and read without bank conflicts, and there is no bit-scan per term; a lane's unlisted pairs run as
+// invalid slots (about a fifth of the slots of a dense tile, fewer than the mask walk leaves idle at its pace of the busiest lane)
+constexpr int PQ_DENSE = 512;
+template <bool CUTOFF, bool BOTH>
+__device__ __forceinline__ float born_role_dense(const float4* tabv, const BornSmem& o, float* vm, int lane, unsigned mask, const BornMe& me,
+                                                 float inv_h, float lim2, unsigned& npair) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 2
+    for (int jj = 0; jj < TILE; jj += 2) {
+        const bool v0 = (mask >> jj) & 1u, v1 = (mask >> (jj+1)) & 1u;
+        if (BOTH) { if (!v0) vm[lane*WMAT_STRIDE + jj] = 0.f; if (!v1) vm[lane*WMAT_STRIDE + jj+1] = 0.f; }
+        s0 += born_term<CUTOFF, BOTH>(tabv, o, vm, lane, jj, v0, me, inv_h, lim2, npair);
+        s1 += born_term<CUTOFF, BOTH>(tabv, o, vm, lane, jj+1, v1, me, inv_h, lim2, npair);
+    }
+    return s0+s1;
+}
+__device__ __forceinline__ float born_column_dense(const float* vm, int lane) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int a = 0; a < TILE; a += 2) { s0 += vm[a*WMAT_STRIDE + lane]; s1 += vm[(a+1)*WMAT_STRIDE + lane]; }
+    return s0+s1;
+}
+
 // secondary role: column `lane` of the matrix over the rows in `mask`
 __device__ __forceinline__ float born_column(const float* vm, int lane, unsigned mask) {
     float s0 = 0.f, s1 = 0.f;
@@ -342,11 +367,21 @@ __global__ void __launch_bounds__(PQ_MAX_THREADS) k_born(BornArgs A) {
                 const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
                 rowmask = mk.x; colmask = mk.y;
             }
-            if (diag || !row_heavy) rsum += born_role<CUTOFF, false>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
-            else {
-                rsum += born_role<CUTOFF, true>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
-                __syncwarp();                                // the matrix is read by other lanes
-                const float csum = born_column(vm, lane, colmask);
+            const bool dense = __reduce_add_sync(FULL, __popc(rowmask)) >= PQ_DENSE;
+            if (diag || !row_heavy) {
+                if (dense) rsum += born_role_dense<CUTOFF, false>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
+                else rsum += born_role<CUTOFF, false>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
+            } else {
+                float csum;
+                if (dense) {
+                    rsum += born_role_dense<CUTOFF, true>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
+                    __syncwarp();                            // the matrix is read by other lanes
+                    csum = born_column_dense(vm, lane);
+                } else {
+                    rsum += born_role<CUTOFF, true>(tabv, Cc, vm, lane, rowmask, me, A.c.inv_h, lim2, npair);
+                    __syncwarp();
+                    csum = born_column(vm, lane, colmask);
+                }
                 if (csum != 0.f) atomicAdd(&A.bsum[cb*TILE+lane], csum);
             }
         }
@@ -765,6 +800,35 @@ __device__ __forceinline__ float4 deriv_role(const float4* tabv, const DerivSmem
     return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
 }
 
+// dense tiles (see born_role_dense): partner jj = 0..31 in step, unlisted pairs as invalid slots that store zeros
+template <bool CUTOFF, int MODE>
+__device__ __forceinline__ float4 deriv_role_dense(const float4* tabv, const DerivSmem& o, float2* wm, int lane, unsigned mask,
+                                                   const DerivMe& me, float inv_h, float lim2) {
+    float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
+#pragma unroll 2
+    for (int jj = 0; jj < TILE; jj += 2) {
+        const bool v0 = (mask >> jj) & 1u, v1 = (mask >> (jj+1)) & 1u;
+        if (MODE != 0) {
+            if (!v0) wm[lane*WMAT_STRIDE + jj] = make_float2(0.f, 0.f);
+            if (!v1) wm[lane*WMAT_STRIDE + jj+1] = make_float2(0.f, 0.f);
+        }
+        deriv_term<CUTOFF, MODE>(tabv, o, wm, lane, jj, v0, me, inv_h, lim2, fx0, fy0, fz0, wu0);
+        deriv_term<CUTOFF, MODE>(tabv, o, wm, lane, jj+1, v1, me, inv_h, lim2, fx1, fy1, fz1, wu1);
+    }
+    return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
+}
+__device__ __forceinline__ float4 deriv_column_dense(const DerivSmem& r, const float2* wm, int lane, float px, float py, float pz) {
+    float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
+#pragma unroll 4
+    for (int a = 0; a < TILE; a += 2) {
+        const float4 r0 = r.p[a], r1 = r.p[a+1];
+        const float2 m0 = wm[a*WMAT_STRIDE + lane], m1 = wm[(a+1)*WMAT_STRIDE + lane];
+        fx0 = fmaf(r0.x-px, m0.x, fx0); fy0 = fmaf(r0.y-py, m0.x, fy0); fz0 = fmaf(r0.z-pz, m0.x, fz0); wu0 += m0.y;
+        fx1 = fmaf(r1.x-px, m1.x, fx1); fy1 = fmaf(r1.y-py, m1.x, fy1); fz1 = fmaf(r1.z-pz, m1.x, fz1); wu1 += m1.y;
+    }
+    return make_float4(fx0+fx1, fy0+fy1, fz0+fz1, wu0+wu1);
+}
+
 // secondary role: column atom `lane` at (px, py, pz) adds up its column of the pair matrix over the rows in `mask`
 __device__ __forceinline__ float4 deriv_column(const DerivSmem& r, const float2* wm, int lane, unsigned mask, float px, float py, float pz) {
     float fx0 = 0.f, fy0 = 0.f, fz0 = 0.f, wu0 = 0.f, fx1 = 0.f, fy1 = 0.f, fz1 = 0.f, wu1 = 0.f;
@@ -840,15 +904,22 @@ __global__ void __launch_bounds__(PQ_MAX_THREADS) k_deriv(DerivArgs A) {
             __syncwarp();
             const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
             const unsigned rowmask = mk.x, colmask = mk.y;
+            const bool dense = __reduce_add_sync(FULL, __popc(rowmask)) >= PQ_DENSE;
             float4 r;
-            if (diag) r = deriv_role<CUTOFF, 0>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
-            else if (row_heavy) r = deriv_role<CUTOFF, 1>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
-            else r = deriv_role<CUTOFF, 2>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+            if (dense) {
+                if (diag) r = deriv_role_dense<CUTOFF, 0>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+                else if (row_heavy) r = deriv_role_dense<CUTOFF, 1>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+                else r = deriv_role_dense<CUTOFF, 2>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+            } else {
+                if (diag) r = deriv_role<CUTOFF, 0>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+                else if (row_heavy) r = deriv_role<CUTOFF, 1>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+                else r = deriv_role<CUTOFF, 2>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
+            }
             racc.x += r.x; racc.y += r.y; racc.z += r.z; racc.w += r.w;
             if (!diag) {
                 __syncwarp();                                   // the matrix is read by other lanes
                 const float4 pc = Cc.p[lane];
-                const float4 cs = deriv_column(R, wm, lane, colmask, pc.x, pc.y, pc.z);
+                const float4 cs = dense ? deriv_column_dense(R, wm, lane, pc.x, pc.y, pc.z) : deriv_column(R, wm, lane, colmask, pc.x, pc.y, pc.z);
                 if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], cs);
             }
         }
