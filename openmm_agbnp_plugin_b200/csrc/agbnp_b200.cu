@@ -705,8 +705,22 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
         h->gb_chunk = (int) std::max<long long>(1, std::min<long long>(GB_CHUNK, tiles_total/(4*std::max<long long>(warps, 1))));
     }
     std::vector<int2> units;
-    for (int ra = 0; ra < h->nb; ra++)
-        for (int c = ra; c < h->nb; c += h->gb_chunk) units.push_back(make_int2(ra, c));
+    // (row block, first column block | number of column blocks << 20).  Units are claimed in this order, so the last ones set
+    // the kernel's tail: the final fifth of the tiles goes out in half- and quarter-size units (AGBNP_B200_GB_TAIL=0: all equal)
+    {
+        static const bool taper = !(std::getenv("AGBNP_B200_GB_TAIL") && std::atoi(std::getenv("AGBNP_B200_GB_TAIL")) == 0);
+        const long long tiles_total = (long long) h->nb*(h->nb+1)/2;
+        long long done = 0;
+        for (int ra = 0; ra < h->nb; ra++)
+            for (int c = ra; c < h->nb; ) {
+                int n = h->gb_chunk;
+                if (taper && done*100 >= tiles_total*92) n = std::max(1, h->gb_chunk/4);
+                else if (taper && done*100 >= tiles_total*80) n = std::max(1, h->gb_chunk/2);
+                n = std::min(n, h->nb-c);
+                units.push_back(make_int2(ra, c | (n << 20)));
+                c += n; done += n;
+            }
+    }
     h->nunits = (int) units.size();
     h->d_units.upload(units, s);
     // range-limited pair passes: heavy rows x heavy columns cb >= ra, then hydrogen rows x heavy columns (agbnp_pair.cuh)

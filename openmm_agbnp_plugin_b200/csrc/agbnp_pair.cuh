@@ -257,7 +257,10 @@ __device__ __forceinline__ float born_role(const float4* tabv, const BornSmem& o
 // mask walk -- every lane visits partner jj = 0..31 in step, so the partner's data is one broadcast load instead of a gather,
 // the matrix is written and read without bank conflicts, and there is no bit-scan per term; a lane's unlisted pairs run as
 // invalid slots (about a fifth of the slots of a dense tile, fewer than the mask walk leaves idle at its pace of the busiest lane)
-constexpr int PQ_DENSE = 512;
+#ifndef PQ_DENSE_MIN
+#define PQ_DENSE_MIN 512
+#endif
+constexpr int PQ_DENSE = PQ_DENSE_MIN;
 template <bool CUTOFF, bool BOTH>
 __device__ __forceinline__ float born_role_dense(const float4* tabv, const BornSmem& o, float* vm, int lane, unsigned mask, const BornMe& me,
                                                  float inv_h, float lim2, unsigned& npair) {
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(256) k_born_finish(BornFinishArgs A) {
 struct GBArgs {
     PairCommon c;
     const float4* gbj;          // [3*np] GB atom records in broadcast form {x,x,y,y | z,z,q,q | B,B,ib,ib}
-    const int2* units;          // (row block, first column block): triangular cover in chunks of `chunk` column tiles
+    const int2* units;          // (row block, first column block | column blocks << 20): triangular cover in chunks of up to `chunk` column tiles
     int nunits;
     int chunk;                  // column tiles per unit (<= GB_CHUNK), chosen on the host so that every warp gets several units
     int shard_rank, shard_count;
@@ -618,22 +621,22 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
         if (u >= A.nunits) break;
         const int2 un = A.units[u];
         const int ra = un.x;
-        const int cend = min(un.y+A.chunk, A.c.nb);
+        const int ucol = un.y & 0xfffff, cend = ucol + (un.y >> 20);
         const float4 ca = A.c.bbc[ra], ha = A.c.bbh[ra];
         // column tiles of this unit that take part (cutoff: bounding boxes within range), as a bit mask
         unsigned tiles = 0, fartiles = 0;
         {
             bool hit = false, far = false;
-            if (lane < cend-un.y) {
-                const float bd2 = box_box_dist2(ca, ha, A.c.bbc[un.y+lane], A.c.bbh[un.y+lane]);
+            if (lane < cend-ucol) {
+                const float bd2 = box_box_dist2(ca, ha, A.c.bbc[ucol+lane], A.c.bbh[ucol+lane]);
                 hit = !CUTOFF || bd2 < A.c.cut2;
-                far = bd2 > GB_FAR_FACTOR*A.bmax[ra]*A.bmax[un.y+lane];
+                far = bd2 > GB_FAR_FACTOR*A.bmax[ra]*A.bmax[ucol+lane];
             }
             tiles = __ballot_sync(FULL, hit);
             fartiles = __ballot_sync(FULL, far);
         }
         if (!tiles) continue;
-        const int col0 = un.y;
+        const int col0 = ucol;
         __syncwarp();                                             // the previous unit is done with the stages
         int cur = 0;
         gb_prefetch(A, col0 + __ffs(tiles)-1, lane, stage[0]);
