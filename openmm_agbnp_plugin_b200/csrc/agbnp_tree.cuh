@@ -240,6 +240,18 @@ struct TreeWork {
     }
 };
 
+// per-warp global staging (sweep records, children sums): written once and read once by the same warp within one item.
+// TREE_STAGE_STREAM (off): st.global.cs / ld.global.cs (evict-first), so that the staging churn of the whole grid does not push
+// the persisted TreeStore -- which k_tree_gamma reads 300 us later -- out of L2.  Measured (r2aa): k_tree_gamma 41.1 -> 39.4 us,
+// but k_tree 151.5 -> 156.1 us (its own re-reads then miss more often): not enabled.
+#ifdef TREE_STAGE_STREAM
+#define STAGE_ST(p, v) __stcs((p), (v))
+#define STAGE_LD(p) __ldcs((p))
+#else
+#define STAGE_ST(p, v) (*(p) = (v))
+#define STAGE_LD(p) (*(p))
+#endif
+
 // position of a lane within its segment (lanes with equal key are contiguous) and the largest position in the warp:
 // a segmented scan then needs only the steps d <= maxpos (sibling groups are short: usually 2-3 of the 5 steps), and a
 // lane takes the value d lanes below iff pos >= d
@@ -262,9 +274,9 @@ __device__ __forceinline__ void seg_step(float (&v)[10], bool take, int d) {
 }
 
 __device__ __forceinline__ void hu_store(float4* hu, int node, const float (&v)[10]) {
-    hu[4*node] = make_float4(v[0], v[1], v[2], v[3]);
-    hu[4*node+1] = make_float4(v[4], v[5], v[6], v[7]);
-    hu[4*node+2] = make_float4(v[8], v[9], 0.f, 0.f);
+    STAGE_ST(&hu[4*node], make_float4(v[0], v[1], v[2], v[3]));
+    STAGE_ST(&hu[4*node+1], make_float4(v[4], v[5], v[6], v[7]));
+    STAGE_ST(&hu[4*node+2], make_float4(v[8], v[9], 0.f, 0.f));
 }
 
 // the bottom-up sweep over a finished subtree, both radius sets at once (gaussvol.cpp:400-487): self-volumes and the
@@ -299,10 +311,10 @@ __device__ __forceinline__ void tree_sweep(const TreeWork& W, const float4* swL,
 #pragma unroll
             for (int c = 0; c < 10; c++) v[c] = 0.f;
             if (valid) {
-                const float4 l0 = swL[2*sl], l1 = swL[2*sl+1], s0v = swS[2*sl], s1v = swS[2*sl+1];
+                const float4 l0 = STAGE_LD(&swL[2*sl]), l1 = STAGE_LD(&swL[2*sl+1]), s0v = STAGE_LD(&swS[2*sl]), s1v = STAGE_LD(&swS[2*sl+1]);
                 float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, h2 = h0;
                 const bool has_kids = STORED ? W.ccount[sl] > 0 : ((W.hc[sl >> 5] >> (sl & 31)) & 1u) != 0;
-                if (has_kids) { const float4* hs = hu + 4*(sl+rd_off); h0 = hs[0]; h1 = hs[1]; h2 = hs[2]; }
+                if (has_kids) { const float4* hs = hu + 4*(sl+rd_off); h0 = STAGE_LD(hs); h1 = STAGE_LD(hs+1); h2 = STAGE_LD(hs+2); }
                 int ja;
                 if (STORED) ja = ja_arr[sl];
                 else { const int ia = W.nbr[sl]; ja = ia == 0 ? W.rt[sl] : W.nbi[ia-1]; }     // ia == 0: a root, slot = its index
@@ -690,8 +702,8 @@ __global__ void __launch_bounds__(SMEM_WORK ? 32*TREE_WARPS : 256, SMEM_WORK ? T
                         const double mL = 2.0*df*gvol;                        // -dVdr
                         const float vl = (float) keyv;
                         // dvv1 = V/V_parent feeds the sweeps only: a float division (the FP64 one is 30 instructions on the chain)
-                        swL[2*slot] = make_float4(vl, (float) (sp*gvol + s), v1 > 0 ? (float) gvol/(float) v1 : 0.f, (float) a2/(float) g.aL);
-                        swL[2*slot+1] = make_float4((float) ((x2-x1)*mL), (float) ((y2-y1)*mL), (float) ((z2-z1)*mL), gam);
+                        STAGE_ST(&swL[2*slot], make_float4(vl, (float) (sp*gvol + s), v1 > 0 ? (float) gvol/(float) v1 : 0.f, (float) a2/(float) g.aL));
+                        STAGE_ST(&swL[2*slot+1], make_float4((float) ((x2-x1)*mL), (float) ((y2-y1)*mL), (float) ((z2-z1)*mL), gam));
                         // vdW radii on the same topology (rescan, gaussvol.cpp:261-279)
                         const double ex = x2-u1, ey = y2-q1, ez = z2-r1;
                         double dS, dfS, sS, spS;
@@ -705,8 +717,8 @@ __global__ void __launch_bounds__(SMEM_WORK ? 32*TREE_WARPS : 256, SMEM_WORK ? T
                         W.scv[slot-new_start] = (float) gvol;
                         const double mS = 2.0*dfS*gS;
                         const float vs = (float) (sS*gS);
-                        swS[2*slot] = make_float4(vs, (float) (spS*gS + sS), w1 > 0 ? (float) gS/(float) w1 : 0.f, (float) b2/(float) g.aS);
-                        swS[2*slot+1] = make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam);
+                        STAGE_ST(&swS[2*slot], make_float4(vs, (float) (spS*gS + sS), w1 > 0 ? (float) gS/(float) w1 : 0.f, (float) b2/(float) g.aS));
+                        STAGE_ST(&swS[2*slot+1], make_float4((float) (ex*mS), (float) (ey*mS), (float) (ez*mS), gam));
                         W.parent[slot] = (short) p; W.nbr[slot] = (short) (kn+1);
                         // energies and volumes need no tree accumulation (gaussvol.cpp:425-433 summed over the subtree)
                         if (level > 1 || nparts == 1) {                   // level-2 nodes of a split root: after the sort, when ownership is known

@@ -12,6 +12,6 @@ for w in 2clr 1dwc rnaseh; do python bench.py --md 2000 --workload $w --cutoff 1
 python bench.py --md 1000 > gpurun_out/md_${TAG}_hivrt.json 2> gpurun_out/md_${TAG}_hivrt.err
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:k_(prep|blocklist|tree|born|gb|deriv|finish)" --launch-skip 270 --launch-count 9 -f -o gpurun_out/prof_${TAG}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:k_(prep|blocklist|tree|born|gb|deriv|finish)" --launch-skip 240 --launch-count 8 -f -o gpurun_out/prof_${TAG}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 ncu -i gpurun_out/prof_${TAG}_full.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_full_raw.csv 2>/dev/null
 tail -c 600 gpurun_out/bench_${TAG}.json
