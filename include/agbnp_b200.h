@@ -147,6 +147,15 @@ long long agbnp_b200_launch_count(const agbnp_b200* h);
  * ops/s, out[4] instruction lanes/s of a 14:1 FFMA:MUFU mix.  n_out >= 5. */
 int agbnp_b200_measure_peaks(int device, double* out, int n_out);
 
+/* Host-only diagnostic (no device needed): the radius typing and the natural-cubic-spline I4 tables that agbnp_b200_create
+ * builds for these particles -- what AGBNPI4LookupTable / the Reference kernel's initialize produce
+ * (openmmapi/src/AGBNPUtils.cpp:13-214, platforms/reference/src/ReferenceAGBNPKernels.cpp:96-137).
+ * type_screened[N], type_screener[N] (-1 for hydrogens); dims[3] = {screened types, screener types, nodes per table};
+ * y / y2 (each of capacity `cap` doubles, may be NULL to query dims): knot values and second derivatives,
+ * table (ti, tj) at [(ti*dims[1] + tj)*dims[2] ...].  Knot k sits at k*2.0/(nodes-1) nm. */
+int agbnp_b200_host_i4_tables(int n, const double* radius, const unsigned char* ishydrogen, int* type_screened,
+                              int* type_screener, int* dims, double* y, double* y2, size_t cap);
+
 /* diagnostics / by-products of the last evaluation, copied to host (atom order = caller's order).  `what`: */
 typedef enum {
     AGBNP_B200_GET_SELF_VOLUME_VDW = 0,   /* double[N]  self-volumes, vdW radii (after S3) */

@@ -1567,6 +1567,25 @@ int agbnp_b200_profile_read(agbnp_b200* h, double* ms_sum, int* launches, int ma
     return K_COUNT;
 }
 
+int agbnp_b200_host_i4_tables(int n, const double* radius, const unsigned char* ishydrogen, int* type_screened,
+                              int* type_screener, int* dims, double* y, double* y2, size_t cap) {
+    if (n <= 0 || !radius || !ishydrogen || !dims) return AGBNP_B200_ERR_ARG;
+    const Constants c = Constants::make();
+    I4Tables t;
+    t.build(std::vector<double>(radius, radius+n), std::vector<int>(ishydrogen, ishydrogen+n), c);
+    dims[0] = t.ntypes_screened; dims[1] = t.ntypes_screener; dims[2] = t.nodes;
+    for (int i = 0; i < n; i++) {
+        if (type_screened) type_screened[i] = t.type_screened[i];
+        if (type_screener) type_screener[i] = t.type_screener[i];
+    }
+    if (y || y2) {
+        if (cap < t.y.size()) return AGBNP_B200_ERR_ARG;
+        if (y) std::copy(t.y.begin(), t.y.end(), y);
+        if (y2) std::copy(t.y2.begin(), t.y2.end(), y2);
+    }
+    return AGBNP_B200_OK;
+}
+
 int agbnp_b200_measure_peaks(int device, double* out, int n_out) {
     if (!out || n_out < 5) return AGBNP_B200_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return AGBNP_B200_ERR_CUDA;
