@@ -426,7 +426,12 @@ void alloc_tree_scratch(agbnp_b200* h) {
     alloc_l2_lists(h, h->own_stream);
     if (h->nhp > 0) CK(cudaStreamSynchronize(h->own_stream));
     const size_t per_warp = tree_work_bytes(h->nbrmax, h->tree_cap, h->tree_wcap);
-    const size_t smem_sm = 200*1024;                       // of 227 KB; leaves room for L1
+    // shared memory the tree kernels may fill per SM, of 228 KB (every CTA also pays 1 KB).  Round 1 left 28 KB "for L1";
+    // measured (r2ac): at the capacities a thermal state needs (576, 224, 96) the full budget fits 16 instead of 14 warps of
+    // k_tree (180 -> 167.5 us, HIV-RT MD step 0.517 -> 0.491 ms), and the gamma sweep runs 16 instead of 12 warps at the default
+    // capacities (35.2 -> 32.7 us); k_tree at the default capacities fits 16 warps either way.
+    static const size_t smem_kb = std::getenv("AGBNP_B200_TREE_SMEM_KB") ? (size_t) std::atoi(std::getenv("AGBNP_B200_TREE_SMEM_KB")) : 226;
+    const size_t smem_sm = smem_kb*1024;
     // CTAs of 2 warps (warps never cooperate); 128 registers/thread bound the residency at 16 warps per SM
     h->tree_warps = TREE_WARPS;
     size_t ctas = std::min<size_t>(TREE_SMEM_CTAS, smem_sm/(h->tree_warps*per_warp + 1024));
