@@ -571,6 +571,7 @@ void build_order(agbnp_b200* h, const float* xyz, int stride, cudaStream_t s) {
             open.nroots++; open.cost += (float) c; g_nodes += pred[k]; g_nbr += nbr_k;
         }
         close();
+        // (ordering by predicted nodes instead of the cubic cost changes nothing measurable, r2ag)
         std::stable_sort(its.begin(), its.end(), [](const It& a, const It& b) { return a.cost > b.cost; });
         h->items.clear();
         for (const It& t : its) h->items.push_back(make_int2(t.first, t.nroots | (t.part << 8) | (t.parts << 16)));
@@ -634,6 +635,9 @@ void build_pq_units(agbnp_b200* h, std::vector<int2>& out) {
     }
     if (std::getenv("AGBNP_B200_DEBUG_UNITS")) { double ct = 0; for (const U& u : us) ct += u.cost; std::fprintf(stderr, "pq units %zu total cost %.1f unit_cost %.2f nb %d nhb %d\n", us.size(), ct, unit_cost, h->nb, h->nhb); }
     std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+    // (Tried, r2ag: cutting the units that hold the last 40-60 % of the cost again, at a quarter of the size, because the average
+    // k_born / k_deriv warp is done at 81 / 87 % of its kernel's span.  The warps then finish together -- 92 / 96 % -- but the
+    // extra units cost what the shorter tail gains: k_born 52.6 -> 54.0 us, k_deriv 77.1 -> 76.3 us.)
     out.clear();
     for (const U& u : us) out.push_back(make_int2(u.ra, u.cb0 | (u.n << 20)));
 }
@@ -1848,6 +1852,19 @@ int agbnp_b200_shard_finish(agbnp_b200* h, void* stream, void* d_force, int forc
 }
 
 long long agbnp_b200_launch_count(const agbnp_b200* h) { return h ? h->launches : -1; }
+#ifdef TAIL_DEBUG
+// -DTAIL_DEBUG builds only (tools/tail_probe.py): when did the warps of the persistent kernels finish, relative to their kernel's span?
+int agbnp_b200_debug_tail_reset(void) {
+    unsigned long long z[16][8];
+    for (auto& r : z) { for (auto& v : r) v = 0; r[0] = ~0ull; }
+    cudaDeviceSynchronize();
+    return cudaMemcpyToSymbol(g_tail, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+int agbnp_b200_debug_tail_read(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, g_tail, sizeof(unsigned long long)*16*8) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 namespace {
 // bytes of every exchange buffer; they depend only on the padded atom count, which is fixed at creation

@@ -57,6 +57,21 @@ __device__ __forceinline__ int claim_unit(int* counter, int lane) {
 __device__ __forceinline__ int first_unit() { return (int) (blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5)); }
 __device__ __forceinline__ int next_unit(int* counter, int lane) { return claim_unit(counter, lane) + (int) (gridDim.x*(blockDim.x >> 5)); }
 
+#ifdef TAIL_DEBUG
+// Diagnostic build (tools/build_variant.sh taildbg -DTAIL_DEBUG; tools/tail_probe.py): every warp of a persistent kernel stamps
+// %globaltimer when it enters and leaves its work loop -- the mean leaving time against the kernel's span says how much of the
+// kernel is tail (r2ag: k_gb 98 %, k_tree 89 %, k_deriv 87 %, k_born 81 % on HIV-RT; 58-67 % for the tree and Born kernels of 2clr).
+// per kernel slot k: [0] min start, [1] max end, [2] sum of warp end times, [3] number of warps, [4] sum of squares (unused)
+__device__ unsigned long long g_tail[16][8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t & ((1ull << 40)-1); }
+__device__ __forceinline__ void tail_begin(int k) { if ((threadIdx.x & 31) == 0) atomicMin(&g_tail[k][0], gtimer()); }
+__device__ __forceinline__ void tail_end(int k) {
+    if ((threadIdx.x & 31) == 0) { const unsigned long long t = gtimer(); atomicMax(&g_tail[k][1], t); atomicAdd(&g_tail[k][2], t); atomicAdd(&g_tail[k][3], 1ull); }
+}
+#else
+__device__ __forceinline__ void tail_begin(int) {}
+__device__ __forceinline__ void tail_end(int) {}
+#endif
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 

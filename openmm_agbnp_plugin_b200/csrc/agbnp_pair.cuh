@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(PQ_MAX_THREADS) k_born(BornArgs A) {
     // rebuild the pair masks (all units, this evaluation) or walk the stored ones?  Nothing below writes ctl[0] / ctl[1].
     const bool rebuild = A.u.ctl[0] == 0 || __int_as_float(A.u.ctl[1]) > A.u.move2;
     if (rebuild && blockIdx.x == 0 && threadIdx.x == 0) A.u.ctl[2] = 1;
+    tail_begin(0);
     unsigned npair = 0;
     // units are dealt round-robin to the shards: claim c is this shard's c-th unit (a shard never touches, or pays a claim
     // for, the units of another)
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(PQ_MAX_THREADS) k_born(BornArgs A) {
         }
         if (rsum != 0.f) atomicAdd(&A.bsum[ra*TILE+lane], rsum);
     }
+    tail_end(0);
     unsigned long long np64 = (unsigned long long) warp_sum((double) npair);
     if (lane == 0 && np64) atomicAdd(&A.counters[CT_PQ], np64);
 }
@@ -616,6 +618,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
     GBStage* stage = s_stage[warp];
     double e_acc = 0.0;
     unsigned long long npair = 0, ntile = 0;
+    tail_begin(1);
     for (int c = claim_unit(A.work_counter, lane); ; c = claim_unit(A.work_counter, lane)) {
         const int u = c*A.shard_count + A.shard_rank;             // this shard's c-th unit (round-robin deal)
         if (u >= A.nunits) break;
@@ -713,6 +716,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_MIN_BLOCKS) k_gb(GBArgs A) {
         }
         atomicAdd(&A.gbacc[ra*TILE + li*8 + lj], make_float4(v1[0], v1[1], v1[2], v1[3]));
     }
+    tail_end(1);
     e_acc = warp_sum(e_acc);
     npair = (unsigned long long) warp_sum((double) npair);
     if (lane == 0) {
@@ -879,6 +883,7 @@ __global__ void __launch_bounds__(PQ_MAX_THREADS) k_deriv(DerivArgs A) {
     DerivSmem& R = sm[2*warp];
     DerivSmem& Cc = sm[2*warp+1];
     const float lim2 = CUTOFF ? fminf(A.c.range2, A.c.cut2) : A.c.range2;
+    tail_begin(2);
     for (int c = first_unit(); ; c = next_unit(A.u.work_counter, lane)) {
         const int u = c*A.u.shard_count + A.u.shard_rank;         // this shard's c-th unit (round-robin deal, as in k_born)
         if (u >= A.u.nunits) break;
@@ -928,6 +933,7 @@ __global__ void __launch_bounds__(PQ_MAX_THREADS) k_deriv(DerivArgs A) {
         }
         atomicAdd(&A.dacc[a], racc);
     }
+    tail_end(2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 32*TREE_WARPS : 256, SMEM_WORK ? T
 
     // raw claim -> item: with shards, items are dealt block-cyclically (blocks of 32 in longest-first order)
     const int raw_end = A.shard_count > 1 ? (A.nitems+TILE-1)/TILE*TILE : A.nitems;
+    tail_begin(3);
     for (int raw = first_unit(); ; raw = next_unit(A.work_counter, lane)) {
         int item = raw;
         if (A.shard_count > 1) {
@@ -797,6 +798,7 @@ __global__ void __launch_bounds__(SMEM_WORK ? 32*TREE_WARPS : 256, SMEM_WORK ? T
 
 #undef part
 #undef nparts
+    tail_end(3);
     eL_tot = warp_sum(eL_tot); eS_tot = warp_sum(eS_tot); vsumL = warp_sum(vsumL); vsumS = warp_sum(vsumS);
     m_tot = (unsigned long long) warp_sum((double) m_tot);
     if (lane == 0) {
@@ -1016,6 +1018,7 @@ __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
     short* par = (short*) (gam + A.cap);            // [cap] parent slot
     // r: item index (stored subtrees are per item; not-owned nodes carry zeros)
     const int raw_end = A.shard_count > 1 ? (A.nitems+TILE-1)/TILE*TILE : A.nitems;
+    tail_begin(4);
     for (int raw = claim_unit(A.work_counter, lane); ; raw = claim_unit(A.work_counter, lane)) {
         int r = raw;
         if (A.shard_count > 1) {                    // this shard's raw-th item (the same deal as k_tree)
@@ -1102,6 +1105,7 @@ __global__ void __launch_bounds__(128) k_tree_gamma(GammaArgs A) {
             __syncwarp();
         }
     }
+    tail_end(4);
 }
 
 } // namespace agbnp_b200_impl
