@@ -717,7 +717,7 @@ void upload_static(agbnp_b200* h, cudaStream_t s) {
     // (row block, first column block | number of column blocks << 20).  Units are claimed in this order, so the last ones set
     // the kernel's tail: the final fifth of the tiles goes out in half- and quarter-size units (AGBNP_B200_GB_TAIL=0: all equal)
     {
-        static const bool taper = !(std::getenv("AGBNP_B200_GB_TAIL") && std::atoi(std::getenv("AGBNP_B200_GB_TAIL")) == 0);
+        const bool taper = !(std::getenv("AGBNP_B200_GB_TAIL") && std::atoi(std::getenv("AGBNP_B200_GB_TAIL")) == 0);
         const long long tiles_total = (long long) h->nb*(h->nb+1)/2;
         long long done = 0;
         for (int ra = 0; ra < h->nb; ra++)

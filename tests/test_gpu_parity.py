@@ -447,6 +447,31 @@ def test_pair_mask_reuse_across_moves(method, cutoff):
             assert int(ctx.kernel.get("WORK_COUNTERS")[0]) == len(portlib.neighbor_pairs(pos.astype(np.float32), cutoff))
 
 
+@pytest.mark.parametrize("unit_cost,gb_tail", [("0.3", "1"), ("8.0", "0")])
+def test_work_decomposition_does_not_change_results(monkeypatch, unit_cost, gb_tail):
+    """How the pair passes are cut into work units is a performance device only: single-tile units and units packed to the
+    maximum of eight column blocks (with and without the tapering GB units) must give the oracle's Born radii, W+U, pair
+    count, energy and forces -- both the sparse (mask-walk) and the dense tile paths of k_born / k_deriv are on this path
+    (RNase H has both kinds of tiles), and so are their primary / secondary roles (agbnp_pair.cuh)."""
+    monkeypatch.setenv("AGBNP_B200_PQ_UNIT_COST", unit_cost)
+    monkeypatch.setenv("AGBNP_B200_GB_TAIL", gb_tail)
+    s = load_system("rnaseh")
+    pos = systems.float_rounded(s["pos"])
+    o = portlib.OracleKernel(1, *sys_args(s))
+    e_ref, f_ref = o.execute(pos)
+    ctx, e, f = _gpu(s, pos)
+    assert abs(e - e_ref) <= E_TOL * abs(e_ref)
+    assert relrms(f, f_ref) <= F_TOL
+    assert np.abs(ctx.kernel.get("BORN_RADIUS") / o.get("born_radius") - 1).max() <= 1e-5
+    assert relrms(ctx.kernel.get("DERIV_WU"), o.get("W") + o.get("U")) <= 1e-5
+    wc = ctx.kernel.get("WORK_COUNTERS")
+    ish = np.asarray(s["ishydrogen"]) > 0
+    npad = -(-int((~ish).sum()) // 32) * 32 + -(-int(ish.sum()) // 32) * 32
+    assert int(wc[0]) == npad * (npad - 1) // 2                 # every GB pair of the padded blocks once, whatever the unit sizes
+    assert int(wc[1]) == int(o.counter("P_q"))                  # directed screening pairs: the oracle's count, pair for pair
+    ctx.kernel.close(); o.close()
+
+
 def test_verlet_energy_conservation():
     """The reference's end-to-end check (example/test_agbnp.py:55-64): Verlet steps, total energy every few steps.  With
     AGBNP1 (NoCutoff) as the only force the solute collapses -- there are no bonded or repulsive terms -- and converts
