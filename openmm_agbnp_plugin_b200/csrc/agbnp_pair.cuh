@@ -759,7 +759,9 @@ __device__ __forceinline__ float spline_slope(float4 v, float fr2, float fr15) {
 
 // MODE 0: diagonal tile (both directions of a pair are visited by their own lanes: nothing is stored);
 // MODE 1: off-diagonal tile of a heavy row block (both table rows, the column atom's share is stored);
-// MODE 2: hydrogen row block: the row atoms never descreen, one table row, the column atom's share is stored.
+// MODE 2: hydrogen row block: the row atoms never descreen, one table row, the column atom's share is stored;
+// MODE 3: the roles of a hydrogen-row tile swapped ("me" is the heavy column atom, the partners are hydrogens): the other
+//         table row only; what is stored for the partner is the force weight alone.
 template <bool CUTOFF, int MODE>
 __device__ __forceinline__ void deriv_term(const float4* tabv, const DerivSmem& o, float2* wm, int lane, int jj, bool valid,
                                            const DerivMe& me, float inv_h, float lim2, float& fx, float& fy, float& fz, float& wu) {
@@ -773,12 +775,14 @@ __device__ __forceinline__ void deriv_term(const float4* tabv, const DerivSmem& 
     float fr;
     const int k = spline_interval(d*inv_h, fr);
     const float fr2 = fr+fr, fr15 = 1.5f*fr;
-    // row (ts_me, tj_o): o descreens me (needs heavy(o))
-    const float4 tb = tabv[me.ts + (pk & PK_TJ) + k];
-    const bool okb = in && !(pk & PK_HYD);
-    float w = okb ? me.bw*c.w*spline_slope(tb, fr2, fr15) : 0.f;
-    float vcol = 0.f;
-    if (MODE != 0) vcol = okb ? me.bw*spline_value(tb, fr) : 0.f;
+    float w = 0.f, vcol = 0.f;
+    if (MODE != 3) {
+        // row (ts_me, tj_o): o descreens me (needs heavy(o))
+        const float4 tb = tabv[me.ts + (pk & PK_TJ) + k];
+        const bool okb = in && !(pk & PK_HYD);
+        w = okb ? me.bw*c.w*spline_slope(tb, fr2, fr15) : 0.f;
+        if (MODE != 0) vcol = okb ? me.bw*spline_value(tb, fr) : 0.f;
+    }
     if (MODE != 2) {
         // row (ts_o, tj_me): me descreens o (needs heavy(me))
         const float4 ta = tabv[(pk >> PK_TS_SHIFT) + me.tj + k];
@@ -913,6 +917,21 @@ __global__ void __launch_bounds__(PQ_MAX_THREADS) k_deriv(DerivArgs A) {
             const uint2 mk = A.u.masks[(size_t) (toff + cb-cb0)*TILE + lane];
             const unsigned rowmask = mk.x, colmask = mk.y;
             const bool dense = __reduce_add_sync(FULL, __popc(rowmask)) >= PQ_DENSE;
+            // sparse tiles: a warp walks at the pace of its busiest lane, so the side whose busiest atom has fewer partners plays
+            // the primary role (CPU count on 2clr: 22 % fewer primary trips on sparse tiles; measured k_deriv 76.6 -> 74.4 us)
+            if (!dense && !diag && __reduce_max_sync(FULL, __popc(colmask)) < __reduce_max_sync(FULL, __popc(rowmask))) {
+                DerivMe mc;
+                { const float4 pc = Cc.p[lane]; const int pk = Cc.pk[lane];
+                  mc.px = pc.x; mc.py = pc.y; mc.pz = pc.z; mc.s = pc.w; mc.bw = Cc.bw[lane];
+                  mc.ts = pk >> PK_TS_SHIFT; mc.tj = pk & PK_TJ; mc.heavy = !(pk & PK_HYD); }
+                const float4 cs = row_heavy ? deriv_role<CUTOFF, 1>(tabv, R, wm, lane, colmask, mc, A.c.inv_h, lim2)
+                                            : deriv_role<CUTOFF, 3>(tabv, R, wm, lane, colmask, mc, A.c.inv_h, lim2);
+                if (colmask) atomicAdd(&A.dacc[cb*TILE+lane], cs);
+                __syncwarp();                                   // the matrix is read by other lanes
+                const float4 rs = deriv_column(Cc, wm, lane, rowmask, me.px, me.py, me.pz);
+                racc.x += rs.x; racc.y += rs.y; racc.z += rs.z; racc.w += rs.w;
+                continue;
+            }
             float4 r;
             if (dense) {
                 if (diag) r = deriv_role_dense<CUTOFF, 0>(tabv, Cc, wm, lane, rowmask, me, A.c.inv_h, lim2);
