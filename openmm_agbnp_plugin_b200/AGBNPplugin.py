@@ -141,13 +141,14 @@ class CalcAGBNPForceKernel:
         self.handle = h
         self.n = len(radius)
 
-    def execute(self, context, includeForces=True, includeEnergy=True):
-        """Returns the potential energy (kJ/mol); forces are ADDED to context.forces (Reference-platform convention)."""
+    def execute(self, context, includeForces=True, includeEnergy=True, assign=False):
+        """Returns the potential energy (kJ/mol); forces are ADDED to context.forces (Reference-platform convention), or
+        assigned if the caller says it would zero them first (AGBNP_B200_FORCES_ASSIGN)."""
         L = _lib.lib()
         pos = np.ascontiguousarray(context.positions, dtype=np.float64).reshape(-1)
         e = C.c_double(0.0)
         f = context.forces.reshape(-1)
-        rc = L.agbnp_b200_execute_host(self.handle, _dp(pos), int(includeForces), int(includeEnergy), C.byref(e), _dp(f))
+        rc = L.agbnp_b200_execute_host(self.handle, _dp(pos), (2 if assign else 1) if includeForces else 0, int(includeEnergy), C.byref(e), _dp(f))
         if rc != _lib.OK:
             raise OpenMMException(self._err())
         return e.value
@@ -219,9 +220,11 @@ class Context:
         self.positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
 
     def calcForcesAndEnergy(self, includeForces=True, includeEnergy=True):
-        # AGBNPForceImpl::calcForcesAndEnergy (AGBNPForceImpl.cpp:32-36)
-        self.forces[:] = 0.0
-        self.energy = self.kernel.execute(self, includeForces, includeEnergy)
+        # AGBNPForceImpl::calcForcesAndEnergy (AGBNPForceImpl.cpp:32-36) behind ContextImpl's "zero the forces, then let every
+        # force add its own": with one force in the context that is an assignment
+        if not includeForces:
+            self.forces[:] = 0.0
+        self.energy = self.kernel.execute(self, includeForces, includeEnergy, assign=True)
         return self.energy
 
     def getPotentialEnergy(self):

@@ -1478,7 +1478,7 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
         h->evals_since_sort++; h->total_evals++;
         grow_ahead(h, h->h_ctrl);
         const double t4 = timing ? now() : 0;
-        if (include_forces && forces) add_forces(h->h_force, forces, 3*h->n);
+        if (include_forces && forces) { if (include_forces == AGBNP_B200_FORCES_ASSIGN) set_forces(h->h_force, forces, 3*h->n); else add_forces(h->h_force, forces, 3*h->n); }
         if (energy) *energy = include_energy ? h->h_scal[SC_TOTAL] : 0.0;
         if (timing) {
             const double t5 = now();

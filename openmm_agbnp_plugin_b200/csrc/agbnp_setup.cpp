@@ -307,4 +307,8 @@ AGBNP_CLONES void add_forces(const float* __restrict__ src, double* __restrict__
     for (int i = 0; i < n3; i++) dst[i] += (double) src[i];
 }
 
+AGBNP_CLONES void set_forces(const float* __restrict__ src, double* __restrict__ dst, int n3) {
+    for (int i = 0; i < n3; i++) dst[i] = (double) src[i];
+}
+
 } // namespace agbnp_b200_impl

@@ -74,6 +74,7 @@ void morton_order(const float* xyz /*stride 4 or 3*/, int stride, const std::vec
 // clone next to the baseline one; chosen at load time)
 void pack_positions(const double* pos /*[3n]*/, float* posq /*[4n], w = 0*/, int n);
 void add_forces(const float* src, double* dst /* += */, int n3);
+void set_forces(const float* src, double* dst /* = */, int n3);
 
 } // namespace agbnp_b200_impl
 #endif

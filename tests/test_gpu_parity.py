@@ -221,6 +221,10 @@ def test_execute_accumulates_forces_like_the_reference():
     e2 = ctx.kernel.execute(ctx, True, True)
     assert np.allclose(ctx.forces - 1.0, f, rtol=0, atol=1e-6 * np.abs(f).max())
     assert abs(e2 - e) <= 1e-6 * abs(e)       # float red.global accumulation order varies run to run
+    # AGBNP_B200_FORCES_ASSIGN: what Context.calcForcesAndEnergy uses instead of zeroing the array first
+    ctx.forces[:] = 1.0
+    ctx.kernel.execute(ctx, True, True, assign=True)
+    assert np.allclose(ctx.forces, f, rtol=0, atol=1e-6 * np.abs(f).max())
 
 
 def test_energy_only_evaluation_skips_the_force_kernels():
