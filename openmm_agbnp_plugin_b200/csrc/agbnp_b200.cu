@@ -1039,6 +1039,8 @@ void enqueue(agbnp_b200* h, const float4* d_posq_in, cudaStream_t s, int phase_m
         fa.energy_accum = sink ? sink->d_energy : nullptr;
         fa.io = (h->cur_io && h->io_set) ? h->d_io.p : nullptr;
         fa.energy_f32 = (h->cur_io && h->energy_f32) ? 1 : 0;
+        // the host-buffer call (sink layout 2) reads status and energy from a pinned mirror that k_finish fills itself
+        if (sink && sink->layout == 2) { fa.tail_out = (int*) h->h_tail; fa.tail_words = (int) ((512 + sizeof(int)*CW_COUNT)/sizeof(int)); }
         begin(K_FINISH);
         launch(h, k_finish, (h->np+255)/256, 256, 0, s, fa);
         end(K_FINISH);
@@ -1467,7 +1469,8 @@ int agbnp_b200_execute_host(agbnp_b200* h, const double* pos, int include_forces
             if (include_forces && forces)
                 CK(cudaMemcpyAsync(h->h_force, h->d_force_out.p, sizeof(float)*3*h->n, cudaMemcpyDeviceToHost, s));
             if (timing) t3 = now();
-            const int status = fetch_status(h, s);          // the one synchronisation of the call
+            CK(cudaStreamSynchronize(s));                   // the one synchronisation of the call; k_finish has filled h_tail
+            const int status = h->h_ctrl[CW_STATUS];
             if (status == 0) break;
             h->tree_built = false;
             if (attempt >= 8 || !grow(h, h->h_ctrl)) {

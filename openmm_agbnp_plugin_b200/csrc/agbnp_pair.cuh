@@ -983,6 +983,8 @@ struct FinishArgs {
     double* energy_out;                 // optional device/pinned-mapped slot (=)
     const int* io;                      // particle -> position in the caller's force buffers, or null (see PrepArgs)
     int energy_f32;
+    int* tail_out;                      // host path: pinned mirror of the slab's [scalars | counters | control words] span, written
+    int tail_words;                     // by CTA 0 at the very end (one device->host copy less per call), or null
 };
 
 // sharded evaluations: this shard's status word, as 0/1, into the energy scalars, which the ENERGY exchange sums over the shards
@@ -1020,34 +1022,42 @@ __global__ void __launch_bounds__(256) k_finish(FinishArgs A) {
     if (bad) {
         __syncthreads();                // every thread of CTA 0 has read the status word before thread 0 changes it
         if (k == 0 && !mine) atomicOr(A.status, dead ? ST_PEER_TIMEOUT : ST_PEER_OVERFLOW);
-        return;
+    } else {
+        if (k == 0) {
+            // E1 + E2 (ReferenceAGBNPKernels.cpp:188,233,266) + GB + vdW
+            const double e = (A.scalars[SC_EVOL_L] - A.scalars[SC_EVOL_S])*(double) A.inv_roffset + A.scalars[SC_EGB] + A.scalars[SC_EVDW];
+            A.scalars[SC_TOTAL] = e;
+            if (A.energy_out) *A.energy_out = e;
+            if (A.energy_accum) { if (A.energy_f32) atomicAdd((float*) A.energy_accum, (float) e); else atomicAdd(A.energy_accum, e); }
+        }
+        const int o = k < A.np ? A.orig[k] : -1;
+        if (o >= 0) {
+            // force = -gradient: -(grad_L - grad_S)/roffset
+            const float4 l = A.accL[k], s = A.accS[k];
+            double fx = ((double) s.x - (double) l.x)*(double) A.inv_roffset, fy = ((double) s.y - (double) l.y)*(double) A.inv_roffset,
+                   fz = ((double) s.z - (double) l.z)*(double) A.inv_roffset;
+            if (A.gbacc) {
+                const float4 g = A.gbacc[k], d = A.dacc[k], t = A.gacc[k];
+                fx += A.gb_scale*(double) g.x + (double) d.x + (double) t.x; fy += A.gb_scale*(double) g.y + (double) d.y + (double) t.y;
+                fz += A.gb_scale*(double) g.z + (double) d.z + (double) t.z;
+            }
+            if (A.out_set) { A.out_set[3*o+0] = (float) fx; A.out_set[3*o+1] = (float) fy; A.out_set[3*o+2] = (float) fz; }
+            const int dst = A.io ? A.io[o] : o;
+            if (A.out_f32) { A.out_f32[3*dst+0] += (float) fx; A.out_f32[3*dst+1] += (float) fy; A.out_f32[3*dst+2] += (float) fz; }
+            if (A.out_fixed) {
+                atomicAdd(&A.out_fixed[dst], (unsigned long long) (long long) (fx*FORCE_SCALE));
+                atomicAdd(&A.out_fixed[(size_t) A.padded_n+dst], (unsigned long long) (long long) (fy*FORCE_SCALE));
+                atomicAdd(&A.out_fixed[2*(size_t) A.padded_n+dst], (unsigned long long) (long long) (fz*FORCE_SCALE));
+            }
+        }
     }
-    if (k == 0) {
-        // E1 + E2 (ReferenceAGBNPKernels.cpp:188,233,266) + GB + vdW
-        const double e = (A.scalars[SC_EVOL_L] - A.scalars[SC_EVOL_S])*(double) A.inv_roffset + A.scalars[SC_EGB] + A.scalars[SC_EVDW];
-        A.scalars[SC_TOTAL] = e;
-        if (A.energy_out) *A.energy_out = e;
-        if (A.energy_accum) { if (A.energy_f32) atomicAdd((float*) A.energy_accum, (float) e); else atomicAdd(A.energy_accum, e); }
-    }
-    if (k >= A.np) return;
-    const int o = A.orig[k];
-    if (o < 0) return;
-    // force = -gradient: -(grad_L - grad_S)/roffset
-    const float4 l = A.accL[k], s = A.accS[k];
-    double fx = ((double) s.x - (double) l.x)*(double) A.inv_roffset, fy = ((double) s.y - (double) l.y)*(double) A.inv_roffset,
-           fz = ((double) s.z - (double) l.z)*(double) A.inv_roffset;
-    if (A.gbacc) {
-        const float4 g = A.gbacc[k], d = A.dacc[k], t = A.gacc[k];
-        fx += A.gb_scale*(double) g.x + (double) d.x + (double) t.x; fy += A.gb_scale*(double) g.y + (double) d.y + (double) t.y;
-        fz += A.gb_scale*(double) g.z + (double) d.z + (double) t.z;
-    }
-    if (A.out_set) { A.out_set[3*o+0] = (float) fx; A.out_set[3*o+1] = (float) fy; A.out_set[3*o+2] = (float) fz; }
-    const int dst = A.io ? A.io[o] : o;
-    if (A.out_f32) { A.out_f32[3*dst+0] += (float) fx; A.out_f32[3*dst+1] += (float) fy; A.out_f32[3*dst+2] += (float) fz; }
-    if (A.out_fixed) {
-        atomicAdd(&A.out_fixed[dst], (unsigned long long) (long long) (fx*FORCE_SCALE));
-        atomicAdd(&A.out_fixed[(size_t) A.padded_n+dst], (unsigned long long) (long long) (fy*FORCE_SCALE));
-        atomicAdd(&A.out_fixed[2*(size_t) A.padded_n+dst], (unsigned long long) (long long) (fz*FORCE_SCALE));
+    if (A.tail_out && blockIdx.x == 0) {
+        // host path: the evaluation's scalars, counters and control words (status, high-water marks) go straight to the pinned
+        // mirror the host reads after its one synchronisation -- everything in them is final: the earlier kernels have
+        // completed, and thread 0 of this CTA wrote the total energy / the peer bits of the status word above
+        __syncthreads();
+        const volatile int* src = (const volatile int*) A.scalars;
+        for (int i = threadIdx.x; i < A.tail_words; i += blockDim.x) A.tail_out[i] = src[i];
     }
 }
 
